@@ -1,0 +1,7 @@
+"""maxdecoy -- host side of the B200-native MaxDecoy identification hot path."""
+from . import _abi
+from ._abi import ALPHABET, DECOY_EXHAUSTIVE, DECOY_PERMUTE_TARGET, DECOY_REFERENCE_RANDOM
+from .api import Engine, MaxDecoyError, Modification, SearchParams, Spectra, load, mass, pack_proteins
+
+__all__ = ["Engine", "MaxDecoyError", "Modification", "SearchParams", "Spectra", "load", "mass", "pack_proteins",
+           "ALPHABET", "DECOY_REFERENCE_RANDOM", "DECOY_EXHAUSTIVE", "DECOY_PERMUTE_TARGET", "_abi"]
