@@ -1,0 +1,400 @@
+// api.cu -- the C ABI of include/maxdecoy.h on top of the CUDA subsystems (digest / index / decoy / score).
+#include <cctype>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "cubx.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(md_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+// run `body`, translating MdError / std exceptions into status codes
+template <class F>
+int guarded(md_ctx* ctx, F body) {
+  try {
+    if (ctx) MD_CUDA(cudaSetDevice(ctx->device));
+    body();
+    return MD_OK;
+  } catch (const MdError& e) {
+    return fail(ctx, e.code, e.msg);
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, MD_ERR_NOMEM, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(ctx, MD_ERR_INVALID, e.what());
+  }
+}
+
+void host_precursor_window(double mz, uint32_t z, int64_t lppm, int64_t uppm, int64_t* P, int64_t* lo, int64_t* hi) {
+  // tasks/identification.rs:203-211; every product/sum rounded on its own (volatile blocks contraction)
+  const double H = 1.007276;
+  volatile double zc = (double)(uint8_t)z;
+  volatile double q = mz / 1000000.0;
+  volatile double tl = q * (double)lppm;
+  volatile double tu = q * (double)uppm;
+  volatile double b = H * zc;
+  volatile double a = mz * zc;
+  volatile double d0 = a - b;
+  *P = (int64_t)(d0 * 1000000.0);
+  volatile double ml = mz - tl; volatile double al = ml * zc; volatile double dl = al - b;
+  *lo = (int64_t)(dl * 1000000.0);
+  volatile double mu = mz + tu; volatile double au = mu * zc; volatile double du = au - b;
+  *hi = (int64_t)(du * 1000000.0);
+}
+
+template <class T>
+T* host_copy(md_ctx* ctx, const T* dev, size_t n) {
+  T* h = (T*)malloc((n ? n : 1) * sizeof(T));
+  MD_REQUIRE(h != nullptr, MD_ERR_NOMEM, "out of host memory");
+  if (n) MD_CUDA(cudaMemcpyAsync(h, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  return h;
+}
+
+void validate_params(const md_search_params* p) {
+  MD_REQUIRE(p->decoy_mode >= 0 && p->decoy_mode <= 2, MD_ERR_INVALID, "md_identify: unknown decoy mode");
+  const int64_t w = (int64_t)llround(p->fragment_tolerance * 1000000.0);
+  MD_REQUIRE(w >= 100 && w <= 2000000, MD_ERR_INVALID, "md_identify: fragment_tolerance must be in [0.0001, 2] Da");
+  MD_REQUIRE(p->top_k <= 1024, MD_ERR_INVALID, "md_identify: top_k > 1024");
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// the identification of one batch of spectra that already sits in device memory
+void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, md_psm* psm_dev, md_identify_stats* st,
+                    uint32_t id_base) {
+  cudaStream_t s = ctx->stream;
+  MD_CUDA(cudaEventRecord(ctx->ev[0], s));
+  precursors_dev(ctx, S, p, id_base);
+  const uint64_t n_targets = index_candidates_dev(ctx, S.n);
+  MD_CUDA(cudaEventRecord(ctx->ev[1], s));
+  decoys_generate_dev(ctx, S.n, p.n_decoys, p.decoy_mode, p.seed);
+  MD_CUDA(cudaEventRecord(ctx->ev[2], s));
+  score_run_dev(ctx, S, n_peaks, p, p.n_decoys, psm_dev);
+  MD_CUDA(cudaEventRecord(ctx->ev[3], s));
+  MD_CUDA(cudaStreamSynchronize(s));
+  if (st) {
+    st->n_spectra += S.n; st->n_targets += n_targets;
+    if (p.n_decoys && S.n) {
+      std::vector<uint32_t> cnt(S.n);
+      MD_CUDA(cudaMemcpy(cnt.data(), ctx->ws.dec_count.p, S.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (uint32_t c : cnt) { st->n_decoys += c; if (c < p.n_decoys) st->n_less_decoys++; }
+    }
+    st->ms_lookup += elapsed(ctx->ev[0], ctx->ev[1]); st->ms_decoys += elapsed(ctx->ev[1], ctx->ev[2]);
+    st->ms_score += elapsed(ctx->ev[2], ctx->ev[3]); st->ms_total += elapsed(ctx->ev[0], ctx->ev[3]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* md_backend_name(void) { return "cuda-sm100a"; }
+
+int md_create(const md_config* cfg, md_ctx** out) {
+  if (!out) return fail(nullptr, MD_ERR_INVALID, "md_create: out is NULL");
+  *out = nullptr;
+  md_ctx* c = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      return fail(nullptr, MD_ERR_DEVICE, std::string("md_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    c = new md_ctx();
+    c->device = cfg ? cfg->device : 0;
+    MD_REQUIRE(c->device >= 0 && c->device < ndev, MD_ERR_INVALID, "md_create: device ordinal out of range");
+    MD_CUDA(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    MD_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    MD_REQUIRE(prop.major >= 10, MD_ERR_DEVICE, "md_create: this library is built for sm_100a (Blackwell B200) only");
+    c->n_sm = prop.multiProcessorCount;
+    MD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) MD_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return MD_OK;
+  } catch (const MdError& e) {
+    delete c;
+    return fail(nullptr, e.code, e.msg);
+  }
+}
+
+void md_destroy(md_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  cudaStream_t s = ctx->stream;
+  delete ctx;  // frees the device buffers
+  if (s) cudaStreamDestroy(s);
+}
+
+const char* md_last_error(const md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+void md_free(void* p) { free(p); }
+int md_sync(md_ctx* ctx) {
+  if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_sync: null ctx");
+  return guarded(ctx, [&] { MD_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+int64_t md_residue_mass(uint8_t c) { return kResidueMassByCode[md_code_of(c)]; }
+int64_t md_sequence_weight(const uint8_t* seq, uint32_t len) {
+  int64_t w = MD_WATER_UDA;
+  for (uint32_t i = 0; i < len; i++) w += kResidueMassByCode[md_code_of(seq[i])];
+  return w;
+}
+int md_precursor_window(double mz, uint32_t charge, int64_t lppm, int64_t uppm, int64_t* P, int64_t* lo, int64_t* hi) {
+  if (!P || !lo || !hi || charge == 0 || charge > 255) return fail(nullptr, MD_ERR_INVALID, "md_precursor_window: bad argument");
+  host_precursor_window(mz, charge, lppm, uppm, P, lo, hi);
+  return MD_OK;
+}
+
+int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, uint32_t max_var) {
+  if (!ctx || (n && !mods)) return fail(ctx, MD_ERR_INVALID, "md_set_modifications: null argument");
+  return guarded(ctx, [&] {
+    MD_REQUIRE(max_var <= 255, MD_ERR_INVALID, "md_set_modifications: max_variable_mods > 255 (u8 in the reference)");
+    ModTables M;
+    memset(&M, 0, sizeof(M));
+    for (int c = 0; c < MD_NCODES; c++) M.mass[c] = kResidueMassByCode[c];
+    M.nvar = max_var; M.var_simple_code = -1;
+    for (uint32_t i = 0; i < n; i++) {
+      uint8_t pos = (uint8_t)toupper(mods[i].position);
+      MD_REQUIRE(pos != 'N' && pos != 'C', MD_ERR_UNSUPPORTED, "terminal modifications (position N/C) are outside the hot path");
+      MD_REQUIRE(pos == 'A', MD_ERR_INVALID, "modification position must be A, N or C");
+      uint8_t aa = (uint8_t)toupper(mods[i].amino_acid);
+      uint32_t code = md_code_of(aa);
+      MD_REQUIRE(md_alpha_of_code(code) >= 0, MD_ERR_INVALID, "modification on a letter without a <x>_count column (alphabet " MD_ALPHABET ")");
+      if (mods[i].is_fix) { M.has_fix[code] = 1; M.fix[code] = mods[i].mono_mass; }
+      else { M.has_var[code] = 1; M.var[code] = mods[i].mono_mass; }
+    }
+    // sorted modifiable letters (identification.rs:173-178): ascending by character
+    int n_var_letters = 0, var_code = -1;
+    for (int ch = 'A'; ch <= 'Z'; ch++) {
+      uint32_t code = md_code_of((uint8_t)ch);
+      if (!M.has_fix[code] && !M.has_var[code]) continue;
+      int64_t merged = M.has_var[code] ? M.var[code] : M.fix[code];
+      MD_REQUIRE(M.mass[code] + merged > 0, MD_ERR_INVALID, "modified residue mass must be positive");
+      MD_REQUIRE(M.mass[code] + (M.has_fix[code] ? M.fix[code] : 0) > 0, MD_ERR_INVALID, "modified residue mass must be positive");
+      MD_REQUIRE(M.mass[code] + M.fix[code] + M.var[code] < (1ll << 40), MD_ERR_INVALID, "modification mass too large");
+      int k = M.n_letters++;
+      M.letter_alpha[k] = md_alpha_of_code(code); M.letter_delta[k] = merged; M.letter_mass[k] = M.mass[code] + merged;
+      if (M.has_var[code]) { n_var_letters++; var_code = (int)code; }
+    }
+    if (n_var_letters == 1 && !M.has_fix[var_code]) M.var_simple_code = var_code;
+    ctx->mods = M; ctx->mods_set = true; ctx->index.ready = false;
+  });
+}
+
+int md_substitution_map(md_ctx* ctx, int64_t* out) {
+  if (!ctx || !out) return fail(ctx, MD_ERR_INVALID, "md_substitution_map: null argument");
+  ModTables M = ctx->mods;
+  if (!ctx->mods_set) { memset(&M, 0, sizeof(M)); for (int c = 0; c < MD_NCODES; c++) M.mass[c] = kResidueMassByCode[c]; }
+  const char* alpha = MD_ALPHABET;
+  int64_t mp[MD_ALPHABET_SIZE];
+  for (int a = 0; a < MD_ALPHABET_SIZE; a++) { uint32_t c = md_code_of((uint8_t)alpha[a]); mp[a] = M.mass[c] + (M.has_fix[c] ? M.fix[c] : 0); }
+  for (int a = 0; a < MD_ALPHABET_SIZE; a++) for (int b = 0; b < MD_ALPHABET_SIZE; b++) out[a * MD_ALPHABET_SIZE + b] = mp[b] - mp[a];
+  return MD_OK;
+}
+
+int md_digest(md_ctx* ctx, const uint8_t* residues, const uint64_t* off, uint32_t n_prot, const md_digest_params* p, uint64_t* n_out) {
+  if (!ctx || !p || (n_prot && (!residues || !off))) return fail(ctx, MD_ERR_INVALID, "md_digest: null argument");
+  return guarded(ctx, [&] {
+    ctx->launches = 0; ctx->cub_calls = 0;
+    digest_run(ctx, residues, off, n_prot, *p);
+    if (n_out) *n_out = ctx->peps.n;
+  });
+}
+
+int md_peptides_export(md_ctx* ctx, md_peptide_table* out) {
+  if (!ctx || !out) return fail(ctx, MD_ERR_INVALID, "md_peptides_export: null argument");
+  return guarded(ctx, [&] { digest_export(ctx, out); });
+}
+void md_peptide_table_free(md_peptide_table* t) {
+  if (!t) return;
+  free(t->seq); free(t->seq_off); free(t->missed_cleavages); free(t->weight); free(t->counts); free(t->assoc_off); free(t->assoc_protein);
+  memset(t, 0, sizeof(*t));
+}
+
+int md_index_build(md_ctx* ctx) {
+  if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_index_build: null ctx");
+  return guarded(ctx, [&] { ctx->launches = 0; ctx->cub_calls = 0; index_build_run(ctx); });
+}
+
+int md_index_stats_get(md_ctx* ctx, md_index_stats* out) {
+  if (!ctx || !out) return fail(ctx, MD_ERR_INVALID, "md_index_stats_get: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_index_stats_get: md_index_build first");
+  memset(out, 0, sizeof(*out));
+  const MassIndex& X = ctx->index; const PeptideStore& P = ctx->peps;
+  out->n_peptides = X.n; out->seq_bytes = P.seq_bytes; out->min_key = X.min_key; out->max_key = X.max_key;
+  out->device_bytes = X.key.bytes() + X.pep.bytes() + X.wfix.bytes() + X.varpos.bytes() + X.desc.bytes() + X.rows.bytes() + P.seq.bytes() + P.seq_off.bytes() +
+                      P.len.bytes() + P.mc.bytes() + P.weight.bytes() + P.counts.bytes() + P.hash.bytes() + P.assoc_off.bytes() + P.assoc_protein.bytes() +
+                      P.ht_key.bytes() + P.ht_val.bytes();
+  return MD_OK;
+}
+
+int md_window_search(md_ctx* ctx, const int64_t* lo, const int64_t* hi, uint32_t n, uint64_t* begin, uint64_t* end) {
+  if (!ctx || (n && (!lo || !hi || !begin || !end))) return fail(ctx, MD_ERR_INVALID, "md_window_search: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_window_search: md_index_build first");
+  return guarded(ctx, [&] {
+    if (!n) return;
+    std::vector<md_precursor> pr(n);
+    for (uint32_t i = 0; i < n; i++) { pr[i].mass = 0; pr[i].lo = lo[i]; pr[i].hi = hi[i]; pr[i].charge = 1; pr[i].spectrum_id = i; }
+    IdentifyWorkspace& W = ctx->ws;
+    W.prec.need(n); W.rbegin.need(n); W.rend.need(n);
+    MD_CUDA(cudaMemcpyAsync(W.prec.p, pr.data(), n * sizeof(md_precursor), cudaMemcpyHostToDevice, ctx->stream));
+    index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
+    MD_CUDA(cudaMemcpyAsync(begin, W.rbegin.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaMemcpyAsync(end, W.rend.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int md_index_export(md_ctx* ctx, uint64_t begin, uint64_t count, uint64_t* pid, int64_t* key) {
+  if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_index_export: null ctx");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_index_export: md_index_build first");
+  if (begin + count > ctx->index.n) return fail(ctx, MD_ERR_INVALID, "md_index_export: range out of bounds");
+  return guarded(ctx, [&] {
+    if (!count) return;
+    if (key) MD_CUDA(cudaMemcpyAsync(key, ctx->index.key.p + begin, count * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> pep(count);
+    MD_CUDA(cudaMemcpyAsync(pep.data(), ctx->index.pep.p + begin, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pid) for (uint64_t i = 0; i < count; i++) pid[i] = (uint64_t)pep[i] + 1;
+  });
+}
+
+int md_candidates(md_ctx* ctx, const md_precursor* pr, uint32_t n, md_candidate_table* out) {
+  if (!ctx || !out || (n && !pr)) return fail(ctx, MD_ERR_INVALID, "md_candidates: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_candidates: md_index_build first");
+  return guarded(ctx, [&] {
+    memset(out, 0, sizeof(*out));
+    IdentifyWorkspace& W = ctx->ws;
+    W.prec.need(n + 1);
+    if (n) MD_CUDA(cudaMemcpyAsync(W.prec.p, pr, n * sizeof(md_precursor), cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t total = index_candidates_dev(ctx, n);
+    out->n_spectra = n; out->n = total;
+    if (n) out->off = host_copy(ctx, W.cand_off.p, n + 1);
+    else { out->off = (uint64_t*)calloc(1, sizeof(uint64_t)); }
+    out->var_mask = host_copy(ctx, W.cand_mask.p, total);
+    out->mod_weight = host_copy(ctx, W.cand_w.p, total);
+    uint32_t* pep = host_copy(ctx, W.cand_pep.p, total);
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->peptide_id = (uint64_t*)malloc((total + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < total; i++) out->peptide_id[i] = (uint64_t)pep[i] + 1;
+    free(pep);
+  });
+}
+void md_candidate_table_free(md_candidate_table* t) {
+  if (!t) return;
+  free(t->off); free(t->peptide_id); free(t->var_mask); free(t->mod_weight);
+  memset(t, 0, sizeof(*t));
+}
+
+int md_generate_decoys(md_ctx* ctx, const md_precursor* pr, uint32_t n_spec, uint32_t n_per, int mode, uint64_t seed, md_decoy_table* out) {
+  if (!ctx || !out || (n_spec && !pr)) return fail(ctx, MD_ERR_INVALID, "md_generate_decoys: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_generate_decoys: md_index_build first");
+  if (mode < 0 || mode > 2) return fail(ctx, MD_ERR_INVALID, "md_generate_decoys: unknown mode");
+  return guarded(ctx, [&] {
+    IdentifyWorkspace& W = ctx->ws;
+    ctx->launches = 0; ctx->cub_calls = 0;
+    W.prec.need(n_spec + 1);
+    if (n_spec) MD_CUDA(cudaMemcpyAsync(W.prec.p, pr, n_spec * sizeof(md_precursor), cudaMemcpyHostToDevice, ctx->stream));
+    if (mode == MD_DECOY_PERMUTE_TARGET) index_candidates_dev(ctx, n_spec);
+    decoys_generate_dev(ctx, n_spec, n_per, mode, seed);
+    decoys_export(ctx, n_spec, n_per, out);
+  });
+}
+void md_decoy_table_free(md_decoy_table* t) {
+  if (!t) return;
+  free(t->off); free(t->seq); free(t->seq_off); free(t->var_mask); free(t->weight); free(t->mod_weight); free(t->attempt);
+  memset(t, 0, sizeof(*t));
+}
+
+int md_identify_device(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_psm* psms_dev, md_identify_stats* stats) {
+  if (!ctx || !S || !p || (S->n && p->top_k && !psms_dev)) return fail(ctx, MD_ERR_INVALID, "md_identify_device: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_identify_device: md_index_build first");
+  return guarded(ctx, [&] {
+    validate_params(p);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    ctx->launches = 0; ctx->cub_calls = 0; ctx->last.have = false;
+    if (!S->n) return;
+    uint64_t n_peaks = 0;
+    MD_CUDA(cudaMemcpy(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    SpectraDev D{S->n, S->precursor_mz, S->charge, S->spectrum_id, S->peak_off, S->peak_mz, S->peak_intensity};
+    identify_batch(ctx, D, n_peaks, *p, psms_dev, stats, 0);
+    if (stats) stats->n_kernel_launches = ctx->launches;
+  });
+}
+
+int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_psm* psms, md_identify_stats* stats, int64_t** all_scores, uint64_t** all_off) {
+  if (!ctx || !S || !p || (S->n && p->top_k && !psms)) return fail(ctx, MD_ERR_INVALID, "md_identify: null argument");
+  if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_identify: md_index_build first");
+  if (S->n && (!S->precursor_mz || !S->charge || !S->peak_off)) return fail(ctx, MD_ERR_INVALID, "spectra: null array");
+  return guarded(ctx, [&] {
+    validate_params(p);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (all_scores) *all_scores = nullptr;
+    if (all_off) *all_off = nullptr;
+    ctx->launches = 0; ctx->cub_calls = 0; ctx->last.have = false;
+    const uint32_t n = S->n;
+    for (uint32_t s = 0; s < n; s++) {
+      MD_REQUIRE(S->peak_off[s + 1] >= S->peak_off[s], MD_ERR_INVALID, "spectra: peak_off not monotone");
+      MD_REQUIRE(S->charge[s] != 0, MD_ERR_INVALID, "spectra: charge 0");
+    }
+    if (!n) { if (all_scores && all_off) { *all_scores = (int64_t*)calloc(1, 8); *all_off = (uint64_t*)calloc(1, 8); } return; }
+    IdentifyWorkspace& W = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const uint64_t np = S->peak_off[n] - S->peak_off[0];
+    MD_REQUIRE(S->peak_off[0] == 0, MD_ERR_INVALID, "spectra: peak_off[0] must be 0");
+    W.pmz.need(n); W.charge.need(n); W.sid.need(n); W.peak_off.need(n + 1); W.peak_mz.need(np + 1); W.peak_int.need(np + 1);
+    W.psm.need((size_t)n * p->top_k + 1);
+    MD_CUDA(cudaMemcpyAsync(W.pmz.p, S->precursor_mz, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    MD_CUDA(cudaMemcpyAsync(W.charge.p, S->charge, n, cudaMemcpyHostToDevice, st));
+    if (S->spectrum_id) MD_CUDA(cudaMemcpyAsync(W.sid.p, S->spectrum_id, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MD_CUDA(cudaMemcpyAsync(W.peak_off.p, S->peak_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (np) {
+      MD_CUDA(cudaMemcpyAsync(W.peak_mz.p, S->peak_mz, np * sizeof(double), cudaMemcpyHostToDevice, st));
+      MD_CUDA(cudaMemcpyAsync(W.peak_int.p, S->peak_intensity, np * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    SpectraDev D{n, W.pmz.p, W.charge.p, S->spectrum_id ? W.sid.p : nullptr, W.peak_off.p, W.peak_mz.p, W.peak_int.p};
+    identify_batch(ctx, D, np, *p, W.psm.p, stats, 0);
+    if (p->top_k) MD_CUDA(cudaMemcpyAsync(psms, W.psm.p, (size_t)n * p->top_k * sizeof(md_psm), cudaMemcpyDeviceToHost, st));
+    MD_CUDA(cudaStreamSynchronize(st));
+    if (stats) stats->n_kernel_launches = ctx->launches;
+    if (all_scores && all_off) {
+      std::vector<uint64_t> coff(n + 1); std::vector<uint32_t> dcnt(n, 0);
+      MD_CUDA(cudaMemcpy(coff.data(), W.cand_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      if (p->n_decoys) MD_CUDA(cudaMemcpy(dcnt.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      std::vector<int64_t> ts(coff[n] + 1), ds((size_t)n * p->n_decoys + 1);
+      if (coff[n]) MD_CUDA(cudaMemcpy(ts.data(), W.tscore.p, coff[n] * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      if ((size_t)n * p->n_decoys) MD_CUDA(cudaMemcpy(ds.data(), W.dscore.p, (size_t)n * p->n_decoys * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      uint64_t total = coff[n];
+      for (uint32_t s = 0; s < n; s++) total += dcnt[s];
+      int64_t* flat = (int64_t*)malloc((total + 1) * sizeof(int64_t)); uint64_t* off = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
+      uint64_t k = 0; off[0] = 0;
+      for (uint32_t s = 0; s < n; s++) {
+        for (uint64_t c = coff[s]; c < coff[s + 1]; c++) flat[k++] = ts[c];
+        for (uint32_t j = 0; j < dcnt[s]; j++) flat[k++] = ds[(size_t)s * p->n_decoys + j];
+        off[s + 1] = k;
+      }
+      *all_scores = flat; *all_off = off;
+    }
+    if (p->keep_decoys) {
+      LastDecoys& L = ctx->last;
+      L.n_spectra = n; L.n_per = p->n_decoys; L.have = true;
+    }
+  });
+}
+
+int md_last_decoys_export(md_ctx* ctx, md_decoy_table* out) {
+  if (!ctx || !out) return fail(ctx, MD_ERR_INVALID, "md_last_decoys_export: null argument");
+  if (!ctx->last.have) return fail(ctx, MD_ERR_STATE, "md_last_decoys_export: no identify call with keep_decoys");
+  return guarded(ctx, [&] { decoys_export(ctx, ctx->last.n_spectra, ctx->last.n_per, out); });
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// ctx.h -- the per-device context: everything that stays resident in HBM between calls.
+#pragma once
+#include "common.cuh"
+
+// Resident peptide table (rows of `peptides`, db/schema.sql:14-43), canonical order.
+struct PeptideStore {
+  bool ready = false;
+  uint64_t n = 0;          // unique peptides
+  uint64_t seq_bytes = 0;
+  uint64_t n_assoc = 0;
+  DevBuf<uint8_t> seq;     // generalized ASCII sequences, concatenated
+  DevBuf<uint32_t> seq_off;// n+1
+  DevBuf<uint8_t> len;     // n
+  DevBuf<uint8_t> mc;      // n, min over occurrences
+  DevBuf<int64_t> weight;  // n
+  DevBuf<int16_t> counts;  // n*21
+  DevBuf<uint64_t> hash;   // n
+  DevBuf<uint32_t> assoc_off;     // n+1
+  DevBuf<uint32_t> assoc_protein; // n_assoc
+  // membership table for Decoy::is_peptide (decoy.rs:49-60): open addressing on hash64
+  DevBuf<uint64_t> ht_key; // 0 = empty
+  DevBuf<uint32_t> ht_val; // peptide ordinal
+  uint32_t ht_mask = 0;
+};
+
+// Mass-sorted index (replaces `weight BETWEEN ... AND x_count = ...`, identification.rs:24,180-188)
+struct MassIndex {
+  bool ready = false;
+  uint64_t n = 0;
+  DevBuf<int64_t> key;      // W*, ascending
+  DevBuf<uint32_t> pep;     // peptide ordinal
+  DevBuf<int64_t> wfix;     // weight incl. fixed mods
+  DevBuf<uint64_t> varpos;  // positions whose letter has a variable modification
+  DevBuf<uint64_t> desc;    // score-row descriptor: row offset/16 | len << 40
+  DevBuf<uint8_t> rows;     // residue codes, 16-byte padded rows, index order
+  uint64_t row_bytes = 0;
+  int64_t min_key = 0, max_key = 0;
+};
+
+struct IdentifyWorkspace {
+  // spectra staged on device by the host-buffer entry point
+  DevBuf<double> pmz; DevBuf<uint8_t> charge; DevBuf<uint32_t> sid; DevBuf<uint64_t> peak_off;
+  DevBuf<double> peak_mz; DevBuf<float> peak_int;
+  DevBuf<md_psm> psm;
+  // per spectrum
+  DevBuf<md_precursor> prec;
+  DevBuf<uint64_t> rbegin, rend;     // index range
+  DevBuf<uint64_t> flat_off;         // prefix of range sizes (n+1)
+  DevBuf<uint64_t> cand_off;         // CSR of accepted targets (n+1)
+  // per index entry in the flattened ranges
+  DevBuf<uint8_t> flag; DevBuf<uint64_t> emask; DevBuf<int64_t> ew; DevBuf<uint64_t> epos;
+  // accepted targets
+  DevBuf<uint64_t> cand_desc; DevBuf<uint64_t> cand_mask; DevBuf<int64_t> cand_w; DevBuf<uint32_t> cand_pep;
+  // decoy attempts (one slot per attempt of the current round) and accepted decoys (n_per slots per spectrum)
+  DevBuf<uint8_t> att_rows; DevBuf<uint8_t> att_len; DevBuf<uint64_t> att_mask; DevBuf<int64_t> att_w; DevBuf<uint64_t> att_hash;
+  DevBuf<uint8_t> dec_rows; DevBuf<uint8_t> dec_len; DevBuf<uint64_t> dec_mask; DevBuf<int64_t> dec_w; DevBuf<uint64_t> dec_hash;
+  DevBuf<uint32_t> dec_attempt; DevBuf<uint32_t> dec_count; DevBuf<uint32_t> att_base; DevBuf<uint32_t> att_limit;
+  DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters;
+  // binned spectra
+  DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
+  // scores
+  DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
+  DevBuf<uint8_t> cub_tmp;
+  // exhaustive mode
+  DevBuf<int32_t> ex_comp; DevBuf<uint64_t> ex_cum; DevBuf<uint32_t> ex_ncomp;
+};
+
+struct LastDecoys {
+  bool have = false;
+  uint32_t n_spectra = 0, n_per = 0;
+  std::vector<uint8_t> rows, len;
+  std::vector<uint64_t> mask;
+  std::vector<int64_t> w;
+  std::vector<uint32_t> attempt, count;
+};
+
+struct md_ctx {
+  std::string err;
+  int device = 0;
+  int n_sm = MD_NSM_FALLBACK;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  // modifications
+  bool mods_set = false;
+  ModTables mods;          // host copy (passed to kernels by value)
+  // stores
+  PeptideStore peps;
+  MassIndex index;
+  IdentifyWorkspace ws;
+  LastDecoys last;
+  uint64_t launches = 0;   // hand-written kernels launched by the current call
+  uint64_t cub_calls = 0;  // CUB primitive invocations (scan/select/sort), counted separately
+};
+
+// per-call helper: count our own kernel launches (bench.py reports it as gpu_launches)
+#define MD_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                         \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+    (ctx)->launches++;                                                         \
+    MD_CUDA(cudaGetLastError());                                               \
+  } while (0)
+
+// stage entry points (each file implements one subsystem)
+void digest_run(md_ctx* ctx, const uint8_t* residues, const uint64_t* off, uint32_t n_prot, const md_digest_params& p);
+void digest_export(md_ctx* ctx, md_peptide_table* out);
+void index_build_run(md_ctx* ctx);
+void index_window_search_dev(md_ctx* ctx, const md_precursor* prec_dev, uint32_t n, uint64_t* begin_dev, uint64_t* end_dev);
+// fills ws.cand_* and ws.cand_off for the n precursors in ws.prec; returns total accepted
+uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n);
+// fills ws.dec_* for n precursors in ws.prec
+void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint64_t seed);
+void decoys_export(md_ctx* ctx, uint32_t n, uint32_t n_per, md_decoy_table* out);
+// bins the n spectra (device SoA), scores targets+decoys, writes PSM rows
+struct SpectraDev { uint32_t n; const double* pmz; const uint8_t* charge; const uint32_t* sid; const uint64_t* peak_off; const double* peak_mz; const float* peak_int; };
+void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev);
+void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p, uint32_t id_base);
+
+size_t cub_temp_bytes_max(size_t n);

@@ -1,0 +1,247 @@
+// index.cu -- K2: the mass-sorted in-HBM peptide index and the candidate lookup.
+//
+// Replaces the per-spectrum SQL fan-out of identification_task (tasks/identification.rs:24,180-188,
+// 214-241,374-403; models/persistable.rs:251-267): every enumerated query
+//   weight BETWEEN lo - sum k_a d_a AND hi - sum k_a d_a AND a_count = k_a ...
+// retrieves exactly the peptides with lo <= W* <= hi, W* = weight + sum_a count_a * d_a, so one radix
+// sort by W* and one window search per spectrum serve all of them.  The ModifiedPeptide filter
+// (identification.rs:242-257) then runs on the window's entries, one thread per entry.
+#include "cubx.cuh"
+#include "modpep.cuh"
+
+namespace {
+
+inline uint32_t blocks(uint64_t n, uint32_t bs = 256) { return (uint32_t)((n + bs - 1) / bs); }
+
+__global__ void k_index_keys(const int64_t* __restrict__ weight, const int16_t* __restrict__ counts, uint32_t n, const __grid_constant__ ModTables M,
+                             int64_t* __restrict__ key, uint32_t* __restrict__ ord) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int64_t k = weight[p];
+  for (int i = 0; i < M.n_letters; i++) k += (int64_t)counts[(size_t)p * MD_ALPHABET_SIZE + M.letter_alpha[i]] * M.letter_delta[i];
+  key[p] = k;
+  ord[p] = p;
+}
+
+// per index entry: weight with fixed mods, mask of variable-modifiable positions, padded row length
+__global__ void k_index_entries(const uint32_t* __restrict__ pep, uint32_t n, const uint8_t* __restrict__ seq, const uint32_t* __restrict__ seq_off,
+                                const uint8_t* __restrict__ len, const int64_t* __restrict__ weight, const __grid_constant__ ModTables M, int64_t* __restrict__ wfix,
+                                uint64_t* __restrict__ varpos, uint32_t* __restrict__ row16) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { row16[i] = 0; return; }
+  uint32_t p = pep[i];
+  const uint8_t* s = seq + seq_off[p];
+  uint32_t L = len[p];
+  int64_t w = weight[p];
+  uint64_t vp = 0;
+  for (uint32_t k = 0; k < L; k++) {
+    uint32_t c = md_code_of(s[k]);
+    if (M.has_fix[c]) w += M.fix[c];
+    if (M.has_var[c]) vp |= 1ULL << k;
+  }
+  wfix[i] = w; varpos[i] = vp;
+  row16[i] = (L + 15) >> 4;
+}
+
+__global__ void k_index_rows(const uint32_t* __restrict__ pep, uint32_t n, const uint8_t* __restrict__ seq, const uint32_t* __restrict__ seq_off,
+                             const uint8_t* __restrict__ len, const uint32_t* __restrict__ row_off16, uint8_t* __restrict__ rows, uint64_t* __restrict__ desc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t p = pep[i];
+  const uint8_t* s = seq + seq_off[p];
+  uint32_t L = len[p];
+  uint8_t* d = rows + (size_t)row_off16[i] * 16;
+  uint32_t padded = ((L + 15) >> 4) << 4;
+  for (uint32_t k = 0; k < padded; k++) d[k] = k < L ? (uint8_t)md_code_of(s[k]) : (uint8_t)MD_CODE_OTHER;
+  desc[i] = (uint64_t)row_off16[i] | ((uint64_t)L << 40);
+}
+
+// Warp-cooperative 32-ary search: first index in [0,n) whose key is >= target (UPPER: > target).
+template <bool UPPER>
+__device__ uint64_t warp_bound(const int64_t* __restrict__ key, uint64_t n, int64_t target, uint32_t lane) {
+  uint64_t lo = 0, hi = n;  // answer in [lo, hi]; everything below lo is "false", hi (if < n) is "true"
+  while (hi - lo > 32) {
+    uint64_t stride = (hi - lo + 31) / 32;
+    uint64_t pos = lo + (uint64_t)(lane + 1) * stride - 1;
+    bool valid = pos < hi;
+    int64_t v = valid ? key[pos] : 0;
+    bool t = valid ? (UPPER ? v > target : v >= target) : true;
+    uint32_t b = __ballot_sync(0xffffffffu, t);
+    if (b == 0) return hi;                           // every probe is "false": the answer is the upper end
+    uint32_t f = __ffs(b) - 1;
+    uint64_t new_lo = lo + (uint64_t)f * stride;
+    uint64_t new_hi = lo + (uint64_t)(f + 1) * stride - 1;
+    lo = new_lo;
+    hi = new_hi < hi ? new_hi : hi;
+  }
+  uint64_t pos = lo + lane;
+  bool valid = pos < hi;
+  int64_t v = valid ? key[pos] : 0;
+  bool t = valid ? (UPPER ? v > target : v >= target) : true;
+  uint32_t b = __ballot_sync(0xffffffffu, t);
+  if (b == 0) return hi;
+  uint32_t f = __ffs(b) - 1;
+  uint64_t ans = lo + f;
+  return ans < hi ? ans : hi;
+}
+
+// one warp per precursor: [begin, end) = { i : lo <= W*[i] <= hi }
+__global__ void k_window_search(const int64_t* __restrict__ key, uint64_t n, const md_precursor* __restrict__ prec, uint32_t n_prec,
+                                uint64_t* __restrict__ begin, uint64_t* __restrict__ end) {
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_prec) return;
+  int64_t lo = prec[warp].lo, hi = prec[warp].hi;
+  uint64_t b = warp_bound<false>(key, n, lo, lane);
+  uint64_t e = warp_bound<true>(key, n, hi, lane);
+  if (e < b) e = b;
+  if (lane == 0) { begin[warp] = b; end[warp] = e; }
+}
+
+__global__ void k_range_sizes(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e, uint32_t n, uint64_t* __restrict__ size) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  size[i] = i < n ? e[i] - b[i] : 0;
+}
+
+// identification.rs:214-222: K_a = (P / (m_a + d_a)) as i16, one per (spectrum, modifiable letter)
+__global__ void k_spectrum_limits(const md_precursor* __restrict__ prec, uint32_t n, const __grid_constant__ ModTables M, int16_t* __restrict__ K) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint32_t)MD_ALPHABET_SIZE) return;
+  uint32_t s = t / MD_ALPHABET_SIZE, i = t % MD_ALPHABET_SIZE;
+  int16_t k = 0;
+  if ((int)i < M.n_letters) k = (int16_t)(prec[s].mass / M.letter_mass[i]);
+  K[t] = k;
+}
+
+struct RowSeq {
+  const uint8_t* r;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return r[i]; }
+};
+
+// The ModifiedPeptide filter for every entry of every window (identification.rs:231-257,374-403).
+__global__ void k_filter(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, const md_precursor* __restrict__ prec, uint32_t n_spec,
+                         uint64_t n_entries, const uint32_t* __restrict__ idx_pep, const int64_t* __restrict__ idx_wfix, const uint64_t* __restrict__ idx_varpos,
+                         const uint64_t* __restrict__ idx_desc, const uint8_t* __restrict__ rows, const int16_t* __restrict__ counts,
+                         const int16_t* __restrict__ specK, const __grid_constant__ ModTables M, uint32_t* __restrict__ flag, uint64_t* __restrict__ emask,
+                         int64_t* __restrict__ ew, int* __restrict__ overflow) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  // spectrum of this entry: last s with flat_off[s] <= e
+  uint32_t lo = 0, hi = n_spec;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
+  const uint32_t s = lo;
+  const uint64_t i = rbegin[s] + (e - flat_off[s]);
+  const md_precursor pr = prec[s];
+  const uint32_t p = idx_pep[i];
+  bool ok = M.n_letters > 0;  // no modifiable letter -> the recursion emits no query (identification.rs:375-379)
+  int64_t cur_lo = pr.lo;
+  for (int k = 0; k < M.n_letters && ok; k++) {
+    int16_t c = counts[(size_t)p * MD_ALPHABET_SIZE + M.letter_alpha[k]];
+    if (!(c < specK[s * MD_ALPHABET_SIZE + k])) ok = false;   // 0..max_modification_count (exclusive, :381)
+    if (!(cur_lo > 0)) ok = false;                           // :387
+    cur_lo -= (int64_t)c * M.letter_delta[k];
+  }
+  int64_t w = idx_wfix[i];
+  uint64_t mask = 0;
+  if (ok) {
+    if (!md_in_window(w, pr.lo, pr.hi)) {                    // :246-249
+      uint64_t d = idx_desc[i];
+      RowSeq seq{rows + (d & 0xFFFFFFFFFFull) * 16};
+      (void)idx_varpos;
+      ok = md_try_variable(M, seq, (uint32_t)(d >> 40) & 0xFF, w, mask, pr.lo, pr.hi, overflow);
+    }
+  }
+  flag[e] = ok ? 1u : 0u;
+  emask[e] = mask;
+  ew[e] = w;
+}
+
+__global__ void k_scatter_candidates(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, uint32_t n_spec, uint64_t n_entries,
+                                     const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, const uint64_t* __restrict__ emask,
+                                     const int64_t* __restrict__ ew, const uint32_t* __restrict__ idx_pep, const uint64_t* __restrict__ idx_desc,
+                                     uint64_t* __restrict__ cand_desc, uint64_t* __restrict__ cand_mask, int64_t* __restrict__ cand_w,
+                                     uint32_t* __restrict__ cand_pep) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries || !flag[e]) return;
+  uint32_t lo = 0, hi = n_spec;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
+  const uint64_t i = rbegin[lo] + (e - flat_off[lo]);
+  uint32_t o = pos[e];
+  cand_desc[o] = idx_desc[i]; cand_mask[o] = emask[e]; cand_w[o] = ew[e]; cand_pep[o] = idx_pep[i];
+}
+
+__global__ void k_cand_offsets(const uint64_t* __restrict__ flat_off, const uint32_t* __restrict__ pos, uint32_t n_spec, uint64_t* __restrict__ cand_off) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_spec) return;
+  cand_off[s] = pos[flat_off[s]];  // pos has n_entries+1 elements (exclusive scan incl. the total)
+}
+
+}  // namespace
+
+void index_build_run(md_ctx* ctx) {
+  PeptideStore& P = ctx->peps; MassIndex& X = ctx->index;
+  MD_REQUIRE(P.ready, MD_ERR_STATE, "md_index_build: md_digest first");
+  MD_REQUIRE(ctx->mods_set, MD_ERR_STATE, "md_index_build: md_set_modifications first");
+  X.ready = false;
+  const uint32_t n = (uint32_t)P.n;
+  X.n = n; X.row_bytes = 0; X.min_key = X.max_key = 0;
+  if (n == 0) { X.key.need(1); X.ready = true; return; }
+  DevBuf<int64_t> d_key; DevBuf<uint32_t> d_ord, d_row16, d_rowoff;
+  d_key.need(n); d_ord.need(n); d_row16.need(n + 1); d_rowoff.need(n + 1);
+  X.key.need(n); X.pep.need(n); X.wfix.need(n); X.varpos.need(n); X.desc.need(n);
+  MD_LAUNCH(ctx, k_index_keys, blocks(n), 256, 0, P.weight.p, P.counts.p, n, ctx->mods, d_key.p, d_ord.p);
+  cubx_sort_pairs(ctx, d_key.p, X.key.p, d_ord.p, X.pep.p, n);  // stable: ties keep canonical peptide order
+  MD_LAUNCH(ctx, k_index_entries, blocks(n + 1), 256, 0, X.pep.p, n, P.seq.p, P.seq_off.p, P.len.p, P.weight.p, ctx->mods, X.wfix.p, X.varpos.p, d_row16.p);
+  cubx_exclusive_sum(ctx, d_row16.p, d_rowoff.p, n + 1);
+  const uint32_t total16 = d2h_scalar(ctx, d_rowoff.p + n);
+  X.row_bytes = (uint64_t)total16 * 16;
+  X.rows.need(X.row_bytes + 64);
+  MD_LAUNCH(ctx, k_index_rows, blocks(n), 256, 0, X.pep.p, n, P.seq.p, P.seq_off.p, P.len.p, d_rowoff.p, X.rows.p, X.desc.p);
+  int64_t mm[2];
+  MD_CUDA(cudaMemcpyAsync(&mm[0], X.key.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaMemcpyAsync(&mm[1], X.key.p + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  X.min_key = mm[0]; X.max_key = mm[1];
+  X.ready = true;
+}
+
+void index_window_search_dev(md_ctx* ctx, const md_precursor* prec_dev, uint32_t n, uint64_t* begin_dev, uint64_t* end_dev) {
+  if (!n) return;
+  MD_LAUNCH(ctx, k_window_search, blocks((uint64_t)n * 32, 128), 128, 0, ctx->index.key.p, ctx->index.n, prec_dev, n, begin_dev, end_dev);
+}
+
+uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
+  IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->index;
+  W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2); W.cand_off.need(n + 2);
+  if (!n) return 0;
+  index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
+  DevBuf<uint64_t> d_size; d_size.need(n + 1);
+  MD_LAUNCH(ctx, k_range_sizes, blocks(n + 1), 256, 0, W.rbegin.p, W.rend.p, n, d_size.p);
+  cubx_exclusive_sum(ctx, d_size.p, W.flat_off.p, n + 1);
+  const uint64_t E = d2h_scalar(ctx, W.flat_off.p + n);
+  MD_REQUIRE(E < 0x7FFFFF00ull, MD_ERR_UNSUPPORTED, "candidate windows of one batch exceed 2^31 index entries; use smaller batches");
+  DevBuf<int16_t> d_K; d_K.need((size_t)n * MD_ALPHABET_SIZE);
+  MD_LAUNCH(ctx, k_spectrum_limits, blocks((uint64_t)n * MD_ALPHABET_SIZE), 256, 0, W.prec.p, n, ctx->mods, d_K.p);
+  DevBuf<uint32_t> d_flag, d_pos; DevBuf<int> d_ovf;
+  d_flag.need(E + 1); d_pos.need(E + 1); d_ovf.need(1);
+  W.emask.need(E + 1); W.ew.need(E + 1);
+  MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
+  MD_CUDA(cudaMemsetAsync(d_flag.p + E, 0, sizeof(uint32_t), ctx->stream));
+  if (E) {
+    MD_LAUNCH(ctx, k_filter, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, W.prec.p, n, E, X.pep.p, X.wfix.p, X.varpos.p, X.desc.p, X.rows.p,
+              ctx->peps.counts.p, d_K.p, ctx->mods, d_flag.p, W.emask.p, W.ew.p, d_ovf.p);
+  }
+  cubx_exclusive_sum(ctx, d_flag.p, d_pos.p, E + 1);
+  const uint32_t total = d2h_scalar(ctx, d_pos.p + E);
+  const int ovf = d2h_scalar(ctx, d_ovf.p);
+  MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "variable-modification placement enumeration exceeds 2^22 subsets for one peptide");
+  W.cand_desc.need(total + 1); W.cand_mask.need(total + 1); W.cand_w.need(total + 1); W.cand_pep.need(total + 1);
+  if (E) {
+    MD_LAUNCH(ctx, k_scatter_candidates, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, d_flag.p, d_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
+              W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
+  }
+  MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, d_pos.p, n, W.cand_off.p);
+  MD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_* temporaries go out of scope
+  return total;
+}

@@ -119,6 +119,9 @@ struct Philox {
   uint32_t next() { if (!have) refill(); return out[4 - have--]; }
   uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
 };
+// diagnostics (oracle only, not part of the ABI): attempts, successes, greedy passes, position evaluations
+std::atomic<uint64_t> g_stat_attempts(0), g_stat_success(0), g_stat_tries(0), g_stat_evals(0);
+
 const uint32_t kTagRandom = 0x4D444543u;   // "MDEC"
 const uint32_t kTagPermute = 0x4D445045u;  // "MDPE"
 
@@ -344,7 +347,9 @@ bool random_attempt(const ModSet& M, const md_precursor& pr, uint64_t seed, uint
   if (st->aa.size() > MD_MAX_PEPTIDE_LEN) return false;
   const uint32_t L = (uint32_t)st->aa.size();
   for (int t = 0; t < 100; t++) {                       // 'tries (:453)
+    g_stat_tries++;
     for (uint32_t i = 0; i < L; i++) {                  // 'sequence (:454)
+      g_stat_evals++;
       int cur = st->aa[i];
       int64_t best = std::llabs(pr.mass - st->w); int bestc = cur;
       for (int c = 0; c < MD_ALPHABET_SIZE; c++) {      // 'swaps (:459-468), alphabet order
@@ -372,6 +377,7 @@ void substitution_map(const ModSet& M, int64_t* out) {  // decoy_generator.rs:30
 
 uint32_t attempt_cap(uint32_t n) { return 16u * n + 1024u; }
 
+
 void decoys_random(const md_ctx* ctx, const md_precursor& pr, uint32_t n, uint64_t seed,
                    std::vector<Decoy>* out) {
   int64_t delta[MD_ALPHABET_SIZE * MD_ALPHABET_SIZE];
@@ -380,7 +386,9 @@ void decoys_random(const md_ctx* ctx, const md_precursor& pr, uint32_t n, uint64
   ModState st;
   const uint32_t cap = attempt_cap(n);
   for (uint32_t a = 0; a < cap && out->size() < n; a++) {
+    g_stat_attempts++;
     if (!random_attempt(ctx->mods, pr, seed, a, delta, &st)) continue;
+    g_stat_success++;
     std::string s((const char*)st.raw.data(), st.raw.size());
     if (ctx->peps.by_seq.count(s)) continue;             // Decoy::is_peptide (decoy.rs:49-60)
     if (!seen.insert(s).second) continue;                // HashSet<Decoy> (decoy_generator.rs:40,164)
@@ -627,6 +635,11 @@ int fill_decoy_table(const std::vector<std::vector<Decoy>>& per, md_decoy_table*
 // C ABI
 // =========================================================================================
 extern "C" {
+
+MD_API void md_oracle_decoy_stats(uint64_t out[4], int reset) {
+  out[0] = g_stat_attempts; out[1] = g_stat_success; out[2] = g_stat_tries; out[3] = g_stat_evals;
+  if (reset) { g_stat_attempts = 0; g_stat_success = 0; g_stat_tries = 0; g_stat_evals = 0; }
+}
 
 const char* md_backend_name(void) { return "cpu-oracle"; }
 
