@@ -260,8 +260,14 @@ typedef struct md_identify_stats {
   uint64_t n_targets;       /* target candidates scored */
   uint64_t n_decoys;        /* decoys generated and scored */
   uint64_t n_less_decoys;   /* spectra that got fewer decoys than requested */
-  uint64_t n_kernel_launches;
+  uint64_t n_kernel_launches; /* hand-written kernels launched by the call (CUB primitives not counted) */
   double ms_lookup, ms_decoys, ms_score, ms_total; /* device time (CUDA events) / host time (oracle) */
+  /* per-kernel device time, CUDA events on the ctx stream (0 in the oracle) */
+  double ms_kernel_score;     /* the fused fragment-and-score kernel alone */
+  double ms_kernel_decoy;     /* the decoy attempt kernels (all rounds) */
+  uint64_t n_attempts;        /* decoy attempts run */
+  uint64_t n_pairs;           /* (spectrum, candidate) pairs scored */
+  uint64_t score_bytes;       /* algorithmic bytes of the score kernel: sum over pairs of (14 + len) */
 } md_identify_stats;
 
 /* identification_task for a batch of spectra (tasks/identification.rs:201-368), with the
@@ -274,11 +280,15 @@ MD_API int md_identify(md_ctx* ctx, const md_spectra* spectra, const md_search_p
                        md_psm* psms, md_identify_stats* stats, int64_t** all_scores,
                        uint64_t** all_off);
 /* Same, with every pointer inside `spectra` and `psms` being a device pointer on the ctx's
- * device; asynchronous on the ctx stream until md_sync.  CUDA implementation only. */
+ * device (e.g. `psms` = the NCCL send buffer of the PSM gather).  The work runs on the ctx
+ * stream; the call returns when the PSM rows are in `psms`.  CUDA implementation only. */
 MD_API int md_identify_device(md_ctx* ctx, const md_spectra* spectra_dev,
                               const md_search_params* params, md_psm* psms_dev,
                               md_identify_stats* stats);
 MD_API int md_sync(md_ctx* ctx);
+/* The cudaStream_t the ctx launches on (NULL in the oracle), for callers that bracket calls
+ * with their own CUDA events. */
+MD_API void* md_stream_handle(md_ctx* ctx);
 /* The decoys of the last md_identify* call with keep_decoys != 0. */
 MD_API int md_last_decoys_export(md_ctx* ctx, md_decoy_table* out);
 MD_API void md_free(void* p);

@@ -2,6 +2,7 @@
 #include <cctype>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -71,15 +72,21 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime
 void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, md_psm* psm_dev, md_identify_stats* st,
                     uint32_t id_base) {
   cudaStream_t s = ctx->stream;
+  ctx->marks.clear(); ctx->mark("begin");
   MD_CUDA(cudaEventRecord(ctx->ev[0], s));
   precursors_dev(ctx, S, p, id_base);
+  ctx->mark("precursors");
   const uint64_t n_targets = index_candidates_dev(ctx, S.n);
+  ctx->mark("candidates");
   MD_CUDA(cudaEventRecord(ctx->ev[1], s));
   decoys_generate_dev(ctx, S.n, p.n_decoys, p.decoy_mode, p.seed);
+  ctx->mark("decoys");
   MD_CUDA(cudaEventRecord(ctx->ev[2], s));
   score_run_dev(ctx, S, n_peaks, p, p.n_decoys, psm_dev);
   MD_CUDA(cudaEventRecord(ctx->ev[3], s));
   MD_CUDA(cudaStreamSynchronize(s));
+  ctx->mark("score");
+  ctx->dump_marks("identify_batch");
   if (st) {
     st->n_spectra += S.n; st->n_targets += n_targets;
     if (p.n_decoys && S.n) {
@@ -93,10 +100,31 @@ void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md
 }
 
 }  // namespace
+void md_ctx::mark(const char* what) {
+  if (!trace) return;
+  cudaStreamSynchronize(stream);
+  marks.push_back({what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count()});
+}
+void md_ctx::dump_marks(const char* call) {
+  if (!trace || marks.empty()) return;
+  fprintf(stderr, "[md_trace] %s:", call);
+  for (size_t i = 1; i < marks.size(); i++) fprintf(stderr, " %s=%.2fms", marks[i].first, marks[i].second - marks[i - 1].second);
+  fprintf(stderr, " total=%.2fms\n", marks.back().second - marks.front().second);
+  marks.clear();
+}
+namespace {
+void fill_kernel_stats(md_ctx* ctx, md_identify_stats* st) {
+  st->n_kernel_launches = ctx->launches;
+  st->ms_kernel_score = ctx->acc_ms_kscore; st->ms_kernel_decoy = ctx->acc_ms_kdecoy;
+  st->n_attempts = ctx->acc_attempts; st->n_pairs = ctx->acc_pairs; st->score_bytes = ctx->acc_score_bytes;
+}
+
+}  // namespace
 
 extern "C" {
 
 const char* md_backend_name(void) { return "cuda-sm100a"; }
+void* md_stream_handle(md_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int md_create(const md_config* cfg, md_ctx** out) {
   if (!out) return fail(nullptr, MD_ERR_INVALID, "md_create: out is NULL");
@@ -115,6 +143,7 @@ int md_create(const md_config* cfg, md_ctx** out) {
     MD_CUDA(cudaGetDeviceProperties(&prop, c->device));
     MD_REQUIRE(prop.major >= 10, MD_ERR_DEVICE, "md_create: this library is built for sm_100a (Blackwell B200) only");
     c->n_sm = prop.multiProcessorCount;
+    c->trace = getenv("MD_TRACE") != nullptr;
     MD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) MD_CUDA(cudaEventCreate(&ev));
     *out = c;
@@ -204,7 +233,7 @@ int md_substitution_map(md_ctx* ctx, int64_t* out) {
 int md_digest(md_ctx* ctx, const uint8_t* residues, const uint64_t* off, uint32_t n_prot, const md_digest_params* p, uint64_t* n_out) {
   if (!ctx || !p || (n_prot && (!residues || !off))) return fail(ctx, MD_ERR_INVALID, "md_digest: null argument");
   return guarded(ctx, [&] {
-    ctx->launches = 0; ctx->cub_calls = 0;
+    ctx->reset_counters();
     digest_run(ctx, residues, off, n_prot, *p);
     if (n_out) *n_out = ctx->peps.n;
   });
@@ -222,7 +251,7 @@ void md_peptide_table_free(md_peptide_table* t) {
 
 int md_index_build(md_ctx* ctx) {
   if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_index_build: null ctx");
-  return guarded(ctx, [&] { ctx->launches = 0; ctx->cub_calls = 0; index_build_run(ctx); });
+  return guarded(ctx, [&] { ctx->reset_counters(); index_build_run(ctx); });
 }
 
 int md_index_stats_get(md_ctx* ctx, md_index_stats* out) {
@@ -301,7 +330,7 @@ int md_generate_decoys(md_ctx* ctx, const md_precursor* pr, uint32_t n_spec, uin
   if (mode < 0 || mode > 2) return fail(ctx, MD_ERR_INVALID, "md_generate_decoys: unknown mode");
   return guarded(ctx, [&] {
     IdentifyWorkspace& W = ctx->ws;
-    ctx->launches = 0; ctx->cub_calls = 0;
+    ctx->reset_counters();
     W.prec.need(n_spec + 1);
     if (n_spec) MD_CUDA(cudaMemcpyAsync(W.prec.p, pr, n_spec * sizeof(md_precursor), cudaMemcpyHostToDevice, ctx->stream));
     if (mode == MD_DECOY_PERMUTE_TARGET) index_candidates_dev(ctx, n_spec);
@@ -321,13 +350,13 @@ int md_identify_device(md_ctx* ctx, const md_spectra* S, const md_search_params*
   return guarded(ctx, [&] {
     validate_params(p);
     if (stats) memset(stats, 0, sizeof(*stats));
-    ctx->launches = 0; ctx->cub_calls = 0; ctx->last.have = false;
+    ctx->reset_counters(); ctx->last.have = false;
     if (!S->n) return;
     uint64_t n_peaks = 0;
     MD_CUDA(cudaMemcpy(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     SpectraDev D{S->n, S->precursor_mz, S->charge, S->spectrum_id, S->peak_off, S->peak_mz, S->peak_intensity};
     identify_batch(ctx, D, n_peaks, *p, psms_dev, stats, 0);
-    if (stats) stats->n_kernel_launches = ctx->launches;
+    if (stats) fill_kernel_stats(ctx, stats);
   });
 }
 
@@ -340,7 +369,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
     if (stats) memset(stats, 0, sizeof(*stats));
     if (all_scores) *all_scores = nullptr;
     if (all_off) *all_off = nullptr;
-    ctx->launches = 0; ctx->cub_calls = 0; ctx->last.have = false;
+    ctx->reset_counters(); ctx->last.have = false;
     const uint32_t n = S->n;
     for (uint32_t s = 0; s < n; s++) {
       MD_REQUIRE(S->peak_off[s + 1] >= S->peak_off[s], MD_ERR_INVALID, "spectra: peak_off not monotone");
@@ -365,7 +394,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
     identify_batch(ctx, D, np, *p, W.psm.p, stats, 0);
     if (p->top_k) MD_CUDA(cudaMemcpyAsync(psms, W.psm.p, (size_t)n * p->top_k * sizeof(md_psm), cudaMemcpyDeviceToHost, st));
     MD_CUDA(cudaStreamSynchronize(st));
-    if (stats) stats->n_kernel_launches = ctx->launches;
+    if (stats) fill_kernel_stats(ctx, stats);
     if (all_scores && all_off) {
       std::vector<uint64_t> coff(n + 1); std::vector<uint32_t> dcnt(n, 0);
       MD_CUDA(cudaMemcpy(coff.data(), W.cand_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));

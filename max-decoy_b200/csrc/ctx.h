@@ -55,7 +55,7 @@ struct IdentifyWorkspace {
   DevBuf<uint8_t> att_rows; DevBuf<uint8_t> att_len; DevBuf<uint64_t> att_mask; DevBuf<int64_t> att_w; DevBuf<uint64_t> att_hash;
   DevBuf<uint8_t> dec_rows; DevBuf<uint8_t> dec_len; DevBuf<uint64_t> dec_mask; DevBuf<int64_t> dec_w; DevBuf<uint64_t> dec_hash;
   DevBuf<uint32_t> dec_attempt; DevBuf<uint32_t> dec_count; DevBuf<uint32_t> att_base; DevBuf<uint32_t> att_limit;
-  DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters;
+  DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters; DevBuf<unsigned long long> stat64;
   // binned spectra
   DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
@@ -90,6 +90,15 @@ struct md_ctx {
   LastDecoys last;
   uint64_t launches = 0;   // hand-written kernels launched by the current call
   uint64_t cub_calls = 0;  // CUB primitive invocations (scan/select/sort), counted separately
+  // per-call accumulators reported through md_identify_stats
+  double acc_ms_kscore = 0, acc_ms_kdecoy = 0;
+  uint64_t acc_attempts = 0, acc_pairs = 0, acc_score_bytes = 0;
+  // MD_TRACE=1: host wall-clock marks of the current call, dumped to stderr at its end
+  bool trace = false;
+  std::vector<std::pair<const char*, double>> marks;
+  void mark(const char* what);
+  void dump_marks(const char* call);
+  void reset_counters() { launches = 0; cub_calls = 0; acc_ms_kscore = acc_ms_kdecoy = 0; acc_attempts = acc_pairs = acc_score_bytes = 0; }
 };
 
 // per-call helper: count our own kernel launches (bench.py reports it as gpu_launches)

@@ -369,6 +369,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaMemcpyAsync(d_list.p, list.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n_list + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaMemcpyAsync(d_base.p, base.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    MD_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (mode == MD_DECOY_REFERENCE_RANDOM) {
       MD_CUDA(cudaMemsetAsync(d_queue.p, 0, sizeof(uint32_t), ctx->stream));
       uint32_t grid = std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * 8u);
@@ -377,11 +378,15 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       MD_LAUNCH(ctx, k_decoy_permute, blocks(total, kThreads), kThreads, 0, W.prec.p, d_list.p, d_off.p, d_base.p, n_list, total, seed, T, W.cand_off.p,
                 W.cand_desc.p, W.cand_mask.p, W.cand_w.p, ctx->index.rows.p, O, PV);
     }
+    MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->mark("  attempts");
     MD_LAUNCH(ctx, k_decoy_select, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p,
               W.dec_attempt.p, W.dec_count.p);
     MD_CUDA(cudaMemcpyAsync(count.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->mark("  select");
     for (uint32_t i = 0; i < n_list; i++) used[list[i]] += off[i + 1] - off[i];
+    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total; }
   }
   const int ovf = d2h_scalar(ctx, d_ovf.p);
   MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "variable-modification placement enumeration exceeds 2^22 subsets for one decoy");

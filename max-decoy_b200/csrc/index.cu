@@ -216,6 +216,7 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2); W.cand_off.need(n + 2);
   if (!n) return 0;
   index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
+  ctx->mark("  window_search");
   DevBuf<uint64_t> d_size; d_size.need(n + 1);
   MD_LAUNCH(ctx, k_range_sizes, blocks(n + 1), 256, 0, W.rbegin.p, W.rend.p, n, d_size.p);
   cubx_exclusive_sum(ctx, d_size.p, W.flat_off.p, n + 1);
@@ -228,10 +229,12 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   W.emask.need(E + 1); W.ew.need(E + 1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   MD_CUDA(cudaMemsetAsync(d_flag.p + E, 0, sizeof(uint32_t), ctx->stream));
+  ctx->mark("  alloc");
   if (E) {
     MD_LAUNCH(ctx, k_filter, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, W.prec.p, n, E, X.pep.p, X.wfix.p, X.varpos.p, X.desc.p, X.rows.p,
               ctx->peps.counts.p, d_K.p, ctx->mods, d_flag.p, W.emask.p, W.ew.p, d_ovf.p);
   }
+  ctx->mark("  filter");
   cubx_exclusive_sum(ctx, d_flag.p, d_pos.p, E + 1);
   const uint32_t total = d2h_scalar(ctx, d_pos.p + E);
   const int ovf = d2h_scalar(ctx, d_ovf.p);
@@ -243,5 +246,6 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   }
   MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, d_pos.p, n, W.cand_off.p);
   MD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_* temporaries go out of scope
+  ctx->mark("  scatter");
   return total;
 }

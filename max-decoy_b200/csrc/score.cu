@@ -167,6 +167,7 @@ struct ScoreArgs {
   int64_t* tscore; int64_t* dscore;
   md_psm* psm;
   uint32_t* work;
+  unsigned long long* stat64;  // [0] pairs scored, [1] algorithmic bytes (14 + len per pair)
 };
 
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAAAAABu) >> 1; }
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per-letter (q, r) tables in registers: lane = residue code
   const uint32_t lq = C.tq[lane], lr = C.tr[lane], lvq = C.vq[lane], lvr = C.vr[lane];
+  unsigned long long my_pairs = 0, my_bytes = 0;
 
   for (;;) {
     if (threadIdx.x == 0) s_work = atomicAdd(A.work, 1u);
@@ -294,6 +296,10 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         *r.score = 0;
       }
     } else {
+      for (uint32_t v = threadIdx.x; v < ncand; v += kScoreThreads) {
+        const uint32_t len = v < nt ? (uint32_t)(A.cand_desc[t0c + v] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (v - nt)];
+        my_pairs++; my_bytes += 14 + len;
+      }
       const uint32_t NB = (uint32_t)hbin + kXcorrOffset + 1;  // table bins [0, NB)
       const uint64_t pk0 = A.peak_off[s]; const uint32_t npk = A.pk_count[s];
       bool first = true;
@@ -391,6 +397,8 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     }
     __syncthreads();
   }
+  for (int o = 16; o; o >>= 1) { my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o); my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, o); }
+  if (lane == 0 && my_pairs) { atomicAdd(&A.stat64[0], my_pairs); atomicAdd(&A.stat64[1], my_bytes); }
 }
 
 void split_qr(int64_t m, uint32_t w, uint32_t* q, uint32_t* r) {
@@ -441,14 +449,17 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1);
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+  W.stat64.need(2);
+  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   ScoreArgs A;
   A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
   A.cand_off = W.cand_off.p; A.cand_desc = W.cand_desc.p; A.cand_mask = W.cand_mask.p; A.cand_w = W.cand_w.p; A.cand_pep = W.cand_pep.p;
   A.idx_rows = ctx->index.rows.p;
   A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
-  A.tscore = W.tscore.p; A.dscore = W.dscore.p; A.psm = psm_dev; A.work = work.p;
+  A.tscore = W.tscore.p; A.dscore = W.dscore.p; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
   const size_t smem = (size_t)kTileBins * sizeof(int32_t);
   const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
+  MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (has_var) {
     MD_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MD_LAUNCH(ctx, k_score<true>, grid, kScoreThreads, smem, A, C);
@@ -456,6 +467,10 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     MD_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MD_LAUNCH(ctx, k_score<false>, grid, kScoreThreads, smem, A, C);
   }
+  MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+  unsigned long long h_stat[2] = {0, 0};
+  MD_CUDA(cudaMemcpyAsync(h_stat, W.stat64.p, sizeof(h_stat), cudaMemcpyDeviceToHost, ctx->stream));
   const int unsorted = d2h_scalar(ctx, d_flag.p);
+  { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->acc_ms_kscore += ms; ctx->acc_pairs += h_stat[0]; ctx->acc_score_bytes += h_stat[1]; }
   MD_REQUIRE(!unsorted, MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
 }

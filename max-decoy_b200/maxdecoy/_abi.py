@@ -97,7 +97,8 @@ class md_identify_stats(C.Structure):
     _fields_ = [("n_spectra", C.c_uint64), ("n_targets", C.c_uint64), ("n_decoys", C.c_uint64),
                 ("n_less_decoys", C.c_uint64), ("n_kernel_launches", C.c_uint64),
                 ("ms_lookup", C.c_double), ("ms_decoys", C.c_double), ("ms_score", C.c_double),
-                ("ms_total", C.c_double)]
+                ("ms_total", C.c_double), ("ms_kernel_score", C.c_double), ("ms_kernel_decoy", C.c_double),
+                ("n_attempts", C.c_uint64), ("n_pairs", C.c_uint64), ("score_bytes", C.c_uint64)]
 
 
 # numpy dtype with the exact md_psm layout (for zero-copy views of PSM buffers)
@@ -135,6 +136,7 @@ SYMBOLS = {
     "md_identify_device": (C.c_int, [ctx_p, C.POINTER(md_spectra), C.POINTER(md_search_params), C.c_void_p,
                                      C.POINTER(md_identify_stats)]),
     "md_sync": (C.c_int, [ctx_p]),
+    "md_stream_handle": (C.c_void_p, [ctx_p]),
     "md_last_decoys_export": (C.c_int, [ctx_p, C.POINTER(md_decoy_table)]),
     "md_free": (None, [C.c_void_p]),
 }

@@ -654,6 +654,7 @@ void md_destroy(md_ctx* ctx) { delete ctx; }
 const char* md_last_error(const md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 void md_free(void* p) { std::free(p); }
 int md_sync(md_ctx*) { return MD_OK; }
+void* md_stream_handle(md_ctx*) { return nullptr; }
 
 int64_t md_residue_mass(uint8_t c) { return residue_mass(c); }
 int64_t md_sequence_weight(const uint8_t* seq, uint32_t len) { return sequence_weight(seq, len); }
@@ -917,6 +918,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
     double th = (double)std::max<uint32_t>(1, ctx->n_threads);
     stats->ms_lookup = t_lookup / 1e6 / th; stats->ms_decoys = t_decoy / 1e6 / th; stats->ms_score = t_score / 1e6 / th;
     stats->ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    stats->n_pairs = stats->n_targets + stats->n_decoys;
   }
   if (all_scores && all_off) {
     std::vector<uint64_t> off(1, 0); std::vector<int64_t> flat;
