@@ -63,14 +63,14 @@ void validate_params(const md_search_params* p) {
   MD_REQUIRE(p->decoy_mode >= 0 && p->decoy_mode <= 2, MD_ERR_INVALID, "md_identify: unknown decoy mode");
   const int64_t w = (int64_t)llround(p->fragment_tolerance * 1000000.0);
   MD_REQUIRE(w >= 100 && w <= 2000000, MD_ERR_INVALID, "md_identify: fragment_tolerance must be in [0.0001, 2] Da");
-  MD_REQUIRE(p->top_k <= 1024, MD_ERR_INVALID, "md_identify: top_k > 1024");
+  MD_REQUIRE(p->top_k <= 128, MD_ERR_INVALID, "md_identify: top_k > 128");
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // the identification of one batch of spectra that already sits in device memory
 void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, md_psm* psm_dev, md_identify_stats* st,
-                    uint32_t id_base) {
+                    uint32_t id_base, bool want_all) {
   cudaStream_t s = ctx->stream;
   ctx->marks.clear(); ctx->mark("begin");
   MD_CUDA(cudaEventRecord(ctx->ev[0], s));
@@ -82,7 +82,7 @@ void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md
   decoys_generate_dev(ctx, S.n, p.n_decoys, p.decoy_mode, p.seed);
   ctx->mark("decoys");
   MD_CUDA(cudaEventRecord(ctx->ev[2], s));
-  score_run_dev(ctx, S, n_peaks, p, p.n_decoys, psm_dev);
+  score_run_dev(ctx, S, n_peaks, p, p.n_decoys, psm_dev, want_all);
   MD_CUDA(cudaEventRecord(ctx->ev[3], s));
   MD_CUDA(cudaStreamSynchronize(s));
   ctx->mark("score");
@@ -355,7 +355,7 @@ int md_identify_device(md_ctx* ctx, const md_spectra* S, const md_search_params*
     uint64_t n_peaks = 0;
     MD_CUDA(cudaMemcpy(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     SpectraDev D{S->n, S->precursor_mz, S->charge, S->spectrum_id, S->peak_off, S->peak_mz, S->peak_intensity};
-    identify_batch(ctx, D, n_peaks, *p, psms_dev, stats, 0);
+    identify_batch(ctx, D, n_peaks, *p, psms_dev, stats, 0, false);
     if (stats) fill_kernel_stats(ctx, stats);
   });
 }
@@ -391,7 +391,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
       MD_CUDA(cudaMemcpyAsync(W.peak_int.p, S->peak_intensity, np * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     SpectraDev D{n, W.pmz.p, W.charge.p, S->spectrum_id ? W.sid.p : nullptr, W.peak_off.p, W.peak_mz.p, W.peak_int.p};
-    identify_batch(ctx, D, np, *p, W.psm.p, stats, 0);
+    identify_batch(ctx, D, np, *p, W.psm.p, stats, 0, all_scores && all_off);
     if (p->top_k) MD_CUDA(cudaMemcpyAsync(psms, W.psm.p, (size_t)n * p->top_k * sizeof(md_psm), cudaMemcpyDeviceToHost, st));
     MD_CUDA(cudaStreamSynchronize(st));
     if (stats) fill_kernel_stats(ctx, stats);

@@ -57,10 +57,13 @@ struct IdentifyWorkspace {
   DevBuf<uint32_t> dec_attempt; DevBuf<uint32_t> dec_count; DevBuf<uint32_t> att_base; DevBuf<uint32_t> att_limit;
   DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters; DevBuf<unsigned long long> stat64;
   // binned spectra
-  DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
+  DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_pre; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
   DevBuf<uint8_t> cub_tmp;
+  // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
+  DevBuf<uint64_t> t_size; DevBuf<int16_t> t_K; DevBuf<uint32_t> t_flag, t_pos; DevBuf<int> t_ovf, t_unsorted;
+  DevBuf<uint32_t> t_list, t_off, t_base, t_queue;
   // exhaustive mode
   DevBuf<int32_t> ex_comp; DevBuf<uint64_t> ex_cum; DevBuf<uint32_t> ex_ncomp;
 };
@@ -121,7 +124,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
 void decoys_export(md_ctx* ctx, uint32_t n, uint32_t n_per, md_decoy_table* out);
 // bins the n spectra (device SoA), scores targets+decoys, writes PSM rows
 struct SpectraDev { uint32_t n; const double* pmz; const uint8_t* charge; const uint32_t* sid; const uint64_t* peak_off; const double* peak_mz; const float* peak_int; };
-void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev);
+void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev, bool want_all);
 void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p, uint32_t id_base);
 
 size_t cub_temp_bytes_max(size_t n);

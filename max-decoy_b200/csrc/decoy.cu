@@ -344,7 +344,8 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     if (mode == MD_DECOY_PERMUTE_TARGET) c = std::min<uint64_t>(c, (h_cand_off[s + 1] - h_cand_off[s]) * 1000ull);
     cap[s] = (uint32_t)c;
   }
-  DevBuf<uint32_t> d_list, d_off, d_base, d_queue; DevBuf<int> d_ovf;
+  DevBuf<uint32_t>& d_list = W.t_list; DevBuf<uint32_t>& d_off = W.t_off; DevBuf<uint32_t>& d_base = W.t_base; DevBuf<uint32_t>& d_queue = W.t_queue;
+  DevBuf<int>& d_ovf = W.t_ovf;
   d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(1); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   std::vector<uint32_t> list, off, base;

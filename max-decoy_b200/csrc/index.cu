@@ -217,14 +217,14 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   if (!n) return 0;
   index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
   ctx->mark("  window_search");
-  DevBuf<uint64_t> d_size; d_size.need(n + 1);
+  DevBuf<uint64_t>& d_size = W.t_size; d_size.need(n + 1);
   MD_LAUNCH(ctx, k_range_sizes, blocks(n + 1), 256, 0, W.rbegin.p, W.rend.p, n, d_size.p);
   cubx_exclusive_sum(ctx, d_size.p, W.flat_off.p, n + 1);
   const uint64_t E = d2h_scalar(ctx, W.flat_off.p + n);
   MD_REQUIRE(E < 0x7FFFFF00ull, MD_ERR_UNSUPPORTED, "candidate windows of one batch exceed 2^31 index entries; use smaller batches");
-  DevBuf<int16_t> d_K; d_K.need((size_t)n * MD_ALPHABET_SIZE);
+  DevBuf<int16_t>& d_K = W.t_K; d_K.need((size_t)n * MD_ALPHABET_SIZE);
   MD_LAUNCH(ctx, k_spectrum_limits, blocks((uint64_t)n * MD_ALPHABET_SIZE), 256, 0, W.prec.p, n, ctx->mods, d_K.p);
-  DevBuf<uint32_t> d_flag, d_pos; DevBuf<int> d_ovf;
+  DevBuf<uint32_t>& d_flag = W.t_flag; DevBuf<uint32_t>& d_pos = W.t_pos; DevBuf<int>& d_ovf = W.t_ovf;
   d_flag.need(E + 1); d_pos.need(E + 1); d_ovf.need(1);
   W.emask.need(E + 1); W.ew.need(E + 1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
@@ -245,7 +245,6 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
               W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
   }
   MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, d_pos.p, n, W.cand_off.p);
-  MD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_* temporaries go out of scope
   ctx->mark("  scatter");
   return total;
 }

@@ -12,12 +12,16 @@
 //   T[b]       = 151*y[b] - sum_{j=b-75..b+75} y[j]          (= 150 * 2^16 * fast_xcorr[b])
 //   raw score  = sum over b/y fragments and fragment charges of T[bin];   score = 0.005 * raw / (150 * 2^16)
 //
-// Kernel design (B200): one persistent CTA per SM; per spectrum the CTA expands the sparse binned spectrum into a
-// dense int32 table tile in shared memory (zero + shared-memory atomic scatter of +-75-bin windows), then every
-// thread scores one candidate at a time: the row (residue codes, 16-byte padded) comes in with 128-bit coalesced
-// loads, the per-letter (quotient, remainder) mass table lives in registers and is read with warp shuffles, fragment
-// bins follow from a division-free running (q, r) sum, and each fragment costs exactly one shared-memory gather.
-// Spectra wider than one tile are processed tile by tile; partial scores are kept in HBM (L2-resident).
+// Kernel design (B200): one persistent CTA of 1024 threads per SM (spectra from a global queue).  Per spectrum the CTA
+// stages the sparse binned spectrum (bin, y, prefix sums of y) in shared memory and expands it, tile by tile, into a
+// dense int32 table tile of 49152 bins (192 KiB): vectorised zero fill, then one warp per window edge paints the
+// piecewise-constant -sum(y) segments with coalesced stores (no atomics: segment values come from the prefix sums),
+// then one thread per peak adds the 151*y spike.  Every thread then scores one candidate at a time: the row (residue
+// codes, 16-byte padded) comes in with 128-bit loads, the per-letter packed (quotient, remainder) mass table lives in
+// registers and is read with one warp shuffle per residue, fragment bins follow from a division-free running (q, r)
+// sum, and each fragment costs exactly one shared-memory gather.  Partial scores of a
+// candidate chunk stay in shared memory across tiles; top-k packs (score, ordinal) into one 64-bit key and selects with
+// warp REDUX max.  Nothing but the PSM rows is written to HBM unless the caller asks for all scores.
 #include "cubx.cuh"
 
 namespace {
@@ -25,8 +29,12 @@ namespace {
 inline uint32_t blocks(uint64_t n, uint32_t bs = 256) { return (uint32_t)((n + bs - 1) / bs); }
 
 constexpr int kXcorrOffset = 75;
-constexpr int kScoreThreads = 512;
-constexpr uint32_t kTileBins = 49152;  // 192 KiB of int32 per CTA
+constexpr int kScoreThreads = 1024;
+constexpr uint32_t kTileBins = 49152;     // 192 KiB of int32 per CTA
+constexpr uint32_t kCandChunk = 1536;     // candidates whose partial scores stay in shared memory across tiles
+constexpr uint32_t kPeakCap = 1024;       // binned peaks staged in shared memory (larger spectra read them from HBM)
+constexpr uint32_t kMaxBins = 1u << 30;   // table bins per spectrum (bins are 32-bit)
+constexpr uint32_t kMaxTopK = 128;
 
 // ------------------------------------------------------------------------------------------------
 // precursor windows: tasks/identification.rs:203-211 (utility/mod.rs:9-11; models/mass/mod.rs:6-8,14-16)
@@ -73,7 +81,7 @@ __device__ __forceinline__ PeakEval eval_peak(double mz, float I, int64_t P, int
 
 __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const double* __restrict__ peak_mz, const float* __restrict__ peak_int,
                               const md_precursor* __restrict__ prec, uint32_t n, int64_t w, uint32_t min_peaks, int32_t* __restrict__ pk_bin,
-                              int32_t* __restrict__ pk_yq, uint32_t* __restrict__ pk_count, int32_t* __restrict__ pk_hbin, int* __restrict__ unsorted) {
+                              int32_t* __restrict__ pk_yq, uint32_t* __restrict__ pk_pre, uint32_t* __restrict__ pk_count, int32_t* __restrict__ pk_hbin, int* __restrict__ unsorted) {
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= n) return;
   const uint64_t p0 = peak_off[s], p1 = peak_off[s + 1];
@@ -143,6 +151,19 @@ __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const doubl
     if (last > carry_bin) carry_bin = last;
   }
   if (lane == 0) { pk_count[s] = carry_cnt; pk_hbin[s] = hbin; }
+  // exclusive prefix sums of y (mod 2^32: window sums are < 2^31, differences stay exact); carry_cnt + 1 entries at p0 + s
+  __syncwarp();
+  uint32_t run = 0;
+  uint32_t* pre = pk_pre + p0 + s;
+  for (uint32_t base = 0; base < carry_cnt; base += 32) {
+    const uint32_t i = base + lane;
+    const uint32_t v = i < carry_cnt ? (uint32_t)__ldcg(&pk_yq[p0 + i]) : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    if (i < carry_cnt) pre[i] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) pre[carry_cnt] = run;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -150,250 +171,309 @@ __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const doubl
 // ------------------------------------------------------------------------------------------------
 struct ScoreConst {
   uint32_t w;                 // bin width, uDa
+  uint32_t rbits;             // remainder field width of the packed tables
   uint32_t qp, rp;            // proton  = qp*w + rp
   uint32_t q2p, r2p;          // 2*proton
-  uint32_t tq[32], tr[32];    // per residue code: (mass + fixed delta) = tq*w + tr
-  uint32_t vq[32], vr[32];    // per residue code: (mass + variable delta)
+  uint32_t tqr[32];           // per residue code: (mass + fixed delta) = q*w + r, packed q << rbits | r
+  uint32_t vqr[32];           // per residue code: (mass + fixed + variable delta)
   uint32_t max_frag_charge;
   uint32_t top_k, n_per;
 };
 
 struct ScoreArgs {
   const md_precursor* prec; uint32_t n_spec;
-  const uint64_t* peak_off; const int32_t* pk_bin; const int32_t* pk_yq; const uint32_t* pk_count; const int32_t* pk_hbin;
+  const uint64_t* peak_off; const int32_t* pk_bin; const int32_t* pk_yq; const uint32_t* pk_pre; const uint32_t* pk_count; const int32_t* pk_hbin;
   const uint64_t* cand_off; const uint64_t* cand_desc; const uint64_t* cand_mask; const int64_t* cand_w; const uint32_t* cand_pep;
   const uint8_t* idx_rows;
   const uint8_t* dec_rows; const uint8_t* dec_len; const uint64_t* dec_mask; const int64_t* dec_w; const uint32_t* dec_count;
-  int64_t* tscore; int64_t* dscore;
+  int64_t* tscore; int64_t* dscore;   // raw score of every candidate, or NULL (PSM rows only)
   md_psm* psm;
   uint32_t* work;
   unsigned long long* stat64;  // [0] pairs scored, [1] algorithmic bytes (14 + len per pair)
+  int* error;                  // set when a spectrum needs more table bins than kMaxBins
 };
 
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAAAAABu) >> 1; }
 
-// partial raw score of one candidate against the table tile [t0, t0+tn)
+// Raw score of one candidate against the table tile [t0, t0+tn).
+//   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
+// with X = B_k + proton kept as (Q, R), X = Q*w + R, so no fragment needs a division.
+// one table gather, branch-free: out-of-range (or switched-off) fragments read the always-zero sentinel slot
+__device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
+  int32_t v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void acc_wide(int64_t& acc, int32_t v) {  // acc += v as one IMAD.WIDE
+  asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(acc) : "r"(v));
+}
+#define MD_GATHER(bin) acc_wide(acc, lds_s32(tab_s + 4u * ((on && (bin) < tn) ? (bin) : kTileBins)))
+
 template <int NCH, bool HASVAR>
 __device__ __forceinline__ int64_t score_one(const uint4* __restrict__ row, uint32_t len, uint64_t mask, int64_t modw, uint32_t maxlen,
-                                             const int32_t* __restrict__ tab, uint32_t t0, uint32_t tn, const ScoreConst& C, uint32_t lq, uint32_t lr,
-                                             uint32_t lvq, uint32_t lvr) {
-  const uint32_t w = C.w;
+                                             uint32_t tab_s, uint32_t t0, uint32_t tn, const ScoreConst& C, uint32_t lqr, uint32_t lvqr) {
+  const uint32_t w = C.w, rbits = C.rbits, rmask = (1u << rbits) - 1u;
   // T_c = modw + (c+1)*proton  ->  (Qt, Rt)
-  uint64_t T1 = (uint64_t)modw + 2ull * MD_PROTON_UDA;
-  uint32_t Qt1 = (uint32_t)(T1 / w), Rt1 = (uint32_t)(T1 - (uint64_t)Qt1 * w);
+  const uint64_t T1 = (uint64_t)modw + 2ull * MD_PROTON_UDA;
+  const uint32_t Qt1 = (uint32_t)(T1 / w), Rt1 = (uint32_t)(T1 - (uint64_t)Qt1 * w);
   uint32_t Rt2 = Rt1 + C.rp, Qt2 = Qt1 + C.qp; if (Rt2 >= w) { Rt2 -= w; Qt2++; }
   uint32_t Rt3 = Rt2 + C.rp, Qt3 = Qt2 + C.qp; if (Rt3 >= w) { Rt3 -= w; Qt3++; }
-  uint32_t Q1 = C.qp, R1 = C.rp;  // X1 = B_k + proton
+  const uint32_t off = 1u - t0;                 // bins are taken relative to the tile
+  uint32_t Q1 = C.qp, R1 = C.rp;                // X = B_k + proton
   int64_t acc = 0;
-  const uint32_t nsplit = len > 0 ? len - 1 : 0;            // residues 0..len-2 are followed by a split
+  const uint32_t nsplit = len > 0 ? len - 1 : 0;                    // residues 0..len-2 are followed by a split
   const uint32_t nchunk = maxlen > 1 ? (maxlen - 1 + 15) >> 4 : 0;  // warp-uniform
   for (uint32_t c = 0; c < nchunk; c++) {
     const uint4 v = __ldg(row + c);
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const uint32_t i = c * 16 + j;
       const uint32_t code = (words[j >> 2] >> (8 * (j & 3))) & 31u;
-      uint32_t q = __shfl_sync(0xffffffffu, lq, code), r = __shfl_sync(0xffffffffu, lr, code);
+      uint32_t qr = __shfl_sync(0xffffffffu, lqr, code);
       if (HASVAR) {
-        uint32_t q2 = __shfl_sync(0xffffffffu, lvq, code), r2 = __shfl_sync(0xffffffffu, lvr, code);
-        if ((mask >> i) & 1) { q = q2; r = r2; }
+        const uint32_t qr2 = __shfl_sync(0xffffffffu, lvqr, code);
+        if ((mask >> (c * 16 + j)) & 1) qr = qr2;
       }
-      const bool on = i < nsplit;
-      Q1 += q; R1 += r; if (R1 >= w) { R1 -= w; Q1++; }
+      const bool on = c * 16 + j < nsplit;
+      Q1 += qr >> rbits; R1 += qr & rmask;
+      if (R1 >= w) { R1 -= w; Q1++; }
       {  // fragment charge 1
-        uint32_t bb = Q1 + 1 - t0;
-        uint32_t yb = Qt1 - Q1 - (Rt1 < R1 ? 1u : 0u) + 1 - t0;
-        if (on && bb < tn) acc += tab[bb];
-        if (on && yb < tn) acc += tab[yb];
+        const uint32_t bb = Q1 + off;
+        const uint32_t yb = Qt1 - Q1 - (Rt1 < R1 ? 1u : 0u) + off;
+        MD_GATHER(bb); MD_GATHER(yb);
       }
       if (NCH >= 2) {
-        uint32_t r2 = R1 + C.rp, q2 = Q1 + C.qp + (r2 >= w ? 1u : 0u);
-        uint32_t bb = (q2 >> 1) + 1 - t0;
-        uint32_t yb = ((Qt2 - Q1 - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1 - t0;
-        if (on && bb < tn) acc += tab[bb];
-        if (on && yb < tn) acc += tab[yb];
+        const uint32_t r2 = R1 + C.rp, q2 = Q1 + C.qp + (r2 >= w ? 1u : 0u);
+        const uint32_t bb = (q2 >> 1) + off;
+        const uint32_t yb = ((Qt2 - Q1 - (Rt2 < R1 ? 1u : 0u)) >> 1) + off;
+        MD_GATHER(bb); MD_GATHER(yb);
       }
       if (NCH >= 3) {
-        uint32_t r3 = R1 + C.r2p, q3 = Q1 + C.q2p + (r3 >= w ? 1u : 0u);
-        uint32_t bb = div3(q3) + 1 - t0;
-        uint32_t yb = div3(Qt3 - Q1 - (Rt3 < R1 ? 1u : 0u)) + 1 - t0;
-        if (on && bb < tn) acc += tab[bb];
-        if (on && yb < tn) acc += tab[yb];
+        const uint32_t r3 = R1 + C.r2p, q3 = Q1 + C.q2p + (r3 >= w ? 1u : 0u);
+        const uint32_t bb = div3(q3) + off;
+        const uint32_t yb = div3(Qt3 - Q1 - (Rt3 < R1 ? 1u : 0u)) + off;
+        MD_GATHER(bb); MD_GATHER(yb);
       }
     }
   }
   return acc;
 }
 
-struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; int64_t* score; };
+struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; };
 
 __device__ __forceinline__ CandRef cand_ref(const ScoreArgs& A, uint32_t s, uint32_t v, uint32_t nt, uint64_t t0c, uint32_t n_per) {
   CandRef r;
   if (v < nt) {
     const uint64_t c = t0c + v, d = A.cand_desc[c];
     r.row = reinterpret_cast<const uint4*>(A.idx_rows + (d & 0xFFFFFFFFFFull) * 16);
-    r.len = (uint32_t)(d >> 40) & 0xFF; r.mask = A.cand_mask[c]; r.modw = A.cand_w[c]; r.score = A.tscore + c;
+    r.len = (uint32_t)(d >> 40) & 0xFF; r.mask = A.cand_mask[c]; r.modw = A.cand_w[c];
   } else {
     const uint64_t j = (uint64_t)s * n_per + (v - nt);
     r.row = reinterpret_cast<const uint4*>(A.dec_rows + j * MD_DECOY_ROW);
-    r.len = A.dec_len[j]; r.mask = A.dec_mask[j]; r.modw = A.dec_w[j]; r.score = A.dscore + j;
+    r.len = A.dec_len[j]; r.mask = A.dec_mask[j]; r.modw = A.dec_w[j];
   }
   return r;
 }
 
-template <int NCH, bool HASVAR>
-__device__ void score_tile(const ScoreArgs& A, const ScoreConst& C, uint32_t s, uint32_t nt, uint32_t nd, uint64_t t0c, const int32_t* tab, uint32_t t0,
-                           uint32_t tn, bool first, uint32_t lq, uint32_t lr, uint32_t lvq, uint32_t lvr) {
-  const uint32_t ncand = nt + nd;
-  const uint32_t rounds = (ncand + kScoreThreads - 1) / kScoreThreads;
-  for (uint32_t it = 0; it < rounds; it++) {
-    const uint32_t v = it * kScoreThreads + threadIdx.x;
-    const bool live = v < ncand;
-    CandRef r; r.row = reinterpret_cast<const uint4*>(A.idx_rows); r.len = 0; r.mask = 0; r.modw = 0; r.score = nullptr;
-    if (live) r = cand_ref(A, s, v, nt, t0c, C.n_per);
-    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, r.len);
-    int64_t part = score_one<NCH, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab, t0, tn, C, lq, lr, lvq, lvr);
-    if (live) *r.score = first ? part : *r.score + part;
-  }
+// PSM order: raw score descending, candidate ordinal ascending  <=>  key descending
+constexpr int64_t kKeyBias = 1ll << 39;
+__device__ __forceinline__ unsigned long long psm_key(int64_t score, uint32_t v) {
+  return ((unsigned long long)(score + kKeyBias) << 24) | (unsigned long long)(0xFFFFFFu - v);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+  const uint32_t hi = (uint32_t)(k >> 32);
+  const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? (uint32_t)k : 0u);
+  return ((unsigned long long)mh << 32) | ml;
 }
 
-// ordering of PSMs: raw score descending, candidate ordinal ascending
-__device__ __forceinline__ bool psm_better(int64_t sa, uint32_t va, int64_t sb, uint32_t vb) { return sa > sb || (sa == sb && va < vb); }
+// first index in [0, n) with a[i] >= x
+__device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* a, uint32_t n, int32_t x) {
+  uint32_t l = 0, h = n;
+  while (l < h) { const uint32_t m = (l + h) >> 1; if (a[m] < x) l = m + 1; else h = m; }
+  return l;
+}
+
+struct SpecShared {
+  uint32_t work[2];
+  unsigned long long wkey[2][kScoreThreads / 32];
+  unsigned long long top[kMaxTopK];
+};
 
 template <bool HASVAR>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C) {
-  extern __shared__ __align__(16) int32_t tab[];
-  __shared__ uint32_t s_work;
-  __shared__ int64_t s_rs[kScoreThreads / 32];
-  __shared__ uint32_t s_rv[kScoreThreads / 32];
-  __shared__ int64_t s_best_s; __shared__ uint32_t s_best_v;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per-letter (q, r) tables in registers: lane = residue code
-  const uint32_t lq = C.tq[lane], lr = C.tr[lane], lvq = C.vq[lane], lvr = C.vr[lane];
+  extern __shared__ __align__(16) int32_t tab[];                     // kTileBins
+  int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins + 4); // kCandChunk (tab[kTileBins] = always-zero sentinel slot)
+  int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // kPeakCap
+  int32_t* s_yq = s_bin + kPeakCap;                                  // kPeakCap
+  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_yq + kPeakCap);    // kPeakCap + 1
+  __shared__ SpecShared sh;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t NW = kScoreThreads / 32;
+  // per-letter packed (q, r) tables in registers: lane = residue code
+  const uint32_t lqr = C.tqr[lane], lvqr = C.vqr[lane];
   unsigned long long my_pairs = 0, my_bytes = 0;
 
-  for (;;) {
-    if (threadIdx.x == 0) s_work = atomicAdd(A.work, 1u);
-    __syncthreads();
-    const uint32_t s = s_work;
-    __syncthreads();
+  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
+  if (tid == 0) { sh.work[0] = atomicAdd(A.work, 1u); tab[kTileBins] = 0; }
+  __syncthreads();
+  for (uint32_t it = 0;; it++) {
+    const uint32_t s = sh.work[it & 1];
     if (s >= A.n_spec) break;
+    if (tid == 0) sh.work[(it + 1) & 1] = atomicAdd(A.work, 1u);     // next spectrum, read after this one's barriers
     const md_precursor pr = A.prec[s];
     const uint64_t t0c = A.cand_off[s];
     const uint32_t nt = (uint32_t)(A.cand_off[s + 1] - t0c);
     const uint32_t nd = A.dec_count ? A.dec_count[s] : 0;
     const uint32_t ncand = nt + nd;
     const int32_t hbin = A.pk_hbin[s];
-    const bool scored = hbin >= 0;
+    const uint32_t npk = A.pk_count[s];
+    const uint64_t pk0 = A.peak_off[s];
+    const uint32_t K = C.top_k;
     uint32_t nch = pr.charge > 1 ? pr.charge - 1 : 1;
     if (nch > C.max_frag_charge) nch = C.max_frag_charge;
     if (nch < 1) nch = 1;
+    const uint32_t NB = hbin >= 0 ? (uint32_t)hbin + kXcorrOffset + 1 : 0;  // table bins [0, NB)
+    bool scored = hbin >= 0;
+    if (NB > kMaxBins || ncand > 0xFFFFFFu) { if (tid == 0) *A.error = 1; scored = false; }
 
-    if (!scored || ncand == 0) {
-      for (uint32_t v = threadIdx.x; v < ncand; v += kScoreThreads) {
-        CandRef r = cand_ref(A, s, v, nt, t0c, C.n_per);
-        *r.score = 0;
-      }
-    } else {
-      for (uint32_t v = threadIdx.x; v < ncand; v += kScoreThreads) {
-        const uint32_t len = v < nt ? (uint32_t)(A.cand_desc[t0c + v] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (v - nt)];
-        my_pairs++; my_bytes += 14 + len;
-      }
-      const uint32_t NB = (uint32_t)hbin + kXcorrOffset + 1;  // table bins [0, NB)
-      const uint64_t pk0 = A.peak_off[s]; const uint32_t npk = A.pk_count[s];
-      bool first = true;
-      for (uint32_t t0 = 0; t0 < NB; t0 += kTileBins) {
-        const uint32_t tn = min(kTileBins, NB - t0);
-        // peaks that touch this tile: bin in [t0 - 75, t0 + tn + 75)
-        uint32_t pa, pb;
-        {
-          const int32_t lo_bin = (int32_t)t0 - kXcorrOffset, hi_bin = (int32_t)(t0 + tn) + kXcorrOffset;
-          uint32_t l = 0, h = npk;
-          while (l < h) { uint32_t m = (l + h) >> 1; if (A.pk_bin[pk0 + m] < lo_bin) l = m + 1; else h = m; }
-          pa = l; h = npk;
-          while (l < h) { uint32_t m = (l + h) >> 1; if (A.pk_bin[pk0 + m] < hi_bin) l = m + 1; else h = m; }
-          pb = l;
-        }
-        if (pa == pb) {  // an all-zero tile adds nothing
-          if (first) {
-            for (uint32_t v = threadIdx.x; v < ncand; v += kScoreThreads) { CandRef r = cand_ref(A, s, v, nt, t0c, C.n_per); *r.score = 0; }
-            first = false;
+    // ---- stage the binned spectrum
+    const int32_t* pbin = A.pk_bin + pk0; const int32_t* pyq = A.pk_yq + pk0; const uint32_t* ppre = A.pk_pre + pk0 + s;
+    if (scored && npk <= kPeakCap) {
+      for (uint32_t i = tid; i < npk; i += kScoreThreads) { s_bin[i] = pbin[i]; s_yq[i] = pyq[i]; }
+      for (uint32_t i = tid; i <= npk; i += kScoreThreads) s_pre[i] = ppre[i];
+      pbin = s_bin; pyq = s_yq; ppre = s_pre;
+    }
+    for (uint32_t r = tid; r < K; r += kScoreThreads) sh.top[r] = 0ull;
+    __syncthreads();
+
+    for (uint32_t c0 = 0; c0 < ncand || c0 == 0; c0 += kCandChunk) {
+      const uint32_t cn = min(kCandChunk, ncand - c0);
+      for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
+      bool counted = false;
+      if (scored && cn) {
+        for (uint32_t t0 = 0; t0 < NB; t0 += kTileBins) {
+          const uint32_t tn = min(kTileBins, NB - t0);
+          // peaks whose window edges can reach this tile: bin in [t0 - 230, t0 + tn + 76)
+          const uint32_t pa = lower_bound_i32(pbin, npk, (int32_t)t0 - 230);
+          const uint32_t pb = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1);
+          if (pa == pb) continue;  // an all-zero tile adds nothing
+          // (1) zero the tile
+          {
+            uint4* z = reinterpret_cast<uint4*>(tab);
+            const uint32_t n4 = (tn + 3) >> 2;
+            for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
           }
-          continue;
+          __syncthreads();
+          // (2) paint -S[b], S[b] = sum of y over bins [b-75, b+75]: piecewise constant between window edges.
+          //     Edge 2k   = entry of peak pa+k at x = bin-75: S = pre[p+1] - pre[lo], lo = first peak with bin >= x-75
+          //     Edge 2k+1 = exit  of peak pa+k at x = bin+76: S = pre[hi] - pre[p+1], hi = first peak with bin > x+75
+          //     and the segment runs to the next edge of either kind.
+          for (uint32_t e = warp; e < 2 * (pb - pa); e += NW) {
+            const uint32_t p = pa + (e >> 1);
+            const int32_t bp = pbin[p];
+            int32_t xa, xb; uint32_t S;
+            if ((e & 1) == 0) {
+              uint32_t lo = p;
+              while (lo > 0 && pbin[lo - 1] >= bp - 2 * kXcorrOffset) lo--;
+              S = ppre[p + 1] - ppre[lo];
+              xa = bp - kXcorrOffset;
+              xb = pbin[lo] + kXcorrOffset + 1;                                  // next exit
+              if (p + 1 < npk) xb = min(xb, pbin[p + 1] - kXcorrOffset);         // next entry
+            } else {
+              uint32_t hi = p + 1;
+              while (hi < npk && pbin[hi] <= bp + 2 * kXcorrOffset + 1) hi++;
+              S = ppre[hi] - ppre[p + 1];
+              xa = bp + kXcorrOffset + 1;
+              xb = hi < npk ? pbin[hi] - kXcorrOffset : INT32_MAX;               // next entry
+              if (p + 1 < npk) xb = min(xb, pbin[p + 1] + kXcorrOffset + 1);     // next exit
+            }
+            if (S == 0) continue;
+            const int32_t a = max(xa, (int32_t)t0), b = min(xb, (int32_t)(t0 + tn));
+            const int32_t val = -(int32_t)S;
+            for (int32_t x = a + (int32_t)lane; x < b; x += 32) tab[x - (int32_t)t0] = val;
+          }
+          __syncthreads();
+          // (3) the peak's own bin: + 151*y
+          for (uint32_t i = tid; i < pb - pa; i += kScoreThreads) {
+            const uint32_t x = (uint32_t)pbin[pa + i] - t0;
+            if (x < tn) tab[x] += 151 * pyq[pa + i];
+          }
+          __syncthreads();
+          // (4) score the chunk against the tile
+          for (uint32_t v0 = 0; v0 < cn; v0 += kScoreThreads) {
+            const uint32_t v = v0 + tid;
+            const bool live = v < cn;
+            CandRef r; r.row = reinterpret_cast<const uint4*>(A.idx_rows); r.len = 0; r.mask = 0; r.modw = 0;
+            if (live) r = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
+            if (live && !counted) { my_pairs++; my_bytes += 14 + r.len; }
+            const uint32_t maxlen = __reduce_max_sync(0xffffffffu, r.len);
+            int64_t part;
+            switch (nch) {
+              case 1: part = score_one<1, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
+              case 2: part = score_one<2, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
+              default: part = score_one<3, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
+            }
+            if (live) s_score[v] += part;
+          }
+          counted = true;
+          __syncthreads();
         }
-        // zero the tile
-        {
-          uint4* z = reinterpret_cast<uint4*>(tab);
-          const uint32_t n4 = (tn + 3) >> 2;
-          for (uint32_t i = threadIdx.x; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        // expand: T[b] += 150*y at the peak bin, -= y at the 150 neighbours
-        for (uint32_t p = pa + warp; p < pb; p += kScoreThreads / 32) {
-          const int32_t bin = A.pk_bin[pk0 + p], yq = A.pk_yq[pk0 + p];
-          for (int o = (int)lane - kXcorrOffset; o <= kXcorrOffset; o += 32) {
-            const uint32_t idx = (uint32_t)(bin + o) - t0;
-            if (idx < tn) atomicAdd(&tab[idx], o == 0 ? 150 * yq : -yq);
+        if (!counted) {  // every tile was empty: the pairs were still scored (0)
+          for (uint32_t v = tid; v < cn; v += kScoreThreads) {
+            const uint32_t u = c0 + v;
+            const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
+            my_pairs++; my_bytes += 14 + len;
           }
         }
-        __syncthreads();
-        switch (nch) {
-          case 1: score_tile<1, HASVAR>(A, C, s, nt, nd, t0c, tab, t0, tn, first, lq, lr, lvq, lvr); break;
-          case 2: score_tile<2, HASVAR>(A, C, s, nt, nd, t0c, tab, t0, tn, first, lq, lr, lvq, lvr); break;
-          default: score_tile<3, HASVAR>(A, C, s, nt, nd, t0c, tab, t0, tn, first, lq, lr, lvq, lvr); break;
+      }
+      // ---- raw scores of every candidate (on request)
+      if (A.tscore) {
+        for (uint32_t v = tid; v < cn; v += kScoreThreads) {
+          const uint32_t u = c0 + v;
+          if (u < nt) A.tscore[t0c + u] = s_score[v]; else A.dscore[(uint64_t)s * C.n_per + (u - nt)] = s_score[v];
         }
-        first = false;
+      }
+      // ---- top-k of (this chunk's candidates) U (best of the earlier chunks): K rounds of block-wide max
+      if (scored && cn && K) {
+        // scores -> keys, in place; slots cn..cn+K-1 (conceptually) hold the running list, owned by threads < K
+        for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = (int64_t)psm_key(s_score[v], c0 + v);
+        unsigned long long carry = tid < K ? sh.top[tid] : 0ull;   // this thread's entry of the running list
+        __syncthreads();
+        unsigned long long prev = ~0ull;
+        for (uint32_t r = 0; r < K; r++) {
+          unsigned long long best = (carry < prev) ? carry : 0ull;
+          for (uint32_t v = tid; v < cn; v += kScoreThreads) {
+            const unsigned long long k = (unsigned long long)s_score[v];
+            if (k < prev && k > best) best = k;
+          }
+          best = warp_max_u64(best);
+          if (lane == 0) sh.wkey[r & 1][warp] = best;
+          __syncthreads();
+          unsigned long long m = lane < NW ? sh.wkey[r & 1][lane] : 0ull;
+          m = warp_max_u64(m);
+          if (tid == 0) sh.top[r] = m;
+          prev = m;
+          if (m == 0ull) break;   // fewer candidates than rows (uniform: every thread sees the same m)
+        }
         __syncthreads();
       }
     }
-    __syncthreads();
-    // ---- per-spectrum top-k (PSM rows) ----
-    const uint32_t K = C.top_k;
-    int64_t prev_s = INT64_MAX; uint32_t prev_v = 0; bool have_prev = false;
-    for (uint32_t r = 0; r < K; r++) {
-      int64_t bs = INT64_MIN; uint32_t bv = 0xFFFFFFFFu;
-      if (scored) {
-        for (uint32_t v = threadIdx.x; v < ncand; v += kScoreThreads) {
-          const int64_t sc = v < nt ? A.tscore[t0c + v] : A.dscore[(uint64_t)s * C.n_per + (v - nt)];
-          if (have_prev && !psm_better(prev_s, prev_v, sc, v)) continue;  // already reported
-          if (bv == 0xFFFFFFFFu || psm_better(sc, v, bs, bv)) { bs = sc; bv = v; }
-        }
+    // ---- PSM rows
+    for (uint32_t r = tid; r < K; r += kScoreThreads) {
+      md_psm row;
+      row.spectrum_id = pr.spectrum_id; row.rank = 0; row.is_decoy = 0; row.charge = (uint8_t)pr.charge; row.candidate = 0; row.var_mask = 0;
+      row.mod_weight = 0; row.raw_score = 0; row.score = 0.0f; row.n_targets = nt; row.n_decoys = nd; row._pad = 0;
+      const unsigned long long k = scored ? sh.top[r] : 0ull;
+      if (k != 0ull) {
+        const uint32_t bv = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFull);
+        const int64_t bs = (int64_t)(k >> 24) - kKeyBias;
+        row.rank = (uint16_t)(r + 1); row.raw_score = bs;
+        row.score = (float)(0.005 * (double)bs / (150.0 * 65536.0));
+        if (bv < nt) { row.is_decoy = 0; row.candidate = (uint64_t)A.cand_pep[t0c + bv] + 1; row.var_mask = A.cand_mask[t0c + bv]; row.mod_weight = A.cand_w[t0c + bv]; }
+        else { const uint64_t j = (uint64_t)s * C.n_per + (bv - nt); row.is_decoy = 1; row.candidate = bv - nt; row.var_mask = A.dec_mask[j]; row.mod_weight = A.dec_w[j]; }
       }
-      for (int o = 16; o; o >>= 1) {
-        int64_t os = __shfl_xor_sync(0xffffffffu, bs, o); uint32_t ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        if (ov != 0xFFFFFFFFu && (bv == 0xFFFFFFFFu || psm_better(os, ov, bs, bv))) { bs = os; bv = ov; }
-      }
-      if (lane == 0) { s_rs[warp] = bs; s_rv[warp] = bv; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int q = 1; q < kScoreThreads / 32; q++)
-          if (s_rv[q] != 0xFFFFFFFFu && (bv == 0xFFFFFFFFu || psm_better(s_rs[q], s_rv[q], bs, bv))) { bs = s_rs[q]; bv = s_rv[q]; }
-        s_best_s = bs; s_best_v = bv;
-        md_psm row;
-        row.spectrum_id = pr.spectrum_id; row.rank = 0; row.is_decoy = 0; row.charge = (uint8_t)pr.charge; row.candidate = 0; row.var_mask = 0;
-        row.mod_weight = 0; row.raw_score = 0; row.score = 0.0f; row.n_targets = nt; row.n_decoys = nd; row._pad = 0;
-        if (bv != 0xFFFFFFFFu) {
-          row.rank = (uint16_t)(r + 1); row.raw_score = bs;
-          row.score = (float)(0.005 * (double)bs / (150.0 * 65536.0));
-          if (bv < nt) { row.is_decoy = 0; row.candidate = (uint64_t)A.cand_pep[t0c + bv] + 1; row.var_mask = A.cand_mask[t0c + bv]; row.mod_weight = A.cand_w[t0c + bv]; }
-          else { const uint64_t j = (uint64_t)s * C.n_per + (bv - nt); row.is_decoy = 1; row.candidate = bv - nt; row.var_mask = A.dec_mask[j]; row.mod_weight = A.dec_w[j]; }
-        }
-        A.psm[(uint64_t)s * K + r] = row;
-      }
-      __syncthreads();
-      prev_s = s_best_s; prev_v = s_best_v; have_prev = prev_v != 0xFFFFFFFFu;
-      if (!have_prev) {  // fewer candidates than rows: the remaining rows are empty
-        if (threadIdx.x == 0) {
-          for (uint32_t r2 = r + 1; r2 < K; r2++) {
-            md_psm row;
-            row.spectrum_id = pr.spectrum_id; row.rank = 0; row.is_decoy = 0; row.charge = (uint8_t)pr.charge; row.candidate = 0; row.var_mask = 0;
-            row.mod_weight = 0; row.raw_score = 0; row.score = 0.0f; row.n_targets = nt; row.n_decoys = nd; row._pad = 0;
-            A.psm[(uint64_t)s * K + r2] = row;
-          }
-        }
-        break;
-      }
+      A.psm[(uint64_t)s * K + r] = row;
     }
     __syncthreads();
   }
@@ -414,24 +494,26 @@ void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p,
   MD_LAUNCH(ctx, k_precursors, blocks(S.n), 256, 0, S.pmz, S.charge, S.sid, S.n, p.lower_ppm, p.upper_ppm, p.abs_lower_uda, p.abs_upper_uda, id_base, ctx->ws.prec.p);
 }
 
-void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev) {
+void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev, bool want_all) {
   IdentifyWorkspace& W = ctx->ws;
   const uint32_t n = S.n;
   if (!n) return;
   const int64_t w = (int64_t)llround(p.fragment_tolerance * 1000000.0);
   const uint32_t mfc = p.max_fragment_charge ? p.max_fragment_charge : 3;
   MD_REQUIRE(mfc <= 3, MD_ERR_UNSUPPORTED, "max_fragment_charge > 3 (the reference fixes it to 3: comet_parameter.rs:55)");
+  MD_REQUIRE(p.top_k <= kMaxTopK, MD_ERR_UNSUPPORTED, "top_k > 128");
   // ---- K4a
-  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
-  DevBuf<int> d_flag; d_flag.need(1);
-  MD_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), ctx->stream));
+  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_pre.need(n_peaks + n + 2); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
+  DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(2);
+  MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 2 * sizeof(int), ctx->stream));
   MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), ctx->stream));
   MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
-            W.pk_count.p, W.pk_hbin.p, d_flag.p);
+            W.pk_pre.p, W.pk_count.p, W.pk_hbin.p, d_flag.p);
   // ---- K4
   ScoreConst C;
   memset(&C, 0, sizeof(C));
   C.w = (uint32_t)w; C.max_frag_charge = mfc; C.top_k = p.top_k; C.n_per = n_per;
+  C.rbits = 1; while ((1u << C.rbits) < C.w) C.rbits++;   // r < w <= 2^rbits
   split_qr(MD_PROTON_UDA, C.w, &C.qp, &C.rp);
   split_qr(2 * MD_PROTON_UDA, C.w, &C.q2p, &C.r2p);
   bool has_var = false;
@@ -439,25 +521,33 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     int64_t m = c < MD_NCODES ? ctx->mods.mass[c] : 0;
     int64_t f = (c < MD_NCODES && ctx->mods.has_fix[c]) ? ctx->mods.fix[c] : 0;
     int64_t v = (c < MD_NCODES && ctx->mods.has_var[c]) ? ctx->mods.var[c] : 0;
-    split_qr(m + f, C.w, &C.tq[c], &C.tr[c]);
-    split_qr(m + f + v, C.w, &C.vq[c], &C.vr[c]);
+    uint32_t q, r;
+    split_qr(m + f, C.w, &q, &r);
+    MD_REQUIRE(((uint64_t)q << C.rbits) < (1ull << 31), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
+    C.tqr[c] = (q << C.rbits) | r;
+    split_qr(m + f + v, C.w, &q, &r);
+    MD_REQUIRE(((uint64_t)q << C.rbits) < (1ull << 31), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
+    C.vqr[c] = (q << C.rbits) | r;
     if (c < MD_NCODES && ctx->mods.has_var[c]) has_var = true;
   }
   uint64_t n_targets = 0;
-  MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  MD_CUDA(cudaStreamSynchronize(ctx->stream));
-  W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1);
+  if (want_all) {
+    MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1);
+  }
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
   W.stat64.need(2);
   MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   ScoreArgs A;
-  A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
+  A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_pre = W.pk_pre.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
   A.cand_off = W.cand_off.p; A.cand_desc = W.cand_desc.p; A.cand_mask = W.cand_mask.p; A.cand_w = W.cand_w.p; A.cand_pep = W.cand_pep.p;
   A.idx_rows = ctx->index.rows.p;
   A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
-  A.tscore = W.tscore.p; A.dscore = W.dscore.p; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
-  const size_t smem = (size_t)kTileBins * sizeof(int32_t);
+  A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
+  A.error = d_flag.p + 1;
+  const size_t smem = ((size_t)kTileBins + 4) * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4;
   const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
   MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (has_var) {
@@ -469,8 +559,11 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   }
   MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
   unsigned long long h_stat[2] = {0, 0};
+  int h_flag[2] = {0, 0};
   MD_CUDA(cudaMemcpyAsync(h_stat, W.stat64.p, sizeof(h_stat), cudaMemcpyDeviceToHost, ctx->stream));
-  const int unsorted = d2h_scalar(ctx, d_flag.p);
+  MD_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof(h_flag), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaStreamSynchronize(ctx->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->acc_ms_kscore += ms; ctx->acc_pairs += h_stat[0]; ctx->acc_score_bytes += h_stat[1]; }
-  MD_REQUIRE(!unsorted, MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
+  MD_REQUIRE(!h_flag[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
+  MD_REQUIRE(!h_flag[1], MD_ERR_UNSUPPORTED, "a spectrum needs more than 2^30 fragment bins or has more than 2^24 candidates");
 }
