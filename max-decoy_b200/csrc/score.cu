@@ -29,12 +29,17 @@ namespace {
 inline uint32_t blocks(uint64_t n, uint32_t bs = 256) { return (uint32_t)((n + bs - 1) / bs); }
 
 constexpr int kXcorrOffset = 75;
-constexpr int kScoreThreads = 1024;
+#ifndef MD_SCORE_THREADS
+#define MD_SCORE_THREADS 768
+#endif
+constexpr int kScoreThreads = MD_SCORE_THREADS;
 constexpr uint32_t kTileBins = 49152;     // 192 KiB of int32 per CTA
 constexpr uint32_t kCandChunk = 1536;     // candidates whose partial scores stay in shared memory across tiles
 constexpr uint32_t kPeakCap = 1024;       // binned peaks staged in shared memory (larger spectra read them from HBM)
-constexpr uint32_t kMaxBins = 1u << 30;   // table bins per spectrum (bins are 32-bit)
+constexpr uint32_t kMaxBins = 1u << 26;   // table bins per spectrum (byte offsets 4*bin must stay far below kStop4)
 constexpr uint32_t kMaxTopK = 128;
+constexpr uint32_t kTileCache = 32;
+constexpr uint32_t kFastTopK = 8;
 
 // ------------------------------------------------------------------------------------------------
 // precursor windows: tasks/identification.rs:203-211 (utility/mod.rs:9-11; models/mass/mod.rs:6-8,14-16)
@@ -171,11 +176,10 @@ __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const doubl
 // ------------------------------------------------------------------------------------------------
 struct ScoreConst {
   uint32_t w;                 // bin width, uDa
-  uint32_t rbits;             // remainder field width of the packed tables
   uint32_t qp, rp;            // proton  = qp*w + rp
   uint32_t q2p, r2p;          // 2*proton
-  uint32_t tqr[32];           // per residue code: (mass + fixed delta) = q*w + r, packed q << rbits | r
-  uint32_t vqr[32];           // per residue code: (mass + fixed + variable delta)
+  uint32_t tq4[32], tr[32];   // per residue code: (mass + fixed delta) = q*w + r; tq4 = 4*q (table byte offsets)
+  uint32_t vq4[32], vr[32];   // per residue code: (mass + fixed + variable delta)
   uint32_t max_frag_charge;
   uint32_t top_k, n_per;
 };
@@ -191,6 +195,7 @@ struct ScoreArgs {
   uint32_t* work;
   unsigned long long* stat64;  // [0] pairs scored, [1] algorithmic bytes (14 + len per pair)
   int* error;                  // set when a spectrum needs more table bins than kMaxBins
+  unsigned long long* timing;  // MD_SCORE_TIMING=1: per-phase SM cycles summed over CTAs (thread 0's clock), else NULL
 };
 
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAAAAABu) >> 1; }
@@ -198,7 +203,7 @@ __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAA
 // Raw score of one candidate against the table tile [t0, t0+tn).
 //   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
 // with X = B_k + proton kept as (Q, R), X = Q*w + R, so no fragment needs a division.
-// one table gather, branch-free: out-of-range (or switched-off) fragments read the always-zero sentinel slot
+// one table gather, branch-free: the byte offset is clamped to the always-zero slot behind the tile
 __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
   int32_t v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -207,59 +212,88 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
 __device__ __forceinline__ void acc_wide(int64_t& acc, int32_t v) {  // acc += v as one IMAD.WIDE
   asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(acc) : "r"(v));
 }
-#define MD_GATHER(bin) acc_wide(acc, lds_s32(tab_s + 4u * ((on && (bin) < tn) ? (bin) : kTileBins)))
+#define MD_GATHER(acc, off4) acc_wide(acc, lds_s32(tab_s + min((uint32_t)(off4), tn4)))
+struct LaneTab { uint32_t q4, r, vq4, vr; };   // lane = residue code
+constexpr uint32_t kStop4 = 1u << 30;           // added to the running offset at the last residue: every later bin misses
 
-template <int NCH, bool HASVAR>
-__device__ __forceinline__ int64_t score_one(const uint4* __restrict__ row, uint32_t len, uint64_t mask, int64_t modw, uint32_t maxlen,
-                                             uint32_t tab_s, uint32_t t0, uint32_t tn, const ScoreConst& C, uint32_t lqr, uint32_t lvqr) {
-  const uint32_t w = C.w, rbits = C.rbits, rmask = (1u << rbits) - 1u;
-  // T_c = modw + (c+1)*proton  ->  (Qt, Rt)
-  const uint64_t T1 = (uint64_t)modw + 2ull * MD_PROTON_UDA;
-  const uint32_t Qt1 = (uint32_t)(T1 / w), Rt1 = (uint32_t)(T1 - (uint64_t)Qt1 * w);
-  uint32_t Rt2 = Rt1 + C.rp, Qt2 = Qt1 + C.qp; if (Rt2 >= w) { Rt2 -= w; Qt2++; }
-  uint32_t Rt3 = Rt2 + C.rp, Qt3 = Qt2 + C.qp; if (Rt3 >= w) { Rt3 -= w; Qt3++; }
-  const uint32_t off = 1u - t0;                 // bins are taken relative to the tile
-  uint32_t Q1 = C.qp, R1 = C.rp;                // X = B_k + proton
-  int64_t acc = 0;
-  const uint32_t nsplit = len > 0 ? len - 1 : 0;                    // residues 0..len-2 are followed by a split
-  const uint32_t nchunk = maxlen > 1 ? (maxlen - 1 + 15) >> 4 : 0;  // warp-uniform
-  for (uint32_t c = 0; c < nchunk; c++) {
-    const uint4 v = __ldg(row + c);
-    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; };
+
+// Raw scores of NC candidates of one thread against the table tile [t0, t0+tn).
+//   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
+// with X = B_k + proton kept as (Q, R), X = Q*w + R, R < w, so no fragment needs a division.  Q is carried as the byte
+// offset of the charge-1 b bin in the tile (QB = 4*(Q + 1 - t0), wrapping); bins outside the tile wrap or overshoot and
+// are clamped onto the zero slot tab[tn] by one unsigned min.  The last residue is never a prefix: at position len-1
+// kStop4 is added to QB, which throws every later b and y bin of every charge out of the tile -- no per-residue
+// length predicate.  The loop runs in 4-residue words up to the longest candidate of the warp.
+template <int NCH, bool HASVAR, int NC>
+__device__ __forceinline__ void score_multi(const CandRef (&cr)[NC], uint32_t maxlen, uint32_t tab_s, uint32_t t0, uint32_t tn, const ScoreConst& C,
+                                            const LaneTab& L, int64_t (&out)[NC]) {
+  const uint32_t w = C.w, tn4 = 4u * tn, off4 = 4u * (1u - t0);
+  const uint32_t K2 = 4u * C.qp - off4, K3 = 4u * C.q2p - off4;
+  const uint32_t nword = maxlen > 1 ? (maxlen - 1 + 3) >> 2 : 0;  // warp-uniform
+  uint32_t Y1[NC], Rt1[NC], Y2[NC], Rt2[NC], Y3[NC], Rt3[NC], QB[NC], R1[NC], nsplit[NC];
+  int64_t accb[NC], accy[NC];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const uint32_t code = (words[j >> 2] >> (8 * (j & 3))) & 31u;
-      uint32_t qr = __shfl_sync(0xffffffffu, lqr, code);
-      if (HASVAR) {
-        const uint32_t qr2 = __shfl_sync(0xffffffffu, lvqr, code);
-        if ((mask >> (c * 16 + j)) & 1) qr = qr2;
-      }
-      const bool on = c * 16 + j < nsplit;
-      Q1 += qr >> rbits; R1 += qr & rmask;
-      if (R1 >= w) { R1 -= w; Q1++; }
-      {  // fragment charge 1
-        const uint32_t bb = Q1 + off;
-        const uint32_t yb = Qt1 - Q1 - (Rt1 < R1 ? 1u : 0u) + off;
-        MD_GATHER(bb); MD_GATHER(yb);
-      }
-      if (NCH >= 2) {
-        const uint32_t r2 = R1 + C.rp, q2 = Q1 + C.qp + (r2 >= w ? 1u : 0u);
-        const uint32_t bb = (q2 >> 1) + off;
-        const uint32_t yb = ((Qt2 - Q1 - (Rt2 < R1 ? 1u : 0u)) >> 1) + off;
-        MD_GATHER(bb); MD_GATHER(yb);
-      }
-      if (NCH >= 3) {
-        const uint32_t r3 = R1 + C.r2p, q3 = Q1 + C.q2p + (r3 >= w ? 1u : 0u);
-        const uint32_t bb = div3(q3) + off;
-        const uint32_t yb = div3(Qt3 - Q1 - (Rt3 < R1 ? 1u : 0u)) + off;
-        MD_GATHER(bb); MD_GATHER(yb);
+  for (int i = 0; i < NC; i++) {
+    // T_c = modw + (c+1)*proton  ->  (Qt, Rt)
+    const uint64_t T1 = (uint64_t)cr[i].modw + 2ull * MD_PROTON_UDA;
+    uint32_t Qt1 = (uint32_t)(T1 / w); Rt1[i] = (uint32_t)(T1 - (uint64_t)Qt1 * w);
+    uint32_t Qt2 = Qt1 + C.qp; Rt2[i] = Rt1[i] + C.rp; if (Rt2[i] >= w) { Rt2[i] -= w; Qt2++; }
+    uint32_t Qt3 = Qt2 + C.qp; Rt3[i] = Rt2[i] + C.rp; if (Rt3[i] >= w) { Rt3[i] -= w; Qt3++; }
+    Y1[i] = 4u * Qt1 + 2u * off4;               // y1 offset = Y1 - QB - 4*borrow
+    Y2[i] = 4u * Qt2 + off4;                    // 4*(Qt2 - Q - borrow) = Y2 - QB - 4*borrow, then halved
+    Y3[i] = 4u * Qt3 + off4;
+    QB[i] = 4u * C.qp + off4; R1[i] = C.rp;     // X = B_k + proton
+    nsplit[i] = cr[i].len > 0 ? cr[i].len - 1 : 0;   // residues 0..len-2 are followed by a split
+    if (nsplit[i] == 0) QB[i] += kStop4;
+    accb[i] = 0; accy[i] = 0;
+  }
+  for (uint32_t c = 0; c * 4 < nword; c++) {
+    uint32_t words[NC][4];
+#pragma unroll
+    for (int i = 0; i < NC; i++) { const uint4 v = __ldg(cr[i].row + c); words[i][0] = v.x; words[i][1] = v.y; words[i][2] = v.z; words[i][3] = v.w; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (c * 4 + k >= nword) break;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int i = 0; i < NC; i++) {
+          const uint32_t pos = c * 16 + k * 4 + j;
+          const uint32_t code = words[i][k] >> (8 * j);            // (shfl takes the source lane modulo 32; codes are < 32)
+          uint32_t q4 = __shfl_sync(0xffffffffu, L.q4, code), r = __shfl_sync(0xffffffffu, L.r, code);
+          if (HASVAR) {
+            const uint32_t q4v = __shfl_sync(0xffffffffu, L.vq4, code), rv = __shfl_sync(0xffffffffu, L.vr, code);
+            if ((cr[i].mask >> pos) & 1) { q4 = q4v; r = rv; }
+          }
+          QB[i] += q4; R1[i] += r;
+          if (R1[i] >= w) { R1[i] -= w; QB[i] += 4u; }
+          {  // fragment charge 1
+            const uint32_t yb = Y1[i] - QB[i] - (Rt1[i] < R1[i] ? 4u : 0u);
+            MD_GATHER(accb[i], QB[i]); MD_GATHER(accy[i], yb);
+          }
+          if (NCH >= 2) {
+            const uint32_t x4 = QB[i] + K2 + (R1[i] + C.rp >= w ? 4u : 0u);
+            const uint32_t bb = ((x4 >> 1) & ~3u) + off4;
+            const uint32_t y4 = Y2[i] - QB[i] - (Rt2[i] < R1[i] ? 4u : 0u);
+            const uint32_t yb = ((y4 >> 1) & ~3u) + off4;
+            MD_GATHER(accb[i], bb); MD_GATHER(accy[i], yb);
+          }
+          if (NCH >= 3) {
+            const uint32_t x4 = QB[i] + K3 + (R1[i] + C.r2p >= w ? 4u : 0u);
+            const uint32_t bb = ((__umulhi(x4, 0xAAAAAAABu) >> 1) & ~3u) + off4;   // 4*floor(x/3) from 4*x
+            const uint32_t y4 = Y3[i] - QB[i] - (Rt3[i] < R1[i] ? 4u : 0u);
+            const uint32_t yb = ((__umulhi(y4, 0xAAAAAAABu) >> 1) & ~3u) + off4;
+            MD_GATHER(accb[i], bb); MD_GATHER(accy[i], yb);
+          }
+          if (pos + 1 == nsplit[i]) QB[i] += kStop4;   // the next residue is the last one
+        }
       }
     }
   }
-  return acc;
+#pragma unroll
+  for (int i = 0; i < NC; i++) out[i] = accb[i] + accy[i];
 }
-
-struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; };
 
 __device__ __forceinline__ CandRef cand_ref(const ScoreArgs& A, uint32_t s, uint32_t v, uint32_t nt, uint64_t t0c, uint32_t n_per) {
   CandRef r;
@@ -287,6 +321,22 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k)
   return ((unsigned long long)mh << 32) | ml;
 }
 
+__device__ __forceinline__ void write_psm_row(const ScoreArgs& A, const ScoreConst& C, const md_precursor& pr, uint32_t s, uint32_t r, unsigned long long k,
+                                              uint32_t nt, uint32_t nd, uint64_t t0c) {
+  md_psm row;
+  row.spectrum_id = pr.spectrum_id; row.rank = 0; row.is_decoy = 0; row.charge = (uint8_t)pr.charge; row.candidate = 0; row.var_mask = 0;
+  row.mod_weight = 0; row.raw_score = 0; row.score = 0.0f; row.n_targets = nt; row.n_decoys = nd; row._pad = 0;
+  if (k != 0ull) {
+    const uint32_t bv = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFull);
+    const int64_t bs = (int64_t)(k >> 24) - kKeyBias;
+    row.rank = (uint16_t)(r + 1); row.raw_score = bs;
+    row.score = (float)(0.005 * (double)bs / (150.0 * 65536.0));
+    if (bv < nt) { row.is_decoy = 0; row.candidate = (uint64_t)A.cand_pep[t0c + bv] + 1; row.var_mask = A.cand_mask[t0c + bv]; row.mod_weight = A.cand_w[t0c + bv]; }
+    else { const uint64_t j = (uint64_t)s * C.n_per + (bv - nt); row.is_decoy = 1; row.candidate = bv - nt; row.var_mask = A.dec_mask[j]; row.mod_weight = A.dec_w[j]; }
+  }
+  A.psm[(uint64_t)s * C.top_k + r] = row;
+}
+
 // first index in [0, n) with a[i] >= x
 __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* a, uint32_t n, int32_t x) {
   uint32_t l = 0, h = n;
@@ -294,10 +344,42 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* a, uint32_t n
   return l;
 }
 
+// One warp's share of a tile pass: units of 32 candidates in length-descending order (s_order), fetched from a
+// shared counter, so that warps stay busy until the chunk is done and every warp runs candidates of one length.
+template <int NCH, bool HASVAR>
+__device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst& C, uint32_t s, uint32_t c0, uint32_t cn, uint32_t nt, uint64_t t0c,
+                                            uint32_t tab_s, uint32_t t0, uint32_t tn, const LaneTab& L, int64_t* s_score,
+                                            const uint16_t* s_order, uint32_t* s_unit) {
+  const uint32_t lane = threadIdx.x & 31, units = (cn + 31) >> 5;
+  for (;;) {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(s_unit, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= units) break;
+    const uint32_t slot = u * 32 + lane;
+    CandRef cr[1];
+    cr[0].row = reinterpret_cast<const uint4*>(A.idx_rows); cr[0].len = 0; cr[0].mask = 0; cr[0].modw = 0;
+    uint32_t v = 0;
+    if (slot < cn) {
+      v = s_order[slot];
+      cr[0] = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
+    }
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr[0].len);
+    int64_t part[1];
+    score_multi<NCH, HASVAR, 1>(cr, maxlen, tab_s, t0, tn, C, L, part);
+    if (slot < cn) s_score[v] += part[0];
+  }
+}
+
 struct SpecShared {
   uint32_t work[2];
   unsigned long long wkey[2][kScoreThreads / 32];
   unsigned long long top[kMaxTopK];
+  long long tacc[8];
+  unsigned long long wtop[kScoreThreads / 32][kFastTopK];  // per-warp best keys, descending
+  uint32_t hist[64];        // candidates per length (counting sort of the chunk)
+  uint32_t unit;            // next unit of the current tile pass
+  uint32_t tile_pa[kTileCache], tile_pb[kTileCache];  // peaks that can reach each of the first tiles
 };
 
 template <bool HASVAR>
@@ -306,16 +388,20 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins + 4); // kCandChunk (tab[kTileBins] = always-zero sentinel slot)
   int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // kPeakCap
   int32_t* s_yq = s_bin + kPeakCap;                                  // kPeakCap
-  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_yq + kPeakCap);    // kPeakCap + 1
+  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_yq + kPeakCap);    // kPeakCap + 4
+  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_pre + kPeakCap + 4);  // kCandChunk: chunk slots in length-descending order
   __shared__ SpecShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t NW = kScoreThreads / 32;
   // per-letter packed (q, r) tables in registers: lane = residue code
-  const uint32_t lqr = C.tqr[lane], lvqr = C.vqr[lane];
-  unsigned long long my_pairs = 0, my_bytes = 0;
+  const LaneTab L{C.tq4[lane], C.tr[lane], C.vq4[lane], C.vr[lane]};
+  uint32_t my_pairs = 0, my_bytes = 0;   // per thread, summed at the end
+  long long t_last = A.timing ? clock64() : 0;
+  if (tid < 8) sh.tacc[tid] = 0;
+#define MD_TICK(k) do { if (A.timing && tid == 0) { const long long now_ = clock64(); sh.tacc[k] += now_ - t_last; t_last = now_; } } while (0)
 
   const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
-  if (tid == 0) { sh.work[0] = atomicAdd(A.work, 1u); tab[kTileBins] = 0; }
+  if (tid == 0) sh.work[0] = atomicAdd(A.work, 1u);
   __syncthreads();
   for (uint32_t it = 0;; it++) {
     const uint32_t s = sh.work[it & 1];
@@ -346,29 +432,67 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     }
     for (uint32_t r = tid; r < K; r += kScoreThreads) sh.top[r] = 0ull;
     __syncthreads();
+    // peaks whose window edges can reach each tile: bin in [t0 - 230, t0 + tn + 76)
+    if (scored && tid < kTileCache && (uint64_t)tid * kTileBins < NB) {
+      const uint32_t t0 = tid * kTileBins, tn = min(kTileBins, NB - t0);
+      sh.tile_pa[tid] = lower_bound_i32(pbin, npk, (int32_t)t0 - 230);
+      sh.tile_pb[tid] = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1);
+    }
+    MD_TICK(0);
 
+    const bool fast = K <= kFastTopK && ncand <= kCandChunk;   // warp-local top-k, merged by warp 0 while the others move on
     for (uint32_t c0 = 0; c0 < ncand || c0 == 0; c0 += kCandChunk) {
       const uint32_t cn = min(kCandChunk, ncand - c0);
       for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
-      bool counted = false;
+      // counting sort of the chunk by peptide length, longest first
+      if (tid < 64) sh.hist[tid] = 0;
+      __syncthreads();
+      if (scored) {
+        for (uint32_t v = tid; v < cn; v += kScoreThreads) {
+          const uint32_t u = c0 + v;
+          const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
+          atomicAdd(&sh.hist[63u - min(len, 63u)], 1u);
+          my_pairs++; my_bytes += 14 + len;
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {  // exclusive prefix over the 64 buckets
+        const uint32_t h0 = sh.hist[2 * lane], h1 = sh.hist[2 * lane + 1];
+        uint32_t incl = h0 + h1;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        sh.hist[2 * lane] = incl - h0 - h1; sh.hist[2 * lane + 1] = incl - h1;
+      }
+      __syncthreads();
+      if (scored) {
+        for (uint32_t v = tid; v < cn; v += kScoreThreads) {
+          const uint32_t u = c0 + v;
+          const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
+          s_order[atomicAdd(&sh.hist[63u - min(len, 63u)], 1u)] = (uint16_t)v;
+        }
+      }
+      // (visible to the scoring warps after the table-build barriers)
       if (scored && cn) {
         for (uint32_t t0 = 0; t0 < NB; t0 += kTileBins) {
           const uint32_t tn = min(kTileBins, NB - t0);
-          // peaks whose window edges can reach this tile: bin in [t0 - 230, t0 + tn + 76)
-          const uint32_t pa = lower_bound_i32(pbin, npk, (int32_t)t0 - 230);
-          const uint32_t pb = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1);
+          const uint32_t ti = t0 / kTileBins;
+          uint32_t pa, pb;
+          if (ti < kTileCache) { pa = sh.tile_pa[ti]; pb = sh.tile_pb[ti]; }
+          else { pa = lower_bound_i32(pbin, npk, (int32_t)t0 - 230); pb = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1); }
           if (pa == pb) continue;  // an all-zero tile adds nothing
           // (1) zero the tile
           {
             uint4* z = reinterpret_cast<uint4*>(tab);
-            const uint32_t n4 = (tn + 3) >> 2;
+            const uint32_t n4 = (tn + 4) >> 2;            // incl. the zero slot tab[tn] every out-of-tile gather lands on
             for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
+            if (tid == 0) sh.unit = 0;
           }
           __syncthreads();
-          // (2) paint -S[b], S[b] = sum of y over bins [b-75, b+75]: piecewise constant between window edges.
+          MD_TICK(1);
+          // (2) paint -S[b], S[b] = sum of y over bins [b-75, b+75]: piecewise constant between window edges (no atomics:
+          //     the value of every segment comes from the prefix sums of y).
           //     Edge 2k   = entry of peak pa+k at x = bin-75: S = pre[p+1] - pre[lo], lo = first peak with bin >= x-75
           //     Edge 2k+1 = exit  of peak pa+k at x = bin+76: S = pre[hi] - pre[p+1], hi = first peak with bin > x+75
-          //     and the segment runs to the next edge of either kind.
+          //     and the segment runs to the next edge of either kind.  One warp per edge, coalesced stores.
           for (uint32_t e = warp; e < 2 * (pb - pa); e += NW) {
             const uint32_t p = pa + (e >> 1);
             const int32_t bp = pbin[p];
@@ -394,37 +518,22 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
             for (int32_t x = a + (int32_t)lane; x < b; x += 32) tab[x - (int32_t)t0] = val;
           }
           __syncthreads();
+          MD_TICK(2);
           // (3) the peak's own bin: + 151*y
           for (uint32_t i = tid; i < pb - pa; i += kScoreThreads) {
             const uint32_t x = (uint32_t)pbin[pa + i] - t0;
             if (x < tn) tab[x] += 151 * pyq[pa + i];
           }
           __syncthreads();
+          MD_TICK(3);
           // (4) score the chunk against the tile
-          for (uint32_t v0 = 0; v0 < cn; v0 += kScoreThreads) {
-            const uint32_t v = v0 + tid;
-            const bool live = v < cn;
-            CandRef r; r.row = reinterpret_cast<const uint4*>(A.idx_rows); r.len = 0; r.mask = 0; r.modw = 0;
-            if (live) r = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
-            if (live && !counted) { my_pairs++; my_bytes += 14 + r.len; }
-            const uint32_t maxlen = __reduce_max_sync(0xffffffffu, r.len);
-            int64_t part;
-            switch (nch) {
-              case 1: part = score_one<1, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
-              case 2: part = score_one<2, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
-              default: part = score_one<3, HASVAR>(r.row, r.len, r.mask, r.modw, maxlen, tab_s, t0, tn, C, lqr, lvqr); break;
-            }
-            if (live) s_score[v] += part;
+          switch (nch) {
+            case 1: score_units<1, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
+            case 2: score_units<2, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
+            default: score_units<3, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
           }
-          counted = true;
           __syncthreads();
-        }
-        if (!counted) {  // every tile was empty: the pairs were still scored (0)
-          for (uint32_t v = tid; v < cn; v += kScoreThreads) {
-            const uint32_t u = c0 + v;
-            const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
-            my_pairs++; my_bytes += 14 + len;
-          }
+          MD_TICK(4);
         }
       }
       // ---- raw scores of every candidate (on request)
@@ -435,7 +544,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         }
       }
       // ---- top-k of (this chunk's candidates) U (best of the earlier chunks): K rounds of block-wide max
-      if (scored && cn && K) {
+      if (!fast && scored && cn && K) {
         // scores -> keys, in place; slots cn..cn+K-1 (conceptually) hold the running list, owned by threads < K
         for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = (int64_t)psm_key(s_score[v], c0 + v);
         unsigned long long carry = tid < K ? sh.top[tid] : 0ull;   // this thread's entry of the running list
@@ -457,28 +566,45 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           if (m == 0ull) break;   // fewer candidates than rows (uniform: every thread sees the same m)
         }
         __syncthreads();
+        MD_TICK(5);
       }
     }
     // ---- PSM rows
-    for (uint32_t r = tid; r < K; r += kScoreThreads) {
-      md_psm row;
-      row.spectrum_id = pr.spectrum_id; row.rank = 0; row.is_decoy = 0; row.charge = (uint8_t)pr.charge; row.candidate = 0; row.var_mask = 0;
-      row.mod_weight = 0; row.raw_score = 0; row.score = 0.0f; row.n_targets = nt; row.n_decoys = nd; row._pad = 0;
-      const unsigned long long k = scored ? sh.top[r] : 0ull;
-      if (k != 0ull) {
-        const uint32_t bv = 0xFFFFFFu - (uint32_t)(k & 0xFFFFFFull);
-        const int64_t bs = (int64_t)(k >> 24) - kKeyBias;
-        row.rank = (uint16_t)(r + 1); row.raw_score = bs;
-        row.score = (float)(0.005 * (double)bs / (150.0 * 65536.0));
-        if (bv < nt) { row.is_decoy = 0; row.candidate = (uint64_t)A.cand_pep[t0c + bv] + 1; row.var_mask = A.cand_mask[t0c + bv]; row.mod_weight = A.cand_w[t0c + bv]; }
-        else { const uint64_t j = (uint64_t)s * C.n_per + (bv - nt); row.is_decoy = 1; row.candidate = bv - nt; row.var_mask = A.dec_mask[j]; row.mod_weight = A.dec_w[j]; }
+    if (fast) {
+      if (scored && K) {
+        unsigned long long k0 = tid < ncand ? psm_key(s_score[tid], tid) : 0ull;
+        unsigned long long k1 = tid + kScoreThreads < ncand ? psm_key(s_score[tid + kScoreThreads], tid + kScoreThreads) : 0ull;
+        for (uint32_t r = 0; r < K; r++) {
+          const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
+          if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
+          if (lane == 0) sh.wtop[warp][r] = wm;
+        }
       }
-      A.psm[(uint64_t)s * K + r] = row;
+      __syncthreads();
+      MD_TICK(5);
+      if (warp == 0) {
+        unsigned long long mine = 0ull;      // lane r ends up with the r-th best key of the spectrum
+        if (scored && K) {
+          uint32_t idx = 0;
+          for (uint32_t r = 0; r < K; r++) {
+            const unsigned long long head = (lane < NW && idx < K) ? sh.wtop[lane][idx] : 0ull;
+            const unsigned long long wm = warp_max_u64(head);
+            if (wm != 0ull && head == wm) idx++;
+            if (lane == r) mine = wm;
+          }
+        }
+        if (lane < K) write_psm_row(A, C, pr, s, lane, mine, nt, nd, t0c);
+      }
+    } else {
+      for (uint32_t r = tid; r < K; r += kScoreThreads) write_psm_row(A, C, pr, s, r, scored ? sh.top[r] : 0ull, nt, nd, t0c);
+      __syncthreads();
+      MD_TICK(6);
     }
-    __syncthreads();
   }
-  for (int o = 16; o; o >>= 1) { my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o); my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, o); }
-  if (lane == 0 && my_pairs) { atomicAdd(&A.stat64[0], my_pairs); atomicAdd(&A.stat64[1], my_bytes); }
+  if (A.timing && tid == 0) for (int k = 0; k < 8; k++) atomicAdd(&A.timing[k], (unsigned long long)sh.tacc[k]);
+  unsigned long long wp = my_pairs, wb = my_bytes;
+  for (int o = 16; o; o >>= 1) { wp += __shfl_xor_sync(0xffffffffu, wp, o); wb += __shfl_xor_sync(0xffffffffu, wb, o); }
+  if (lane == 0 && wp) { atomicAdd(&A.stat64[0], wp); atomicAdd(&A.stat64[1], wb); }
 }
 
 void split_qr(int64_t m, uint32_t w, uint32_t* q, uint32_t* r) {
@@ -513,7 +639,6 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   ScoreConst C;
   memset(&C, 0, sizeof(C));
   C.w = (uint32_t)w; C.max_frag_charge = mfc; C.top_k = p.top_k; C.n_per = n_per;
-  C.rbits = 1; while ((1u << C.rbits) < C.w) C.rbits++;   // r < w <= 2^rbits
   split_qr(MD_PROTON_UDA, C.w, &C.qp, &C.rp);
   split_qr(2 * MD_PROTON_UDA, C.w, &C.q2p, &C.r2p);
   bool has_var = false;
@@ -523,11 +648,11 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     int64_t v = (c < MD_NCODES && ctx->mods.has_var[c]) ? ctx->mods.var[c] : 0;
     uint32_t q, r;
     split_qr(m + f, C.w, &q, &r);
-    MD_REQUIRE(((uint64_t)q << C.rbits) < (1ull << 31), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
-    C.tqr[c] = (q << C.rbits) | r;
+    MD_REQUIRE(q < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
+    C.tq4[c] = 4u * q; C.tr[c] = r;
     split_qr(m + f + v, C.w, &q, &r);
-    MD_REQUIRE(((uint64_t)q << C.rbits) < (1ull << 31), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
-    C.vqr[c] = (q << C.rbits) | r;
+    MD_REQUIRE(q < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
+    C.vq4[c] = 4u * q; C.vr[c] = r;
     if (c < MD_NCODES && ctx->mods.has_var[c]) has_var = true;
   }
   uint64_t n_targets = 0;
@@ -538,16 +663,17 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   }
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
-  W.stat64.need(2);
-  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  W.stat64.need(16);
+  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  const bool timing = getenv("MD_SCORE_TIMING") != nullptr;
   ScoreArgs A;
   A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_pre = W.pk_pre.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
   A.cand_off = W.cand_off.p; A.cand_desc = W.cand_desc.p; A.cand_mask = W.cand_mask.p; A.cand_w = W.cand_w.p; A.cand_pep = W.cand_pep.p;
   A.idx_rows = ctx->index.rows.p;
   A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
   A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
-  A.error = d_flag.p + 1;
-  const size_t smem = ((size_t)kTileBins + 4) * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4;
+  A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
+  const size_t smem = ((size_t)kTileBins + 4) * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4 + (size_t)kCandChunk * 2;
   const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
   MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (has_var) {
@@ -564,6 +690,15 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof(h_flag), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->acc_ms_kscore += ms; ctx->acc_pairs += h_stat[0]; ctx->acc_score_bytes += h_stat[1]; }
+  if (timing) {
+    unsigned long long t[8];
+    MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
+    double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
+    static const char* names[6] = {"stage", "zero", "paint", "spike", "score", "topk"};
+    fprintf(stderr, "[md_score_timing] grid=%u", grid);
+    for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.1f%%", names[k], 100.0 * (double)t[k] / tot);
+    fprintf(stderr, " cycles/CTA=%.0f\n", tot / grid);
+  }
   MD_REQUIRE(!h_flag[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
-  MD_REQUIRE(!h_flag[1], MD_ERR_UNSUPPORTED, "a spectrum needs more than 2^30 fragment bins or has more than 2^24 candidates");
+  MD_REQUIRE(!h_flag[1], MD_ERR_UNSUPPORTED, "a spectrum needs more than 2^26 fragment bins or has more than 2^24 candidates");
 }
