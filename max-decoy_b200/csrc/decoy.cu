@@ -98,89 +98,178 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ att_
   return lo;
 }
 
+// Philox4x32-10 output stream of one attempt, buffered in a per-lane shared-memory ring so that the block function runs
+// for the whole warp at once (every kRngPeriod steps of the kernel loop) instead of as a divergent tail behind whichever
+// lane happens to run dry.  The stream is exactly Philox4::next()'s: blocks c0 = 0, 1, 2, ... in order, four words each.
+struct RngRing {
+  uint32_t* buf;                 // 8 words, stride kThreads
+  uint32_t k0, k1, c0, c1, c2;   // key, next block, attempt, spectrum
+  uint32_t head, count;
+  __device__ __forceinline__ void start(uint64_t seed, uint32_t spectrum_id, uint32_t attempt) {
+    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); c0 = 0; c1 = attempt; c2 = spectrum_id; head = 0; count = 0;
+  }
+  __device__ __forceinline__ void produce() {   // one block -> 4 words into the ring (needs count <= 4)
+    uint32_t a = c0, b = c1, c = c2, d = MD_TAG_RANDOM, x = k0, y = k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+      const uint64_t p0 = (uint64_t)0xD2511F53u * a, p1 = (uint64_t)0xCD9E8D57u * c;
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ b ^ x, n1 = (uint32_t)p1;
+      const uint32_t n2 = (uint32_t)(p0 >> 32) ^ d ^ y, n3 = (uint32_t)p0;
+      a = n0; b = n1; c = n2; d = n3;
+      x += 0x9E3779B9u; y += 0xBB67AE85u;
+    }
+    const uint32_t t = head + count;
+    buf[((t + 0) & 7) * kThreads] = a; buf[((t + 1) & 7) * kThreads] = b; buf[((t + 2) & 7) * kThreads] = c; buf[((t + 3) & 7) * kThreads] = d;
+    c0++; count += 4;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    if (count == 0) produce();
+    const uint32_t v = buf[(head & 7) * kThreads];
+    head++; count--;
+    return v;
+  }
+  __device__ __forceinline__ uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
+};
+constexpr uint32_t kRngPeriod = 6;
+
+// One lane = one attempt at a time, run as a flat state machine: every pass of the kernel loop does ONE greedy step for
+// every lane that has an attempt (kSpec positions evaluated side by side against the current residual: independent
+// search chains; the first improving substitution is applied and the positions behind it are looked at again in the
+// next step), so the lanes of a warp stay in the same code although their attempts are at different tries / positions
+// / lengths (nested try/position loops would make 31 finished lanes wait for the one that runs all 100 tries).  Lanes
+// whose attempt ends (hit, or 100 tries without one) park until a quarter of the warp is free, then fetch and grow new
+// attempts together.  All residual arithmetic is 32-bit: |w - P| stays far below 2^30 uDa after the grow phase
+// (checked; reported via `overflow`).
 __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* __restrict__ prec, const uint32_t* __restrict__ list,
                                                            const uint32_t* __restrict__ att_off, const uint32_t* __restrict__ att_base, uint32_t n_list,
                                                            uint32_t total, uint32_t* __restrict__ queue, uint64_t seed, const __grid_constant__ ModTables M,
                                                            const __grid_constant__ DecoyTables T, AttemptOut O, PeptideView PV, int* __restrict__ overflow) {
   __shared__ uint8_t sseq[MD_MAX_PEPTIDE_LEN * kThreads];
-  __shared__ int64_t s_sorted[32];
-  __shared__ int64_t s_mprime[32];
-  __shared__ int64_t s_var[32];
-  __shared__ uint8_t s_sorted_a[32], s_runmin[32], s_hasvar[32], s_hasfix[32];
+  __shared__ uint32_t s_rng[8 * kThreads];
+  __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
+  __shared__ int32_t s_mprime[32];      // by alphabet index
+  __shared__ int32_t s_var[32];
+  __shared__ uint8_t s_runmin[32];
   if (threadIdx.x < 32) {
-    s_sorted[threadIdx.x] = T.sorted_m[threadIdx.x]; s_mprime[threadIdx.x] = T.mprime[threadIdx.x]; s_var[threadIdx.x] = T.var_a[threadIdx.x];
-    s_sorted_a[threadIdx.x] = T.sorted_a[threadIdx.x]; s_runmin[threadIdx.x] = T.run_min_a[threadIdx.x];
-    s_hasvar[threadIdx.x] = T.has_var_a[threadIdx.x]; s_hasfix[threadIdx.x] = T.has_fix_a[threadIdx.x];
+    const int64_t sm = T.sorted_m[threadIdx.x];
+    s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
+    s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
+    s_runmin[threadIdx.x] = T.run_min_a[threadIdx.x];
   }
   __syncthreads();
   TSeq seq{sseq + threadIdx.x};
   const bool any_var = M.nvar > 0;
+  constexpr int kSpec = 4;
 
-  for (;;) {
-    const uint32_t wi = atomicAdd(queue, 1u);
-    if (wi >= total) break;
-    const uint32_t li = find_entry(att_off, n_list, wi);
-    const md_precursor pr = prec[list[li]];
-    const uint32_t attempt = att_base[li] + (wi - att_off[li]);
-    Philox4 rng; rng.init(seed, pr.spectrum_id, attempt, MD_TAG_RANDOM);
+  bool busy = false, drained = false;
+  uint32_t wi = 0, L = 0, pos = 0, tries = 0;
+  int64_t w = 0, P = 0, lo = 0, hi = 0;
+  int32_t d = 0;
+  uint64_t mask = 0;
+  RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(seed, 0, 0);
 
-    // ---- grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
-    int64_t w = MD_WATER_UDA; uint32_t L = 0; bool dead = false;
-    for (;;) {
-      uint32_t a = rng.below(MD_ALPHABET_SIZE);
-      if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
-      seq.at(L++) = (uint8_t)a;
-      w += s_mprime[a];
-      if (w > pr.hi) break;
-    }
-    uint64_t mask = 0; bool hit = false;
-    if (!dead) {
-      // ---- repair (modified_peptide.rs:451-508)
-      for (int t = 0; t < 100 && !hit; t++) {
-        for (uint32_t i = 0; i < L; i++) {
-          const uint32_t cur = seq.at(i);
-          const int64_t d = w - pr.mass;
-          // best single substitution = letter whose (mass+fixed) is closest to mprime[cur] - d; strict improvement,
-          // ties by alphabet order (the reference follows HashMap order there)
-          const int64_t target = s_mprime[cur] - d;
-          uint32_t k = 0;
-          if (s_sorted[k + 15] < target) k += 16;
-          if (s_sorted[k + 7] < target) k += 8;
-          if (s_sorted[k + 3] < target) k += 4;
-          if (s_sorted[k + 1] < target) k += 2;
-          if (s_sorted[k] < target) k += 1;
-          // candidates: sorted[k-1] (< target) and sorted[k] (>= target)
-          int64_t best = d < 0 ? -d : d; uint32_t bestc = cur;
-          int64_t dist_hi = (k < MD_ALPHABET_SIZE) ? s_sorted[k] - target : INT64_MAX;
-          int64_t dist_lo = (k > 0) ? target - s_sorted[k - 1] : INT64_MAX;
-          uint32_t a_hi = (k < MD_ALPHABET_SIZE) ? s_runmin[k] : 255u;
-          uint32_t a_lo = (k > 0) ? s_runmin[k - 1] : 255u;
-          int64_t cd; uint32_t ca;
-          if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; ca = a_lo; } else { cd = dist_hi; ca = a_hi; }
-          if (cd < best && ca != cur) { best = cd; bestc = ca; }
-          if (bestc != cur) {
-            // remove_modification_at + swap + fixed mod of the new letter (:470-482)
-            if ((mask >> i) & 1) { w -= s_var[cur]; mask &= ~(1ULL << i); }
-            w += s_mprime[bestc] - s_mprime[cur];
-            seq.at(i) = (uint8_t)bestc;
-            if (md_in_window(w, pr.lo, pr.hi)) { hit = true; break; }
-            if (any_var) {
-              TSeqCode sc{seq, T.code_of_a};
-              if (md_try_variable(M, sc, L, w, mask, pr.lo, pr.hi, overflow)) { hit = true; break; }
-            }
+  for (uint32_t it = 0;; it++) {
+    // ---- refill: when at least 8 lanes are free (or nobody works), they fetch and grow new attempts together
+    const uint32_t free_m = __ballot_sync(0xffffffffu, !busy && !drained);
+    const uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
+    if (free_m && (__popc(free_m) >= 8 || busy_m == 0)) {
+      if (!busy && !drained) {
+        wi = atomicAdd(queue, 1u);
+        if (wi >= total) drained = true;
+        else {
+          const uint32_t li = find_entry(att_off, n_list, wi);
+          const md_precursor pr = prec[list[li]];
+          P = pr.mass; lo = pr.lo; hi = pr.hi;
+          rng.start(seed, pr.spectrum_id, att_base[li] + (wi - att_off[li]));
+          // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
+          w = MD_WATER_UDA; L = 0; mask = 0; bool dead = false;
+          for (;;) {
+            const uint32_t a = rng.below(MD_ALPHABET_SIZE);
+            if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
+            seq.at(L++) = (uint8_t)a;
+            w += s_mprime[a];
+            if (w > hi) break;
           }
+          const int64_t dd = w - P;
+          if (!dead && (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF)) { *overflow = 2; dead = true; }
+          if (dead) store_attempt(O, wi, seq, 0, 0, 0, T, PV);
+          else { busy = true; tries = 0; pos = 0; d = (int32_t)dd; }
         }
-        if (hit) break;
-        // random kick (:489-505)
-        uint32_t i = rng.below(L);
-        uint32_t c = rng.below(MD_ALPHABET_SIZE);
-        uint32_t cur = seq.at(i);
-        if ((mask >> i) & 1) { w -= s_var[cur]; mask &= ~(1ULL << i); }
-        w += s_mprime[c] - s_mprime[cur];
-        seq.at(i) = (uint8_t)c;
       }
     }
-    store_attempt(O, wi, seq, hit ? L : 0, mask, w, T, PV);
+    if (__ballot_sync(0xffffffffu, busy) == 0) {
+      if (__ballot_sync(0xffffffffu, !drained) == 0) break;
+      continue;
+    }
+    // ---- keep the random-number rings topped up, all lanes together
+    if (it % kRngPeriod == 0) { if (busy && rng.count <= 4) rng.produce(); }
+    // ---- one greedy step (modified_peptide.rs:454-487) of every busy lane
+    if (busy) {
+      const int32_t best = d < 0 ? -d : d;
+      uint32_t cur[kSpec], ca[kSpec]; bool imp[kSpec];
+#pragma unroll
+      for (int j = 0; j < kSpec; j++) {
+        const bool in = pos + j < L;
+        cur[j] = in ? seq.at(pos + j) : 0u;
+        // best single substitution = letter whose (mass+fixed) is closest to mprime[cur] - d; strict improvement,
+        // ties by alphabet order (the reference follows HashMap order there)
+        const int32_t target = s_mprime[cur[j]] - d;
+        uint32_t k = 0;
+        if (s_sorted[k + 15] < target) k += 16;
+        if (s_sorted[k + 7] < target) k += 8;
+        if (s_sorted[k + 3] < target) k += 4;
+        if (s_sorted[k + 1] < target) k += 2;
+        if (s_sorted[k] < target) k += 1;
+        // candidates: sorted[k-1] (< target) and sorted[k] (>= target)
+        const int64_t dist_hi = (k < MD_ALPHABET_SIZE) ? (int64_t)s_sorted[k] - target : INT64_MAX;
+        const int64_t dist_lo = (k > 0) ? (int64_t)target - s_sorted[k - 1] : INT64_MAX;
+        const uint32_t a_hi = (k < MD_ALPHABET_SIZE) ? s_runmin[k] : 255u;
+        const uint32_t a_lo = (k > 0) ? s_runmin[k - 1] : 255u;
+        int64_t cd;
+        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; ca[j] = a_lo; } else { cd = dist_hi; ca[j] = a_hi; }
+        imp[j] = in && cd < (int64_t)best && ca[j] != cur[j];
+      }
+      int first = kSpec;
+#pragma unroll
+      for (int j = kSpec - 1; j >= 0; j--) if (imp[j]) first = j;
+      bool hit = false;
+      if (first < kSpec) {
+        uint32_t c0 = cur[0], a0 = ca[0];
+#pragma unroll
+        for (int j = 1; j < kSpec; j++) if (first == j) { c0 = cur[j]; a0 = ca[j]; }
+        pos += first;
+        // remove_modification_at + swap + fixed mod of the new letter (:470-482)
+        if ((mask >> pos) & 1) { w -= s_var[c0]; mask &= ~(1ULL << pos); }
+        w += s_mprime[a0] - s_mprime[c0];
+        seq.at(pos) = (uint8_t)a0;
+        if (md_in_window(w, lo, hi)) hit = true;
+        else if (any_var) {
+          TSeqCode sc{seq, T.code_of_a};
+          if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
+        }
+        const int64_t dd = w - P;
+        if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
+        d = (int32_t)dd;
+        pos += 1;
+      } else {
+        pos += kSpec;
+      }
+      if (hit) { store_attempt(O, wi, seq, L, mask, w, T, PV); busy = false; }
+      else if (pos >= L) {
+        // random kick (:489-505)
+        const uint32_t i = rng.below(L);
+        const uint32_t c = rng.below(MD_ALPHABET_SIZE);
+        const uint32_t old = seq.at(i);
+        if ((mask >> i) & 1) { w -= s_var[old]; mask &= ~(1ULL << i); }
+        w += s_mprime[c] - s_mprime[old];
+        seq.at(i) = (uint8_t)c;
+        const int64_t dd = w - P;
+        if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
+        d = (int32_t)dd;
+        pos = 0;
+        if (++tries == 100) { store_attempt(O, wi, seq, 0, 0, 0, T, PV); busy = false; }
+      }
+    }
   }
 }
 
@@ -330,6 +419,10 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   MD_REQUIRE(mode == MD_DECOY_REFERENCE_RANDOM || mode == MD_DECOY_PERMUTE_TARGET, MD_ERR_INVALID, "unknown decoy mode");
 
   const DecoyTables T = make_tables(ctx->mods);
+  if (mode == MD_DECOY_REFERENCE_RANDOM)
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++)
+      MD_REQUIRE(T.mprime[a] > 0 && T.mprime[a] < (1 << 29) && T.var_a[a] > -(1 << 29) && T.var_a[a] < (1 << 29), MD_ERR_UNSUPPORTED,
+                 "decoy generation works in 32-bit residuals: residue and modification masses must stay below 536 Da");
   PeptideView PV{(const unsigned long long*)P.ht_key.p, P.ht_val.p, P.ht_mask, P.seq.p, P.seq_off.p, P.len.p};
   std::vector<uint64_t> h_cand_off;
   if (mode == MD_DECOY_PERMUTE_TARGET) {
@@ -339,6 +432,15 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   }
   // per spectrum bookkeeping on the host
   std::vector<uint32_t> used(n, 0), count(n, 0), cap(n);
+  // spectra in ascending precursor mass: neighbouring attempts grow sequences of similar length (lockstep passes)
+  std::vector<uint32_t> by_mass(n);
+  {
+    std::vector<md_precursor> hp(n);
+    MD_CUDA(cudaMemcpyAsync(hp.data(), W.prec.p, n * sizeof(md_precursor), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < n; s++) by_mass[s] = s;
+    std::stable_sort(by_mass.begin(), by_mass.end(), [&](uint32_t a, uint32_t b) { return hp[a].mass < hp[b].mass; });
+  }
   for (uint32_t s = 0; s < n; s++) {
     uint64_t c = md_attempt_cap(n_per);
     if (mode == MD_DECOY_PERMUTE_TARGET) c = std::min<uint64_t>(c, (h_cand_off[s + 1] - h_cand_off[s]) * 1000ull);
@@ -351,7 +453,8 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   std::vector<uint32_t> list, off, base;
   for (int round = 0; round < 64; round++) {
     list.clear(); off.assign(1, 0); base.clear();
-    for (uint32_t s = 0; s < n; s++) {
+    for (uint32_t si = 0; si < n; si++) {
+      const uint32_t s = by_mass[si];
       if (count[s] >= n_per || used[s] >= cap[s]) continue;
       uint32_t want;
       if (used[s] == 0) want = n_per + n_per / 4 + 32;
@@ -390,6 +493,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total; }
   }
   const int ovf = d2h_scalar(ctx, d_ovf.p);
+  MD_REQUIRE(ovf != 2, MD_ERR_UNSUPPORTED, "decoy generation: |weight - precursor| left the 32-bit range (residue or modification masses above ~1000 Da?)");
   MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "variable-modification placement enumeration exceeds 2^22 subsets for one decoy");
 }
 
