@@ -313,7 +313,84 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
 
 // One CTA per listed spectrum: keep the successes of this round that are new (not equal to an accepted decoy or to an
 // earlier success), in attempt order, until the spectrum has n_per decoys (HashSet<Decoy>, decoy_generator.rs:40,164).
+// Linear time: accepted decoys and successes go into a shared-memory hash set keyed by the 64-bit sequence hash, each
+// entry remembering the lowest ordinal (accepted decoys first, then attempts in order) that carried the key; a success
+// is kept iff it is that first carrier.  (Sequences are identified by their 64-bit hash here.)
 __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
+                                                      const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, AttemptOut A,
+                                                      uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
+                                                      int64_t* __restrict__ dec_w, uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt,
+                                                      uint32_t* __restrict__ dec_count) {
+  extern __shared__ __align__(16) unsigned long long s_key[];   // slots (0 = empty)
+  uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_key + slots);   // slots
+  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_ord + slots);    // kMaxRoundAttempts
+  __shared__ uint32_t s_scan[256];
+  __shared__ uint32_t s_base;
+  const uint32_t li = blockIdx.x, s = list[li];
+  const uint32_t a0 = att_off[li], na = att_off[li + 1] - a0;
+  const uint32_t have = dec_count[s];
+  const uint64_t dbase = (uint64_t)s * n_per;
+  const uint32_t smask = slots - 1;
+  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) { s_key[i] = 0ULL; s_ord[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  auto insert = [&](unsigned long long h, uint32_t ord) {
+    if (h == 0ULL) h = 1ULL;
+    uint32_t slot = (uint32_t)h & smask;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&s_key[slot], 0ULL, h);
+      if (prev == 0ULL || prev == h) { atomicMin(&s_ord[slot], ord); return; }
+      slot = (slot + 1) & smask;
+    }
+  };
+  for (uint32_t j = threadIdx.x; j < have; j += blockDim.x) insert(dec_hash[dbase + j], j);
+  for (uint32_t a = threadIdx.x; a < na; a += blockDim.x) if (A.len[a0 + a]) insert(A.hash[a0 + a], have + a);
+  __syncthreads();
+  for (uint32_t a = threadIdx.x; a < na; a += blockDim.x) {
+    bool keep = A.len[a0 + a] != 0;
+    if (keep) {
+      unsigned long long h = A.hash[a0 + a];
+      if (h == 0ULL) h = 1ULL;
+      uint32_t slot = (uint32_t)h & smask;
+      while (s_key[slot] != h) slot = (slot + 1) & smask;
+      keep = s_ord[slot] == have + a;
+    }
+    s_keep[a] = keep ? 1 : 0;
+  }
+  __syncthreads();
+  // ordered compaction: thread t owns the contiguous chunk [t*per, (t+1)*per)
+  const uint32_t per = (na + blockDim.x - 1) / blockDim.x;
+  const uint32_t b = threadIdx.x * per, e = min(b + per, na);
+  uint32_t c = 0;
+  for (uint32_t a = b; a < e; a++) c += s_keep[a];
+  s_scan[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t t = 0; t < blockDim.x; t++) { uint32_t v = s_scan[t]; s_scan[t] = run; run += v; }
+    s_base = run;
+  }
+  __syncthreads();
+  uint32_t o = have + s_scan[threadIdx.x];
+  for (uint32_t a = b; a < e; a++) {
+    if (!s_keep[a]) continue;
+    if (o < n_per) {
+      const uint64_t src = a0 + a, dst = dbase + o;
+      const uint4* sr = reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW);
+      uint4* dr = reinterpret_cast<uint4*>(dec_rows + dst * MD_DECOY_ROW);
+      dr[0] = sr[0]; dr[1] = sr[1]; dr[2] = sr[2]; dr[3] = sr[3];
+      dec_len[dst] = A.len[src]; dec_mask[dst] = A.mask[src]; dec_w[dst] = A.w[src]; dec_hash[dst] = A.hash[src];
+      dec_attempt[dst] = att_base[li] + a;
+    }
+    o++;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) dec_count[s] = min(n_per, have + s_base);
+}
+
+// Fallback of k_decoy_select for tables that do not fit shared memory (quadratic scan, exact sequence compare).
+// One CTA per listed spectrum: keep the successes of this round that are new (not equal to an accepted decoy or to an
+// earlier success), in attempt order, until the spectrum has n_per decoys (HashSet<Decoy>, decoy_generator.rs:40,164).
+__global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
                                                       const uint32_t* __restrict__ att_base, uint32_t n_per, AttemptOut A, uint8_t* __restrict__ dec_rows,
                                                       uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask, int64_t* __restrict__ dec_w,
                                                       uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt, uint32_t* __restrict__ dec_count) {
@@ -484,8 +561,20 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     }
     MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->mark("  attempts");
-    MD_LAUNCH(ctx, k_decoy_select, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p,
-              W.dec_attempt.p, W.dec_count.p);
+    {
+      uint32_t need = 1;                                    // most (accepted + attempted) of one spectrum in this round
+      for (uint32_t i = 0; i < n_list; i++) need = std::max(need, count[list[i]] + (off[i + 1] - off[i]));
+      uint32_t slots = 1024; while (slots < 2 * need) slots <<= 1;
+      const size_t smem = (size_t)slots * 12 + kMaxRoundAttempts;
+      if (smem <= 200 * 1024) {
+        MD_CUDA(cudaFuncSetAttribute(k_decoy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+                  W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
+      } else {
+        MD_LAUNCH(ctx, k_decoy_select_n2, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+                  W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
+      }
+    }
     MD_CUDA(cudaMemcpyAsync(count.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->mark("  select");
