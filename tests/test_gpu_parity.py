@@ -114,7 +114,25 @@ def test_decoys_permute_bit_exact(gpu, cpu):
     assert_tables_equal(dg, dc)
 
 
-@pytest.mark.parametrize("mods,nvar,mode,nd", [((synth.CAM,), 0, 0, 100), ((synth.CAM, synth.OXM), 3, 0, 60), ((synth.CAM,), 0, 2, 30), ((synth.CAM,), 0, 0, 0)])
+@pytest.mark.parametrize("mods,nvar", [((synth.CAM,), 0), ((synth.CAM, synth.OXM), 2)])
+def test_decoys_exhaustive_bit_exact(gpu, cpu, mods, nvar):
+    """Exhaustive-enumeration mode (north star): identical sequences, order, weights and ordinals."""
+    for e in (gpu, cpu):
+        _setup(e, 300, 2, mods, nvar)
+    sp, _ = wl.spectra(300, 48, 2)
+    pre = wl.precursors_of(cpu, sp)
+    # plus tiny precursors (few compositions: fewer decoys than requested) and a wide window
+    pre += [(300_000_000, 299_000_000, 301_000_000, 2, 1000), (75_031_000, 75_000_000, 75_100_000, 1, 1001),
+            (900_400_000, 800_000_000, 1_000_000_000, 2, 1002), (10_000_000, 9_000_000, 11_000_000, 1, 1003)]
+    for n in (1, 37, 400):
+        dg = gpu.generate_decoys(pre, n, maxdecoy.DECOY_EXHAUSTIVE, seed=0)
+        dc = cpu.generate_decoys(pre, n, maxdecoy.DECOY_EXHAUSTIVE, seed=0)
+        assert_tables_equal(dg, dc)
+        assert len(dg["attempt"]) > 0
+
+
+@pytest.mark.parametrize("mods,nvar,mode,nd", [((synth.CAM,), 0, 0, 100), ((synth.CAM, synth.OXM), 3, 0, 60), ((synth.CAM,), 0, 2, 30), ((synth.CAM,), 0, 0, 0),
+                                               ((synth.CAM,), 0, 1, 40)])
 def test_identify_bit_exact(gpu, cpu, mods, nvar, mode, nd):
     for e in (gpu, cpu):
         _setup(e, 600, 2, mods, nvar)
