@@ -164,10 +164,32 @@ def run_reference(args, cfg, rank, world):
                              "sample": "%d spectra of the workload per step, %d host threads; CPU oracle port of the reference's algorithm with an in-memory "
                                        "mass-sorted index (the Rust reference needs cargo + PostgreSQL + Comet, none present)" % (sample, threads)},
             "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE result line: everything else any library prints to fd 1 (e.g. NCCL's version banner)
+    goes to stderr."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -311,10 +333,20 @@ def main():
         pairs_all = float(t.item())
     else:
         pairs_all = float(pairs)
-    if rank != 0:
+    def shutdown():
+        """Ordered teardown, then a hard exit: the library and torch/NCCL each own CUDA state whose static destructors
+        must not race at interpreter exit (seen as SIGSEGV after the result line with N > 1)."""
+        eng.close()
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    if rank != 0:
+        shutdown()
 
     peaks, peak_kind = load_peaks()
     total_spectra = n_spec * world
@@ -351,9 +383,8 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "spectra/s", "cores": os.cpu_count() or 1, "kind": "port", "candidates_per_sec": pv,
                                 "sample": "first %d spectra of the same workload, one pass, %d host threads over spectra; CPU oracle port with an in-memory "
                                           "mass-sorted index (favourable to the CPU: the real reference adds PostgreSQL round trips and an external Comet run)" % (ns, os.cpu_count() or 1)}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    shutdown()
 
 
 if __name__ == "__main__":

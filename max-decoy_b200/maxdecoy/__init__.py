@@ -2,6 +2,7 @@
 from . import _abi
 from ._abi import ALPHABET, DECOY_EXHAUSTIVE, DECOY_PERMUTE_TARGET, DECOY_REFERENCE_RANDOM
 from .api import Engine, MaxDecoyError, Modification, SearchParams, Spectra, load, mass, pack_proteins
+from . import mzml, outputs, parallel, pgexport, synth
 
 __all__ = ["Engine", "MaxDecoyError", "Modification", "SearchParams", "Spectra", "load", "mass", "pack_proteins",
-           "ALPHABET", "DECOY_REFERENCE_RANDOM", "DECOY_EXHAUSTIVE", "DECOY_PERMUTE_TARGET", "_abi"]
+           "mzml", "outputs", "parallel", "pgexport", "synth", "ALPHABET", "DECOY_REFERENCE_RANDOM", "DECOY_EXHAUSTIVE", "DECOY_PERMUTE_TARGET", "_abi"]
