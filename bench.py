@@ -33,6 +33,9 @@ CONFIGS = {
                text="C2: synthetic human-proteome-sized FASTA (20k proteins), trypsin MC=2, len 5..50, fixed CAM-C, 10k synthetic spectra, 10 ppm, target + 1000 reference-random decoys/spectrum (reference default -d 1000), top-5 PSMs"),
     "c3": dict(n_proteins=20000, mc=2, n_spectra=10000, ppm=10, var=True, n_decoys=1000,
                text="C3: C2 + variable Met-oxidation (<=3 mods/peptide), 1000 mass-matched decoys/spectrum"),
+    # BASELINE.json configs[4] on one GPU's share: open search, ~1M candidates per spectrum (no decoys: the window holds them all)
+    "c5": dict(n_proteins=20000, mc=2, n_spectra=64, ppm=10, var=False, n_decoys=0, abs_da=500,
+               text="C5 (one GPU's share): +-500 Da open search over the 20k-protein index, ~1M candidates per spectrum, targets only"),
 }
 TOP_K = 5
 FRAG_TOL = 0.02
@@ -106,8 +109,9 @@ def make_workload(cfg, rank, n_spectra):
 
 def search_params(cfg):
     from maxdecoy import SearchParams
+    a = int(cfg.get("abs_da", 0) * 1000000)
     return SearchParams(cfg["ppm"], cfg["ppm"], fragment_tolerance=FRAG_TOL, n_decoys=cfg["n_decoys"], decoy_mode=0, seed=20260101,
-                        top_k=TOP_K, min_peaks=10, max_fragment_charge=3)
+                        top_k=TOP_K, min_peaks=10, max_fragment_charge=3, abs_lower_uda=a, abs_upper_uda=a)
 
 
 def cpu_identify(cfg, prots, mods, sp, sample, threads, repeats=1):

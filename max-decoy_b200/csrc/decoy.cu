@@ -134,13 +134,16 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   __syncthreads();
   TSeq seq{sseq + threadIdx.x};
   const bool any_var = M.nvar > 0;
+  // one variable letter without a fixed modification (e.g. Met oxidation): its positions are tracked in `vpos`, and
+  // try_variable_modifications needs no walk over the sequence
+  const int va = M.var_simple_code >= 0 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
   constexpr int kSpec = 4;
 
   bool busy = false, drained = false;
   uint32_t wi = 0, L = 0, pos = 0, tries = 0;
   int64_t w = 0, P = 0, lo = 0, hi = 0;
   int32_t d = 0;
-  uint64_t mask = 0;
+  uint64_t mask = 0, vpos = 0;
   RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(seed, 0, 0);
 
   for (uint32_t it = 0;; it++) {
@@ -157,10 +160,11 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
           P = pr.mass; lo = pr.lo; hi = pr.hi;
           rng.start(seed, pr.spectrum_id, att_base[li] + (wi - att_off[li]));
           // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
-          w = MD_WATER_UDA; L = 0; mask = 0; bool dead = false;
+          w = MD_WATER_UDA; L = 0; mask = 0; vpos = 0; bool dead = false;
           for (;;) {
             const uint32_t a = rng.below(MD_ALPHABET_SIZE);
             if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
+            if ((int)a == va) vpos |= 1ULL << L;
             seq.at(L++) = (uint8_t)a;
             w += s_mprime[a];
             if (w > hi) break;
@@ -217,10 +221,15 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         if ((mask >> pos) & 1) { w -= s_var[c0]; mask &= ~(1ULL << pos); }
         w += s_mprime[a0] - s_mprime[c0];
         seq.at(pos) = (uint8_t)a0;
+        vpos = (vpos & ~(1ULL << pos)) | ((int)a0 == va ? 1ULL << pos : 0ULL);
         if (md_in_window(w, lo, hi)) hit = true;
         else if (any_var) {
-          TSeqCode sc{seq, T.code_of_a};
-          if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
+          if (va >= 0) {
+            if (vpos) hit = md_try_variable_simple(M, vpos, w - (int64_t)__popcll(mask) * M.var[M.var_simple_code], w, mask, lo, hi);
+          } else {
+            TSeqCode sc{seq, T.code_of_a};
+            if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
+          }
         }
         const int64_t dd = w - P;
         if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
@@ -238,6 +247,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         if ((mask >> i) & 1) { w -= s_var[old]; mask &= ~(1ULL << i); }
         w += s_mprime[c] - s_mprime[old];
         seq.at(i) = (uint8_t)c;
+        vpos = (vpos & ~(1ULL << i)) | ((int)c == va ? 1ULL << i : 0ULL);
         const int64_t dd = w - P;
         if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
         d = (int32_t)dd;

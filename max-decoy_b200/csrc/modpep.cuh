@@ -29,6 +29,28 @@ __host__ __device__ __forceinline__ uint64_t md_prev_combination(uint64_t m) {
   return (rest & ~low) | moved | packed;
 }
 
+// try_variable_modifications when exactly one letter has a variable modification and no fixed one (M.var_simple_code):
+// the weight depends on the subset size only, and the first subset of size n in NChooseK order is the first n
+// positions.  `allpos` = positions holding that letter, `base` = weight without any variable modification.
+// Same contract as md_try_variable (which calls this): on failure (w, mask) = the last subset tried.
+__device__ __forceinline__ bool md_try_variable_simple(const ModTables& M, uint64_t allpos, int64_t base, int64_t& w, uint64_t& mask, int64_t lo,
+                                                       int64_t hi) {
+  const uint32_t d = (uint32_t)__popcll(allpos);
+  const uint32_t nmax = M.nvar < d ? M.nvar : d;
+  const int64_t delta = M.var[M.var_simple_code];
+  uint64_t first = 0, rest = allpos;
+  for (uint32_t n = 1; n <= nmax; n++) {
+    first |= rest & (~rest + 1); rest &= rest - 1;
+    const int64_t wn = base + (int64_t)n * delta;
+    if (md_in_window(wn, lo, hi)) { w = wn; mask = first; return true; }
+  }
+  // last subset tried: size nmax, the nmax last positions
+  uint64_t last = allpos;
+  for (uint32_t k = d; k > nmax; k--) last &= last - 1;  // drop the d-nmax lowest positions
+  w = base + (int64_t)nmax * delta; mask = last;
+  return false;
+}
+
 // Seq: functor uint32_t operator()(uint32_t i) -> residue code.
 // On return true: (w, mask) = the first configuration inside [lo,hi].  On return false: (w, mask) = the last
 // configuration tried (the reference leaves it applied, which the decoy repair loop then sees), or unchanged
@@ -46,22 +68,7 @@ __device__ bool md_try_variable(const ModTables& M, Seq seq, uint32_t len, int64
   int64_t base = w;
   for (uint64_t m = mask; m; m &= m - 1) base -= M.var[seq((uint32_t)__ffsll((long long)m) - 1)];
   const uint32_t nmax = M.nvar < d ? M.nvar : d;
-  if (M.var_simple_code >= 0) {
-    // one variable letter without fixed mod: the weight depends on the subset size only, and the first
-    // subset of size n in NChooseK order is the first n positions.
-    const int64_t delta = M.var[M.var_simple_code];
-    uint64_t first = 0, rest = allpos;
-    for (uint32_t n = 1; n <= nmax; n++) {
-      first |= rest & (~rest + 1); rest &= rest - 1;
-      int64_t wn = base + (int64_t)n * delta;
-      if (md_in_window(wn, lo, hi)) { w = wn; mask = first; return true; }
-    }
-    // last subset tried: size nmax, the nmax last positions
-    uint64_t last = allpos;
-    for (uint32_t k = d; k > nmax; k--) last &= last - 1;  // drop the d-nmax lowest positions
-    w = base + (int64_t)nmax * delta; mask = last;
-    return false;
-  }
+  if (M.var_simple_code >= 0) return md_try_variable_simple(M, allpos, base, w, mask, lo, hi);
   uint32_t tried = 0;
   uint64_t last_sel = 0; int64_t last_w = w; bool any = false;
   for (uint32_t n = 1; n <= nmax; n++) {
