@@ -32,6 +32,10 @@ struct DecoyTables {
   uint8_t has_var_a[32];
   uint8_t has_fix_a[32];
   int64_t var_a[32];
+  // improving-substitution filter: letter a has a substitution that strictly reduces |d| iff its gap to the next lighter
+  // (d > 0) / heavier (d < 0) distinct mass is < 2|d|.  Gaps sorted ascending + the letter set of every prefix.
+  uint32_t gapb_sorted[32], gapa_sorted[32];   // padded with 0xFFFFFFFF
+  uint32_t maskb_prefix[33], maska_prefix[33];
 };
 
 struct TSeq {  // a lane's working sequence in shared memory (alphabet indices), transposed for conflict-free access
@@ -125,7 +129,10 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   __shared__ int32_t s_mprime[32];      // by alphabet index
   __shared__ int32_t s_var[32];
   __shared__ uint8_t s_runmin[32];
+  __shared__ uint32_t s_gapb[32], s_gapa[32], s_maskb[33], s_maska[33];
+  if (threadIdx.x < 33) { s_maskb[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_maska[threadIdx.x] = T.maska_prefix[threadIdx.x]; }
   if (threadIdx.x < 32) {
+    s_gapb[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gapa[threadIdx.x] = T.gapa_sorted[threadIdx.x];
     const int64_t sm = T.sorted_m[threadIdx.x];
     s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
     s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
@@ -137,9 +144,10 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   // one variable letter without a fixed modification (e.g. Met oxidation): its positions are tracked in `vpos`, and
   // try_variable_modifications needs no walk over the sequence
   const int va = M.var_simple_code >= 0 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
-  constexpr int kSpec = 4;
+  constexpr int kScan = 8;
 
-  bool busy = false, drained = false;
+  bool busy = false, drained = false, fm_stale = true;
+  uint32_t fm = 0;
   uint32_t wi = 0, L = 0, pos = 0, tries = 0;
   int64_t w = 0, P = 0, lo = 0, hi = 0;
   int32_t d = 0;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
           const int64_t dd = w - P;
           if (!dead && (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF)) { *overflow = 2; dead = true; }
           if (dead) store_attempt(O, wi, seq, 0, 0, 0, T, PV);
-          else { busy = true; tries = 0; pos = 0; d = (int32_t)dd; }
+          else { busy = true; tries = 0; pos = 0; d = (int32_t)dd; fm_stale = true; }
         }
       }
     }
@@ -182,17 +190,36 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
     }
     // ---- keep the random-number rings topped up, all lanes together
     if (it % kRngPeriod == 0) { if (busy && rng.count <= 4) rng.produce(); }
-    // ---- one greedy step (modified_peptide.rs:454-487) of every busy lane
+    // ---- one greedy step (modified_peptide.rs:454-487) of every busy lane.  Which LETTERS have a substitution that
+    //      strictly reduces |d| follows from d alone (`fm`, see DecoyTables), so the step scans kScan positions with a
+    //      one-bit test each and runs the full nearest-mass search only at the first position that passes.
     if (busy) {
-      const int32_t best = d < 0 ? -d : d;
-      uint32_t cur[kSpec], ca[kSpec]; bool imp[kSpec];
+      if (fm_stale) {
+        const uint32_t x = 2u * (uint32_t)(d < 0 ? -d : d);
+        const uint32_t* g = d > 0 ? s_gapb : s_gapa;
+        uint32_t k = 0;
+        if (g[k + 15] < x) k += 16;
+        if (g[k + 7] < x) k += 8;
+        if (g[k + 3] < x) k += 4;
+        if (g[k + 1] < x) k += 2;
+        if (g[k] < x) k += 1;
+        fm = d == 0 ? 0u : (d > 0 ? s_maskb[k] : s_maska[k]);
+        fm_stale = false;
+      }
+      uint32_t found = L;
 #pragma unroll
-      for (int j = 0; j < kSpec; j++) {
-        const bool in = pos + j < L;
-        cur[j] = in ? seq.at(pos + j) : 0u;
+      for (int j = kScan - 1; j >= 0; j--) {
+        const uint32_t p = pos + j;
+        if (p < L && ((fm >> seq.at(p)) & 1u)) found = p;
+      }
+      bool hit = false;
+      if (found < L) {
+        pos = found;
+        const uint32_t cur = seq.at(pos);
+        const int32_t best = d < 0 ? -d : d;
         // best single substitution = letter whose (mass+fixed) is closest to mprime[cur] - d; strict improvement,
         // ties by alphabet order (the reference follows HashMap order there)
-        const int32_t target = s_mprime[cur[j]] - d;
+        const int32_t target = s_mprime[cur] - d;
         uint32_t k = 0;
         if (s_sorted[k + 15] < target) k += 16;
         if (s_sorted[k + 7] < target) k += 8;
@@ -204,39 +231,32 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         const int64_t dist_lo = (k > 0) ? (int64_t)target - s_sorted[k - 1] : INT64_MAX;
         const uint32_t a_hi = (k < MD_ALPHABET_SIZE) ? s_runmin[k] : 255u;
         const uint32_t a_lo = (k > 0) ? s_runmin[k - 1] : 255u;
-        int64_t cd;
-        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; ca[j] = a_lo; } else { cd = dist_hi; ca[j] = a_hi; }
-        imp[j] = in && cd < (int64_t)best && ca[j] != cur[j];
-      }
-      int first = kSpec;
-#pragma unroll
-      for (int j = kSpec - 1; j >= 0; j--) if (imp[j]) first = j;
-      bool hit = false;
-      if (first < kSpec) {
-        uint32_t c0 = cur[0], a0 = ca[0];
-#pragma unroll
-        for (int j = 1; j < kSpec; j++) if (first == j) { c0 = cur[j]; a0 = ca[j]; }
-        pos += first;
-        // remove_modification_at + swap + fixed mod of the new letter (:470-482)
-        if ((mask >> pos) & 1) { w -= s_var[c0]; mask &= ~(1ULL << pos); }
-        w += s_mprime[a0] - s_mprime[c0];
-        seq.at(pos) = (uint8_t)a0;
-        vpos = (vpos & ~(1ULL << pos)) | ((int)a0 == va ? 1ULL << pos : 0ULL);
-        if (md_in_window(w, lo, hi)) hit = true;
-        else if (any_var) {
-          if (va >= 0) {
-            if (vpos) hit = md_try_variable_simple(M, vpos, w - (int64_t)__popcll(mask) * M.var[M.var_simple_code], w, mask, lo, hi);
-          } else {
-            TSeqCode sc{seq, T.code_of_a};
-            if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
+        int64_t cd; uint32_t a0;
+        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; a0 = a_lo; } else { cd = dist_hi; a0 = a_hi; }
+        if (cd < (int64_t)best && a0 != cur) {
+          // remove_modification_at + swap + fixed mod of the new letter (:470-482)
+          if ((mask >> pos) & 1) { w -= s_var[cur]; mask &= ~(1ULL << pos); }
+          w += s_mprime[a0] - s_mprime[cur];
+          seq.at(pos) = (uint8_t)a0;
+          vpos = (vpos & ~(1ULL << pos)) | ((int)a0 == va ? 1ULL << pos : 0ULL);
+          if (md_in_window(w, lo, hi)) hit = true;
+          else if (any_var) {
+            if (va >= 0) {
+              if (vpos) hit = md_try_variable_simple(M, vpos, w - (int64_t)__popcll(mask) * M.var[M.var_simple_code], w, mask, lo, hi);
+            } else {
+              TSeqCode sc{seq, T.code_of_a};
+              if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
+            }
           }
+          const int64_t dd = w - P;
+          if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
+          d = (int32_t)dd; fm_stale = true;
+        } else {
+          *overflow = 3;   // the letter filter and the search disagree: cannot happen (reported as an internal error)
         }
-        const int64_t dd = w - P;
-        if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
-        d = (int32_t)dd;
         pos += 1;
       } else {
-        pos += kSpec;
+        pos += kScan;
       }
       if (hit) { store_attempt(O, wi, seq, L, mask, w, T, PV); busy = false; }
       else if (pos >= L) {
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         vpos = (vpos & ~(1ULL << i)) | ((int)c == va ? 1ULL << i : 0ULL);
         const int64_t dd = w - P;
         if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
-        d = (int32_t)dd;
+        d = (int32_t)dd; fm_stale = true;
         pos = 0;
         if (++tries == 100) { store_attempt(O, wi, seq, 0, 0, 0, T, PV); busy = false; }
       }
@@ -463,6 +483,29 @@ DecoyTables make_tables(const ModTables& M) {
     int j = k; while (j > 0 && v[j - 1].m == v[k].m) j--;  // first of the equal-mass run has the lowest alphabet index
     T.run_min_a[k] = (uint8_t)v[j].a;
   }
+  // gap tables
+  {
+    struct G { uint32_t g; int a; };
+    std::vector<G> gb, ga;
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++) {
+      int64_t below = -1, above = -1;
+      for (int c = 0; c < MD_ALPHABET_SIZE; c++) {
+        if (T.mprime[c] < T.mprime[a] && (below < 0 || T.mprime[c] > below)) below = T.mprime[c];
+        if (T.mprime[c] > T.mprime[a] && (above < 0 || T.mprime[c] < above)) above = T.mprime[c];
+      }
+      gb.push_back({below < 0 ? 0xFFFFFFFFu : (uint32_t)std::min<int64_t>(T.mprime[a] - below, 0xFFFFFFFEll), a});
+      ga.push_back({above < 0 ? 0xFFFFFFFFu : (uint32_t)std::min<int64_t>(above - T.mprime[a], 0xFFFFFFFEll), a});
+    }
+    auto by_gap = [](const G& x, const G& y) { return x.g != y.g ? x.g < y.g : x.a < y.a; };
+    std::sort(gb.begin(), gb.end(), by_gap); std::sort(ga.begin(), ga.end(), by_gap);
+    for (int k = 0; k < 32; k++) { T.gapb_sorted[k] = 0xFFFFFFFFu; T.gapa_sorted[k] = 0xFFFFFFFFu; }
+    T.maskb_prefix[0] = 0; T.maska_prefix[0] = 0;
+    for (int k = 0; k < MD_ALPHABET_SIZE; k++) {
+      T.gapb_sorted[k] = gb[k].g; T.maskb_prefix[k + 1] = T.maskb_prefix[k] | (gb[k].g == 0xFFFFFFFFu ? 0u : 1u << gb[k].a);
+      T.gapa_sorted[k] = ga[k].g; T.maska_prefix[k + 1] = T.maska_prefix[k] | (ga[k].g == 0xFFFFFFFFu ? 0u : 1u << ga[k].a);
+    }
+    for (int k = MD_ALPHABET_SIZE + 1; k < 33; k++) { T.maskb_prefix[k] = T.maskb_prefix[MD_ALPHABET_SIZE]; T.maska_prefix[k] = T.maska_prefix[MD_ALPHABET_SIZE]; }
+  }
   return T;
 }
 
@@ -567,6 +610,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total; }
   }
   const int ovf = d2h_scalar(ctx, d_ovf.p);
+  MD_REQUIRE(ovf != 3, MD_ERR_DEVICE, "decoy generation: internal error (substitution filter disagrees with the mass search)");
   MD_REQUIRE(ovf != 2, MD_ERR_UNSUPPORTED, "decoy generation: |weight - precursor| left the 32-bit range (residue or modification masses above ~1000 Da?)");
   MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "variable-modification placement enumeration exceeds 2^22 subsets for one decoy");
 }
