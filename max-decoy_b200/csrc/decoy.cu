@@ -64,7 +64,9 @@ __device__ void store_attempt(const AttemptOut& O, uint64_t slot, const TSeq& se
     ascii[i] = ch; row[i] = code;
     h = md_hash_step(h, ch);
   }
-  for (uint32_t i = L; i < MD_DECOY_ROW; i++) row[i] = MD_CODE_OTHER;
+  for (uint32_t i = L; i < ((L + 15u) & ~15u); i++) row[i] = MD_CODE_OTHER;   // pad the last 16-byte chunk
+  { const uint32_t pad = MD_CODE_OTHER * 0x01010101u;
+    for (uint32_t c = (L + 15u) >> 4; c < MD_DECOY_ROW / 16; c++) reinterpret_cast<uint4*>(row)[c] = make_uint4(pad, pad, pad, pad); }
   h = md_hash_fin(h, L);
   if (is_peptide(ascii, L, h, PV.ht_key, PV.ht_val, PV.ht_mask, PV.seq, PV.off, PV.len)) { O.len[slot] = 0; return; }
   O.len[slot] = (uint8_t)L; O.mask[slot] = mask; O.w[slot] = w; O.hash[slot] = h;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
                                                            const __grid_constant__ DecoyTables T, AttemptOut O, PeptideView PV, int* __restrict__ overflow) {
   __shared__ uint8_t sseq[MD_MAX_PEPTIDE_LEN * kThreads];
   __shared__ uint32_t s_rng[8 * kThreads];
+  __shared__ uint64_t s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
   __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
   __shared__ int32_t s_mprime[32];      // by alphabet index
   __shared__ int32_t s_var[32];
@@ -144,10 +147,12 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   // one variable letter without a fixed modification (e.g. Met oxidation): its positions are tracked in `vpos`, and
   // try_variable_modifications needs no walk over the sequence
   const int va = M.var_simple_code >= 0 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
-  constexpr int kScan = 8;
 
   bool busy = false, drained = false, fm_stale = true;
-  uint32_t fm = 0;
+  uint32_t fm = 0, present = 0;   // letters with an improving substitution at the current d / letters in the sequence
+  uint64_t* pm = s_pm + threadIdx.x;
+  auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= 1ULL << i; present |= 1u << a; };
+  auto del_letter = [&](uint32_t a, uint32_t i) { const uint64_t v = pm[a * kThreads] & ~(1ULL << i); pm[a * kThreads] = v; if (v == 0) present &= ~(1u << a); };
   uint32_t wi = 0, L = 0, pos = 0, tries = 0;
   int64_t w = 0, P = 0, lo = 0, hi = 0;
   int32_t d = 0;
@@ -168,12 +173,13 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
           P = pr.mass; lo = pr.lo; hi = pr.hi;
           rng.start(seed, pr.spectrum_id, att_base[li] + (wi - att_off[li]));
           // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
-          w = MD_WATER_UDA; L = 0; mask = 0; vpos = 0; bool dead = false;
+          w = MD_WATER_UDA; L = 0; mask = 0; vpos = 0; present = 0; bool dead = false;
+          for (int a = 0; a < MD_ALPHABET_SIZE; a++) pm[a * kThreads] = 0;
           for (;;) {
             const uint32_t a = rng.below(MD_ALPHABET_SIZE);
             if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
             if ((int)a == va) vpos |= 1ULL << L;
-            seq.at(L++) = (uint8_t)a;
+            add_letter(a, L); seq.at(L++) = (uint8_t)a;
             w += s_mprime[a];
             if (w > hi) break;
           }
@@ -191,8 +197,8 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
     // ---- keep the random-number rings topped up, all lanes together
     if (it % kRngPeriod == 0) { if (busy && rng.count <= 4) rng.produce(); }
     // ---- one greedy step (modified_peptide.rs:454-487) of every busy lane.  Which LETTERS have a substitution that
-    //      strictly reduces |d| follows from d alone (`fm`, see DecoyTables), so the step scans kScan positions with a
-    //      one-bit test each and runs the full nearest-mass search only at the first position that passes.
+    //      strictly reduces |d| follows from d alone (`fm`, see DecoyTables); per-letter position masks then give the
+    //      first position of the pass that can improve, and only there the full nearest-mass search runs.
     if (busy) {
       if (fm_stale) {
         const uint32_t x = 2u * (uint32_t)(d < 0 ? -d : d);
@@ -206,11 +212,13 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         fm = d == 0 ? 0u : (d > 0 ? s_maskb[k] : s_maska[k]);
         fm_stale = false;
       }
+      // first position at or behind `pos` whose letter can improve (none: the rest of the pass is a no-op)
       uint32_t found = L;
-#pragma unroll
-      for (int j = kScan - 1; j >= 0; j--) {
-        const uint32_t p = pos + j;
-        if (p < L && ((fm >> seq.at(p)) & 1u)) found = p;
+      {
+        uint64_t cand = 0;
+        for (uint32_t m = fm & present; m; m &= m - 1) cand |= pm[(__ffs(m) - 1) * kThreads];
+        cand &= ~0ULL << pos;                       // pos < L <= 60
+        if (cand) found = (uint32_t)__ffsll((long long)cand) - 1;
       }
       bool hit = false;
       if (found < L) {
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
           // remove_modification_at + swap + fixed mod of the new letter (:470-482)
           if ((mask >> pos) & 1) { w -= s_var[cur]; mask &= ~(1ULL << pos); }
           w += s_mprime[a0] - s_mprime[cur];
-          seq.at(pos) = (uint8_t)a0;
+          seq.at(pos) = (uint8_t)a0; del_letter(cur, pos); add_letter(a0, pos);
           vpos = (vpos & ~(1ULL << pos)) | ((int)a0 == va ? 1ULL << pos : 0ULL);
           if (md_in_window(w, lo, hi)) hit = true;
           else if (any_var) {
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         }
         pos += 1;
       } else {
-        pos += kScan;
+        pos = L;
       }
       if (hit) { store_attempt(O, wi, seq, L, mask, w, T, PV); busy = false; }
       else if (pos >= L) {
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         const uint32_t old = seq.at(i);
         if ((mask >> i) & 1) { w -= s_var[old]; mask &= ~(1ULL << i); }
         w += s_mprime[c] - s_mprime[old];
-        seq.at(i) = (uint8_t)c;
+        seq.at(i) = (uint8_t)c; del_letter(old, i); add_letter(c, i);
         vpos = (vpos & ~(1ULL << i)) | ((int)c == va ? 1ULL << i : 0ULL);
         const int64_t dd = w - P;
         if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
