@@ -13,9 +13,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = [sys.executable, os.path.join(ROOT, "max-decoy_b200", "max_decoy.py")]
 
 
+HOST = os.path.join(ROOT, "max-decoy_b200", "host", "max_decoy")
+
+
+def _native_host():
+    if not os.path.exists(HOST):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "max-decoy_b200", "csrc"), "-j8", "-s"])
+        subprocess.check_call(["make", "-C", os.path.dirname(HOST), "-s"])
+    return [HOST]
+
+
 def test_sequence_mass():
-    out = subprocess.check_output(CLI + ["sequence-mass", "-s", "VVGTVK"], text=True)
-    assert out.strip() == "601.379894"                   # tasks/sequence_mass.rs:24-27
+    for cli in (CLI, _native_host()):
+        out = subprocess.check_output(cli + ["sequence-mass", "-s", "VVGTVK"], text=True)
+        assert out.strip() == "601.379894"               # tasks/sequence_mass.rs:24-27
+
+
+def test_native_host_reports_errors_instead_of_falling_back(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    (tmp_path / "db.fasta").write_text(">sp|P00001|X\nMKAAAR\n")
+    r = subprocess.run(_native_host() + ["digest", "-i", str(tmp_path / "db.fasta"), "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
 def test_spectrum_splitup(tmp_path):
@@ -46,3 +66,15 @@ def test_digest_and_identification_end_to_end(tmp_path):
     hits = sum(1 for i, (seq, _) in enumerate(truth) if best.get("scan=%d" % (i + 1), [""] * 6)[5] == seq)
     assert hits >= 6                                       # most database spectra are identified by their generating peptide
     assert (tmp_path / "out" / "1.fasta").exists() and (tmp_path / "out" / "1.comet.params").exists()
+    # the native (C++) host writes the same files from the same inputs
+    subprocess.check_call(_native_host() + ["identification", "-m", str(tmp_path / "mods.csv"), "-s", str(tmp_path / "run.mgf"), "--fasta", str(tmp_path / "db.fasta"),
+                                            "-n", "3", "-d", "40", "-l", "10", "-u", "10", "--seed", "3", "-o", str(tmp_path / "out_native")])
+    for name in ("1.fasta", "7.fasta", "12.fasta"):
+        assert (tmp_path / "out_native" / name).read_text() == (tmp_path / "out" / name).read_text(), name
+    a = (tmp_path / "out_native" / "1.comet.params").read_text().replace("out_native", "out")
+    assert a == (tmp_path / "out" / "1.comet.params").read_text()
+    rows_native = (tmp_path / "out_native" / "psms.csv").read_text().splitlines()
+    assert [r.split(",")[:10] for r in rows_native] == [r.split(",")[:10] for r in rows]
+    subprocess.check_call(_native_host() + ["digest", "-i", str(tmp_path / "db.fasta"), "-c", "2", "-l", "5", "-h", "50", "-o", str(tmp_path / "dig_native")])
+    assert (tmp_path / "dig_native" / "peptides.csv").read_text() == (tmp_path / "dig" / "peptides.csv").read_text()
+    assert (tmp_path / "dig_native" / "peptides_proteins.csv").read_text() == (tmp_path / "dig" / "peptides_proteins.csv").read_text()
