@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   const int va = M.var_simple_code >= 0 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
 
   bool busy = false, drained = false, fm_stale = true;
+  uint32_t pending = 0;           // 1 = hit, 2 = gave up: the result is written when the free lanes refill together
   uint32_t fm = 0, present = 0;   // letters with an improving substitution at the current d / letters in the sequence
   uint64_t* pm = s_pm + threadIdx.x;
   auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= 1ULL << i; present |= 1u << a; };
@@ -161,9 +162,10 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
 
   for (uint32_t it = 0;; it++) {
     // ---- refill: when at least 8 lanes are free (or nobody works), they fetch and grow new attempts together
-    const uint32_t free_m = __ballot_sync(0xffffffffu, !busy && !drained);
+    const uint32_t free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
     const uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
     if (free_m && (__popc(free_m) >= 8 || busy_m == 0)) {
+      if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, mask, w, T, PV); pending = 0; }
       if (!busy && !drained) {
         wi = atomicAdd(queue, 1u);
         if (wi >= total) drained = true;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
       }
     }
     if (__ballot_sync(0xffffffffu, busy) == 0) {
-      if (__ballot_sync(0xffffffffu, !drained) == 0) break;
+      if (__ballot_sync(0xffffffffu, !drained || pending) == 0) break;
       continue;
     }
     // ---- keep the random-number rings topped up, all lanes together
@@ -212,12 +214,17 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         fm = d == 0 ? 0u : (d > 0 ? s_maskb[k] : s_maska[k]);
         fm_stale = false;
       }
-      // first position at or behind `pos` whose letter can improve (none: the rest of the pass is a no-op)
+      // first position at or behind `pos` whose letter can improve (none: the rest of the pass is a no-op): OR of the
+      // position masks of the qualifying letters -- or, when most letters qualify (right after a kick), the complement
+      // of the OR over the few that do not (every position holds exactly one of the present letters).
       uint32_t found = L;
       {
-        uint64_t cand = 0;
-        for (uint32_t m = fm & present; m; m &= m - 1) cand |= pm[(__ffs(m) - 1) * kThreads];
-        cand &= ~0ULL << pos;                       // pos < L <= 60
+        const uint32_t m0 = fm & present, n0 = present & ~fm;
+        const bool inv = __popc(n0) < __popc(m0);
+        uint64_t acc = 0;
+        for (uint32_t m = inv ? n0 : m0; m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
+        uint64_t cand = inv ? ~acc & ((1ULL << L) - 1ULL) : acc;      // L <= 60
+        cand &= ~0ULL << pos;                                          // pos < L
         if (cand) found = (uint32_t)__ffsll((long long)cand) - 1;
       }
       bool hit = false;
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
       } else {
         pos = L;
       }
-      if (hit) { store_attempt(O, wi, seq, L, mask, w, T, PV); busy = false; }
+      if (hit) { pending = 1; busy = false; }
       else if (pos >= L) {
         // random kick (:489-505)
         const uint32_t i = rng.below(L);
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
         d = (int32_t)dd; fm_stale = true;
         pos = 0;
-        if (++tries == 100) { store_attempt(O, wi, seq, 0, 0, 0, T, PV); busy = false; }
+        if (++tries == 100) { pending = 2; busy = false; }
       }
     }
   }
