@@ -187,7 +187,9 @@ typedef enum md_decoy_mode {
    * (utility/decoy_generator.rs:127-188; modified_peptide.rs:451-508) with a counter-based
    * RNG keyed by (seed, spectrum_id, attempt); the reference's RNG is unseeded. */
   MD_DECOY_REFERENCE_RANDOM = 0,
-  /* all compositions in the window in canonical order, permutations in lexicographic order */
+  /* every sequence whose fixed-modification weight lies in the window: compositions (count vectors over MD_ALPHABET)
+   * in ascending lexicographic order, per composition its distinct permutations in ascending lexicographic order;
+   * peptides of the index are skipped; `attempt` = ordinal in that enumeration */
   MD_DECOY_EXHAUSTIVE = 1,
   /* DecoyGenerator::vary_targets (utility/decoy_generator.rs:265-296): shuffled targets */
   MD_DECOY_PERMUTE_TARGET = 2
@@ -232,7 +234,7 @@ typedef struct md_search_params {
   uint32_t n_decoys;            /* -d */
   int32_t decoy_mode;           /* md_decoy_mode */
   uint64_t seed;
-  uint32_t top_k;               /* PSM rows per spectrum */
+  uint32_t top_k;               /* PSM rows per spectrum (<= 128) */
   uint32_t min_peaks;           /* Comet minimum_peaks (comet_parameter.rs:62) */
   uint32_t max_fragment_charge; /* Comet max_fragment_charge (comet_parameter.rs:55) */
   uint32_t keep_decoys;         /* != 0: keep the generated decoys for md_last_decoys_export */

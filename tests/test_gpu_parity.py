@@ -148,3 +148,87 @@ def test_identify_bit_exact(gpu, cpu, mods, nvar, mode, nd):
     assert np.allclose(pg["score"], pc["score"], rtol=1e-5, atol=0)
     assert stg["n_targets"] == stc["n_targets"] and stg["n_decoys"] == stc["n_decoys"]
     assert stg["n_kernel_launches"] > 0
+
+
+def _dense_spectra(n, n_peaks, seed=1):
+    """Spectra with thousands of peaks (more unique bins than the kernel stages in shared memory)."""
+    rng = np.random.default_rng(seed)
+    sp, _ = wl.spectra(600, n, 2)
+    off, mzs, ints = [0], [], []
+    for s in range(n):
+        base = np.sort(np.concatenate([sp.peak_mz[int(sp.peak_off[s]):int(sp.peak_off[s + 1])], rng.uniform(60.0, 2400.0, n_peaks)]))
+        mzs.append(base)
+        ints.append(rng.lognormal(4.0, 1.0, len(base)).astype(np.float32))
+        off.append(off[-1] + len(base))
+    return maxdecoy.Spectra(sp.precursor_mz, sp.charge, np.array(off, dtype=np.uint64), np.concatenate(mzs), np.concatenate(ints))
+
+
+@pytest.mark.parametrize("case", ["wide_window_chunked", "top_k_generic", "dense_peaks", "low_res_bins", "high_charge", "few_peaks_and_empty"])
+def test_identify_kernel_paths(gpu, cpu, case):
+    """The branches of k_score the 10-ppm / top-5 cases never reach: candidate chunks beyond shared memory with the
+    generic top-k merge, top_k > 8, spectra whose binned peaks do not fit shared memory, 1.0005-Da bins (one tile),
+    fragment charges up to 3, and spectra that are not scored at all."""
+    for e in (gpu, cpu):
+        _setup(e, 600, 2, (synth.CAM, synth.OXM), 2)
+    sp, _ = wl.spectra(600, 24, 2, with_ox=True)
+    kw = dict(n_decoys=30, seed=9, top_k=5)
+    if case == "wide_window_chunked":
+        kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=12)     # thousands of targets per spectrum
+    elif case == "top_k_generic":
+        kw.update(top_k=40)
+    elif case == "dense_peaks":
+        sp = _dense_spectra(12, 2500)
+    elif case == "low_res_bins":
+        kw.update(fragment_tolerance=1.0005)
+    elif case == "high_charge":
+        sp = maxdecoy.Spectra(sp.precursor_mz * sp.charge / 5.0 - 1.007276 * sp.charge / 5.0 + 1.007276, np.full(len(sp), 5, dtype=np.uint8), sp.peak_off, sp.peak_mz,
+                              sp.peak_intensity)
+    elif case == "few_peaks_and_empty":
+        off = sp.peak_off.copy()
+        keep = np.ones(len(sp.peak_mz), dtype=bool)
+        for s in (0, 5, 6):                                   # 3 peaks, no peaks, 9 peaks (minimum_peaks = 10)
+            a, b = int(off[s]), int(off[s + 1])
+            keep[a + (3 if s == 0 else (0 if s == 5 else 9)):b] = False
+        lens = np.add.reduceat(keep.astype(np.int64), off[:-1].astype(np.int64))
+        sp = maxdecoy.Spectra(sp.precursor_mz, sp.charge, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64), sp.peak_mz[keep], sp.peak_intensity[keep])
+    prm = SearchParams(10, 10, **kw)
+    pg, stg, scg, offg = gpu.identify(sp, prm, want_all_scores=True)
+    pc, stc, scc, offc = cpu.identify(sp, prm, want_all_scores=True)
+    assert np.array_equal(offg, offc) and np.array_equal(scg, scc)
+    for f in ("spectrum_id", "rank", "is_decoy", "charge", "candidate", "var_mask", "mod_weight", "raw_score", "score", "n_targets", "n_decoys"):
+        assert np.array_equal(pg[f], pc[f]), f
+    if case == "wide_window_chunked":
+        assert int(np.diff(offg).max()) > 1536              # more candidates than one shared-memory chunk
+    if case == "few_peaks_and_empty":
+        assert np.all(pg["rank"][[0, 5, 6]] == 0) and np.any(pg["rank"][1] > 0)
+    # without the per-candidate score output the PSM rows must be the same
+    pg2, _ = gpu.identify(sp, prm)
+    assert pg2.tobytes() == pg.tobytes()
+
+
+def test_error_reporting(gpu):
+    """The ABI reports what the reference panics on (and what lies outside the hot path) as status codes."""
+    e = maxdecoy.Engine()
+    with pytest.raises(maxdecoy.MaxDecoyError) as ei:
+        e.index_build()                                       # no digest yet
+    assert ei.value.status == -2
+    e.digest(list(wl.proteins(50)), 2, 5, 50)
+    with pytest.raises(maxdecoy.MaxDecoyError) as ei:
+        e.set_modifications([maxdecoy.Modification("x:1", "nterm", "N", True, "A", 42.0)], 0)
+    assert ei.value.status == -5                              # terminal modifications: outside the hot path
+    with pytest.raises(maxdecoy.MaxDecoyError):
+        e.digest(["MKR"], 2, 5, 61)
+    e.set_modifications([synth.CAM], 0)
+    e.index_build()
+    sp, _ = wl.spectra(600, 4, 2)
+    with pytest.raises(maxdecoy.MaxDecoyError) as ei:
+        e.identify(sp, SearchParams(10, 10, top_k=500))
+    assert ei.value.status in (-1, -5)
+    bad = maxdecoy.Spectra(sp.precursor_mz[:1], sp.charge[:1], np.array([0, 12], dtype=np.uint64), np.arange(12, 0, -1) * 50.0, np.ones(12, dtype=np.float32))
+    with pytest.raises(maxdecoy.MaxDecoyError) as ei:
+        e.identify(bad, SearchParams(10, 10, n_decoys=0))
+    assert ei.value.status == -1 and "sorted" in str(ei.value)
+    empty = maxdecoy.Spectra(np.zeros(0), np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64), np.zeros(0), np.zeros(0, dtype=np.float32))
+    psms, st = e.identify(empty, SearchParams(10, 10))
+    assert psms.shape == (0, 5) and st["n_spectra"] == 0
+    e.close()
