@@ -99,6 +99,39 @@ void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md
   }
 }
 
+
+// Splits a batch into passes the workspaces can hold: the flattened candidate windows of one pass stay below 2^29 index
+// entries and its decoy slots below 2^26 (open searches with ~1M candidates per spectrum, or 100k-spectrum files, run
+// as several passes; results do not depend on the split).  MD_MAX_PASS_SPECTRA caps the spectra per pass (tests).
+std::vector<uint32_t> plan_passes(md_ctx* ctx, const SpectraDev& S, const md_search_params& p) {
+  const uint32_t n = S.n;
+  IdentifyWorkspace& W = ctx->ws;
+  precursors_dev(ctx, S, p, 0);
+  W.rbegin.need(n + 1); W.rend.need(n + 1);
+  index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
+  std::vector<uint64_t> b(n), e(n);
+  MD_CUDA(cudaMemcpyAsync(b.data(), W.rbegin.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaMemcpyAsync(e.data(), W.rend.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint64_t max_entries = 1ull << 29, max_slots = 1ull << 26;
+  uint64_t max_spectra = 0xFFFFFFFFull;
+  if (const char* env = getenv("MD_MAX_PASS_SPECTRA")) max_spectra = std::max<long long>(1, atoll(env));
+  std::vector<uint32_t> cut{0};
+  uint64_t entries = 0, count = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    const uint64_t sz = e[s] - b[s];
+    MD_REQUIRE(sz < max_entries, MD_ERR_UNSUPPORTED, "one spectrum's precursor window spans more than 2^29 index entries");
+    if (count && (entries + sz > max_entries || (count + 1) * (uint64_t)p.n_decoys > max_slots || count + 1 > max_spectra)) { cut.push_back(s); entries = 0; count = 0; }
+    entries += sz; count++;
+  }
+  cut.push_back(n);
+  return cut;
+}
+
+SpectraDev pass_view(const SpectraDev& S, uint32_t a, uint32_t b) {
+  return SpectraDev{b - a, S.pmz + a, S.charge + a, S.sid ? S.sid + a : nullptr, S.peak_off + a, S.peak_mz, S.peak_int};
+}
+
 }  // namespace
 void md_ctx::mark(const char* what) {
   if (!trace) return;
@@ -355,7 +388,10 @@ int md_identify_device(md_ctx* ctx, const md_spectra* S, const md_search_params*
     uint64_t n_peaks = 0;
     MD_CUDA(cudaMemcpy(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     SpectraDev D{S->n, S->precursor_mz, S->charge, S->spectrum_id, S->peak_off, S->peak_mz, S->peak_intensity};
-    identify_batch(ctx, D, n_peaks, *p, psms_dev, stats, 0, false);
+    const std::vector<uint32_t> cut = plan_passes(ctx, D, *p);
+    MD_REQUIRE(cut.size() == 2 || !p->keep_decoys, MD_ERR_UNSUPPORTED, "keep_decoys needs a batch that fits one pass");
+    for (size_t k = 0; k + 1 < cut.size(); k++)
+      identify_batch(ctx, pass_view(D, cut[k], cut[k + 1]), n_peaks, *p, psms_dev + (size_t)cut[k] * p->top_k, stats, cut[k], false);
     if (stats) fill_kernel_stats(ctx, stats);
   });
 }
@@ -391,27 +427,36 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
       MD_CUDA(cudaMemcpyAsync(W.peak_int.p, S->peak_intensity, np * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     SpectraDev D{n, W.pmz.p, W.charge.p, S->spectrum_id ? W.sid.p : nullptr, W.peak_off.p, W.peak_mz.p, W.peak_int.p};
-    identify_batch(ctx, D, np, *p, W.psm.p, stats, 0, all_scores && all_off);
+    const bool want_all = all_scores && all_off;
+    const std::vector<uint32_t> cut = plan_passes(ctx, D, *p);
+    MD_REQUIRE(cut.size() == 2 || !p->keep_decoys, MD_ERR_UNSUPPORTED, "keep_decoys needs a batch that fits one pass");
+    std::vector<int64_t> flat; std::vector<uint64_t> foff(1, 0);
+    for (size_t k = 0; k + 1 < cut.size(); k++) {
+      const uint32_t a = cut[k], m = cut[k + 1] - cut[k];
+      identify_batch(ctx, pass_view(D, a, a + m), np, *p, W.psm.p + (size_t)a * p->top_k, stats, a, want_all);
+      if (want_all) {  // raw scores of this pass: targets in index order, then decoys
+        std::vector<uint64_t> coff(m + 1); std::vector<uint32_t> dcnt(m, 0);
+        MD_CUDA(cudaMemcpy(coff.data(), W.cand_off.p, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (p->n_decoys) MD_CUDA(cudaMemcpy(dcnt.data(), W.dec_count.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::vector<int64_t> ts(coff[m] + 1), ds((size_t)m * p->n_decoys + 1);
+        if (coff[m]) MD_CUDA(cudaMemcpy(ts.data(), W.tscore.p, coff[m] * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if ((size_t)m * p->n_decoys) MD_CUDA(cudaMemcpy(ds.data(), W.dscore.p, (size_t)m * p->n_decoys * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        for (uint32_t s = 0; s < m; s++) {
+          for (uint64_t c = coff[s]; c < coff[s + 1]; c++) flat.push_back(ts[c]);
+          for (uint32_t j = 0; j < dcnt[s]; j++) flat.push_back(ds[(size_t)s * p->n_decoys + j]);
+          foff.push_back(flat.size());
+        }
+      }
+    }
     if (p->top_k) MD_CUDA(cudaMemcpyAsync(psms, W.psm.p, (size_t)n * p->top_k * sizeof(md_psm), cudaMemcpyDeviceToHost, st));
     MD_CUDA(cudaStreamSynchronize(st));
     if (stats) fill_kernel_stats(ctx, stats);
-    if (all_scores && all_off) {
-      std::vector<uint64_t> coff(n + 1); std::vector<uint32_t> dcnt(n, 0);
-      MD_CUDA(cudaMemcpy(coff.data(), W.cand_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      if (p->n_decoys) MD_CUDA(cudaMemcpy(dcnt.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-      std::vector<int64_t> ts(coff[n] + 1), ds((size_t)n * p->n_decoys + 1);
-      if (coff[n]) MD_CUDA(cudaMemcpy(ts.data(), W.tscore.p, coff[n] * sizeof(int64_t), cudaMemcpyDeviceToHost));
-      if ((size_t)n * p->n_decoys) MD_CUDA(cudaMemcpy(ds.data(), W.dscore.p, (size_t)n * p->n_decoys * sizeof(int64_t), cudaMemcpyDeviceToHost));
-      uint64_t total = coff[n];
-      for (uint32_t s = 0; s < n; s++) total += dcnt[s];
-      int64_t* flat = (int64_t*)malloc((total + 1) * sizeof(int64_t)); uint64_t* off = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
-      uint64_t k = 0; off[0] = 0;
-      for (uint32_t s = 0; s < n; s++) {
-        for (uint64_t c = coff[s]; c < coff[s + 1]; c++) flat[k++] = ts[c];
-        for (uint32_t j = 0; j < dcnt[s]; j++) flat[k++] = ds[(size_t)s * p->n_decoys + j];
-        off[s + 1] = k;
-      }
-      *all_scores = flat; *all_off = off;
+    if (want_all) {
+      int64_t* out_scores = (int64_t*)malloc((flat.size() + 1) * sizeof(int64_t)); uint64_t* out_off = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
+      MD_REQUIRE(out_scores && out_off, MD_ERR_NOMEM, "out of host memory");
+      if (!flat.empty()) memcpy(out_scores, flat.data(), flat.size() * sizeof(int64_t));
+      memcpy(out_off, foff.data(), (n + 1) * sizeof(uint64_t));
+      *all_scores = out_scores; *all_off = out_off;
     }
     if (p->keep_decoys) {
       LastDecoys& L = ctx->last;

@@ -232,3 +232,20 @@ def test_error_reporting(gpu):
     psms, st = e.identify(empty, SearchParams(10, 10))
     assert psms.shape == (0, 5) and st["n_spectra"] == 0
     e.close()
+
+
+def test_passes_do_not_change_results(gpu, cpu, monkeypatch):
+    """Batches too large for the workspaces run as several passes (open searches, 100k-spectrum files); forcing tiny
+    passes must give the same PSM rows and the same per-candidate scores as one pass and as the oracle."""
+    for e in (gpu, cpu):
+        _setup(e, 600, 2, (synth.CAM, synth.OXM), 3)
+    sp, _ = wl.spectra(600, 50, 2, with_ox=True)
+    prm = SearchParams(10, 10, n_decoys=40, seed=3, top_k=5)
+    one, st1, sc1, off1 = gpu.identify(sp, prm, want_all_scores=True)
+    monkeypatch.setenv("MD_MAX_PASS_SPECTRA", "7")
+    many, stm, scm, offm = gpu.identify(sp, prm, want_all_scores=True)
+    monkeypatch.delenv("MD_MAX_PASS_SPECTRA")
+    assert many.tobytes() == one.tobytes() and np.array_equal(scm, sc1) and np.array_equal(offm, off1)
+    assert (stm["n_targets"], stm["n_decoys"], stm["n_pairs"]) == (st1["n_targets"], st1["n_decoys"], st1["n_pairs"])
+    pc, _, scc, offc = cpu.identify(sp, prm, want_all_scores=True)
+    assert np.array_equal(scm, scc) and np.array_equal(many["raw_score"], pc["raw_score"]) and np.array_equal(many["candidate"], pc["candidate"])
