@@ -57,6 +57,7 @@ struct IdentifyWorkspace {
   DevBuf<uint32_t> dec_attempt; DevBuf<uint32_t> dec_count; DevBuf<uint32_t> att_base; DevBuf<uint32_t> att_limit;
   DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters; DevBuf<unsigned long long> stat64;
   // binned spectra
+  DevBuf<uint16_t> gmap; DevBuf<uint32_t> gbits;   // per-CTA block maps in HBM (tables beyond the shared-memory map)
   DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_pre; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;

@@ -12,16 +12,21 @@
 //   T[b]       = 151*y[b] - sum_{j=b-75..b+75} y[j]          (= 150 * 2^16 * fast_xcorr[b])
 //   raw score  = sum over b/y fragments and fragment charges of T[bin];   score = 0.005 * raw / (150 * 2^16)
 //
-// Kernel design (B200): one persistent CTA of 1024 threads per SM (spectra from a global queue).  Per spectrum the CTA
-// stages the sparse binned spectrum (bin, y, prefix sums of y) in shared memory and expands it, tile by tile, into a
-// dense int32 table tile of 49152 bins (192 KiB): vectorised zero fill, then one warp per window edge paints the
-// piecewise-constant -sum(y) segments with coalesced stores (no atomics: segment values come from the prefix sums),
-// then one thread per peak adds the 151*y spike.  Every thread then scores one candidate at a time: the row (residue
-// codes, 16-byte padded) comes in with 128-bit loads, the per-letter packed (quotient, remainder) mass table lives in
-// registers and is read with one warp shuffle per residue, fragment bins follow from a division-free running (q, r)
-// sum, and each fragment costs exactly one shared-memory gather.  Partial scores of a
-// candidate chunk stay in shared memory across tiles; top-k packs (score, ordinal) into one 64-bit key and selects with
-// warp REDUX max.  Nothing but the PSM rows is written to HBM unless the caller asks for all scores.
+// Kernel design (B200): one persistent CTA of 768 threads per SM (spectra from a global queue).  T[b] is non-zero only
+// within 75 bins of a peak, i.e. on a few hundred 64-bin blocks of the 100k+ bins a 0.02-Da table spans, so the CTA keeps
+// a BLOCK-COMPRESSED table in shared memory: a 16-bit block map (bin >> 6 -> compressed block, 0 = the all-zero block)
+// plus up to 719 dense 64-bin blocks (180 KiB of int32).  A centroided MS2 spectrum (~100-400 peaks above the 5 %
+// threshold) fits whole, so every candidate is walked ONCE; denser spectra fall back to several tiles of compressed
+// blocks.  Build: peaks mark their blocks in a bitmap (shared-memory atomicOr), a warp scan numbers the blocks, the
+// occupied blocks are zeroed with vectorised stores, one warp per window edge paints the piecewise-constant -sum(y)
+// segments (values from the prefix sums of y: no atomics), one thread per peak adds the 151*y spike.  Scoring: the
+// candidates are counting-sorted by length into 32-candidate units that warps pull from a shared counter; a thread
+// scores one candidate: 128-bit row loads, the per-letter (q, r) mass table in registers read by warp shuffle, a
+// division-free running (Q, R) prefix, two shared-memory loads per fragment (block map, then table), a stop offset at
+// the last residue instead of a per-residue length predicate, IMAD.WIDE accumulation.  Partial scores of a candidate
+// chunk stay in shared memory across tiles; top-k packs (score, ordinal) into one 64-bit key, warp-local REDUX max,
+// merged by warp 0 while the other warps already stage the next spectrum.  Only PSM rows go to HBM unless the
+// caller asks for all scores.
 #include "cubx.cuh"
 
 namespace {
@@ -33,12 +38,14 @@ constexpr int kXcorrOffset = 75;
 #define MD_SCORE_THREADS 768
 #endif
 constexpr int kScoreThreads = MD_SCORE_THREADS;
-constexpr uint32_t kTileBins = 49152;     // 192 KiB of int32 per CTA
-constexpr uint32_t kCandChunk = 1536;     // candidates whose partial scores stay in shared memory across tiles
-constexpr uint32_t kPeakCap = 1024;       // binned peaks staged in shared memory (larger spectra read them from HBM)
-constexpr uint32_t kMaxBins = 1u << 26;   // table bins per spectrum (byte offsets 4*bin must stay far below kStop4)
+constexpr uint32_t kBlkShift = 6, kBlk = 1u << kBlkShift;      // table block = 64 bins
+constexpr uint32_t kTileBins = 46080;      // 180 KiB of int32 per CTA = 720 blocks, block 0 is the all-zero block
+constexpr uint32_t kTileBlocks = kTileBins / kBlk - 1;          // usable blocks per tile
+constexpr uint32_t kMapCap = 6144;         // block-map entries staged in shared memory (393k bins; larger tables use an HBM map)
+constexpr uint32_t kCandChunk = 1536;      // candidates whose partial scores stay in shared memory across tiles
+constexpr uint32_t kPeakCap = 1024;        // binned peaks staged in shared memory (larger spectra read them from HBM)
+constexpr uint32_t kMaxBins = 1u << 26;    // table bins per spectrum (bins must stay far below kStop)
 constexpr uint32_t kMaxTopK = 128;
-constexpr uint32_t kTileCache = 32;
 constexpr uint32_t kFastTopK = 8;
 
 // ------------------------------------------------------------------------------------------------
@@ -178,8 +185,8 @@ struct ScoreConst {
   uint32_t w;                 // bin width, uDa
   uint32_t qp, rp;            // proton  = qp*w + rp
   uint32_t q2p, r2p;          // 2*proton
-  uint32_t tq4[32], tr[32];   // per residue code: (mass + fixed delta) = q*w + r; tq4 = 4*q (table byte offsets)
-  uint32_t vq4[32], vr[32];   // per residue code: (mass + fixed + variable delta)
+  uint32_t tq[32], tr[32];    // per residue code: (mass + fixed delta) = q*w + r
+  uint32_t vq[32], vr[32];    // per residue code: (mass + fixed + variable delta)
   uint32_t max_frag_charge;
   uint32_t top_k, n_per;
 };
@@ -196,103 +203,95 @@ struct ScoreArgs {
   unsigned long long* stat64;  // [0] pairs scored, [1] algorithmic bytes (14 + len per pair)
   int* error;                  // set when a spectrum needs more table bins than kMaxBins
   unsigned long long* timing;  // MD_SCORE_TIMING=1: per-phase SM cycles summed over CTAs (thread 0's clock), else NULL
+  uint16_t* gmap; uint32_t* gbits; uint32_t gmap_stride;   // per-CTA block map / block bitmap in HBM for tables beyond kMapCap blocks
 };
 
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAAAAABu) >> 1; }
 
-// Raw score of one candidate against the table tile [t0, t0+tn).
-//   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
-// with X = B_k + proton kept as (Q, R), X = Q*w + R, so no fragment needs a division.
-// one table gather, branch-free: the byte offset is clamped to the always-zero slot behind the tile
 __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
   int32_t v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void acc_wide(int64_t& acc, int32_t v) {  // acc += v as one IMAD.WIDE
   asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(acc) : "r"(v));
 }
-#define MD_GATHER(acc, off4) acc_wide(acc, lds_s32(tab_s + min((uint32_t)(off4), tn4)))
-struct LaneTab { uint32_t q4, r, vq4, vr; };   // lane = residue code
-constexpr uint32_t kStop4 = 1u << 30;           // added to the running offset at the last residue: every later bin misses
+// The table as the scoring loop sees it: block map (shared memory address, or an HBM pointer when MAPG) + dense blocks.
+struct TableView { uint32_t tab_s, map_s, nblk; const uint16_t* gmap; };
+// one fragment: bin -> block (clamped onto the map's zero entry) -> compressed block -> table entry; branch-free
+template <bool MAPG>
+__device__ __forceinline__ void gather(int64_t& acc, uint32_t bin, const TableView& V) {
+  const uint32_t blk = min(bin >> kBlkShift, V.nblk);
+  const uint32_t c = MAPG ? (uint32_t)V.gmap[blk] : lds_u16(V.map_s + 2u * blk);
+  acc_wide(acc, lds_s32(V.tab_s + (c << (kBlkShift + 2)) + ((bin & (kBlk - 1u)) << 2)));
+}
+struct LaneTab { uint32_t q, r, vq, vr; };      // lane = residue code
+constexpr uint32_t kStop = 1u << 30;            // added to the running bin at the last residue: every later bin misses
 
 struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; };
 
-// Raw scores of NC candidates of one thread against the table tile [t0, t0+tn).
+// Raw score of one candidate against the (tile of the) block-compressed table.
 //   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
-// with X = B_k + proton kept as (Q, R), X = Q*w + R, R < w, so no fragment needs a division.  Q is carried as the byte
-// offset of the charge-1 b bin in the tile (QB = 4*(Q + 1 - t0), wrapping); bins outside the tile wrap or overshoot and
-// are clamped onto the zero slot tab[tn] by one unsigned min.  The last residue is never a prefix: at position len-1
-// kStop4 is added to QB, which throws every later b and y bin of every charge out of the tile -- no per-residue
-// length predicate.  The loop runs in 4-residue words up to the longest candidate of the warp.
-template <int NCH, bool HASVAR, int NC>
-__device__ __forceinline__ void score_multi(const CandRef (&cr)[NC], uint32_t maxlen, uint32_t tab_s, uint32_t t0, uint32_t tn, const ScoreConst& C,
-                                            const LaneTab& L, int64_t (&out)[NC]) {
-  const uint32_t w = C.w, tn4 = 4u * tn, off4 = 4u * (1u - t0);
-  const uint32_t K2 = 4u * C.qp - off4, K3 = 4u * C.q2p - off4;
+// with X = B_k + proton kept as (Q, R), X = Q*w + R, R < w, so no fragment needs a division.  QB = Q + 1 is the charge-1
+// b bin itself; bins past the table, and the wrapped "negative" ones, are clamped onto the map's zero entry by one
+// unsigned min.  The last residue is never a prefix: at position len-1 kStop is added to QB, which throws every later
+// b and y bin of every charge out of the table -- no per-residue length predicate.  The loop runs in 4-residue words up
+// to the longest candidate of the warp.
+template <int NCH, bool HASVAR, bool MAPG>
+__device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen, const TableView& V, const ScoreConst& C, const LaneTab& L) {
+  const uint32_t w = C.w;
+  const uint32_t K2 = C.qp - 1u, K3 = C.q2p - 1u;
   const uint32_t nword = maxlen > 1 ? (maxlen - 1 + 3) >> 2 : 0;  // warp-uniform
-  uint32_t Y1[NC], Rt1[NC], Y2[NC], Rt2[NC], Y3[NC], Rt3[NC], QB[NC], R1[NC], nsplit[NC];
-  int64_t accb[NC], accy[NC];
-#pragma unroll
-  for (int i = 0; i < NC; i++) {
-    // T_c = modw + (c+1)*proton  ->  (Qt, Rt)
-    const uint64_t T1 = (uint64_t)cr[i].modw + 2ull * MD_PROTON_UDA;
-    uint32_t Qt1 = (uint32_t)(T1 / w); Rt1[i] = (uint32_t)(T1 - (uint64_t)Qt1 * w);
-    uint32_t Qt2 = Qt1 + C.qp; Rt2[i] = Rt1[i] + C.rp; if (Rt2[i] >= w) { Rt2[i] -= w; Qt2++; }
-    uint32_t Qt3 = Qt2 + C.qp; Rt3[i] = Rt2[i] + C.rp; if (Rt3[i] >= w) { Rt3[i] -= w; Qt3++; }
-    Y1[i] = 4u * Qt1 + 2u * off4;               // y1 offset = Y1 - QB - 4*borrow
-    Y2[i] = 4u * Qt2 + off4;                    // 4*(Qt2 - Q - borrow) = Y2 - QB - 4*borrow, then halved
-    Y3[i] = 4u * Qt3 + off4;
-    QB[i] = 4u * C.qp + off4; R1[i] = C.rp;     // X = B_k + proton
-    nsplit[i] = cr[i].len > 0 ? cr[i].len - 1 : 0;   // residues 0..len-2 are followed by a split
-    if (nsplit[i] == 0) QB[i] += kStop4;
-    accb[i] = 0; accy[i] = 0;
-  }
+  // T_c = modw + (c+1)*proton  ->  (Qt, Rt)
+  const uint64_t T1 = (uint64_t)cr.modw + 2ull * MD_PROTON_UDA;
+  const uint32_t Qt1 = (uint32_t)(T1 / w), Rt1 = (uint32_t)(T1 - (uint64_t)Qt1 * w);
+  uint32_t Qt2 = Qt1 + C.qp, Rt2 = Rt1 + C.rp; if (Rt2 >= w) { Rt2 -= w; Qt2++; }
+  uint32_t Qt3 = Qt2 + C.qp, Rt3 = Rt2 + C.rp; if (Rt3 >= w) { Rt3 -= w; Qt3++; }
+  const uint32_t Y1 = Qt1 + 2u;               // y1 bin = Y1 - QB - borrow
+  const uint32_t Y2 = Qt2 + 1u, Y3 = Qt3 + 1u;  // Qt_c - Q - borrow = Y_c - QB - borrow, then halved / divided by 3, + 1
+  uint32_t QB = C.qp + 1u, R1 = C.rp;         // X = B_k + proton
+  const uint32_t nsplit = cr.len > 0 ? cr.len - 1 : 0;   // residues 0..len-2 are followed by a split
+  if (nsplit == 0) QB += kStop;
+  int64_t accb = 0, accy = 0;
   for (uint32_t c = 0; c * 4 < nword; c++) {
-    uint32_t words[NC][4];
-#pragma unroll
-    for (int i = 0; i < NC; i++) { const uint4 v = __ldg(cr[i].row + c); words[i][0] = v.x; words[i][1] = v.y; words[i][2] = v.z; words[i][3] = v.w; }
+    const uint4 v = __ldg(cr.row + c);
+    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (c * 4 + k >= nword) break;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-#pragma unroll
-        for (int i = 0; i < NC; i++) {
-          const uint32_t pos = c * 16 + k * 4 + j;
-          const uint32_t code = words[i][k] >> (8 * j);            // (shfl takes the source lane modulo 32; codes are < 32)
-          uint32_t q4 = __shfl_sync(0xffffffffu, L.q4, code), r = __shfl_sync(0xffffffffu, L.r, code);
-          if (HASVAR) {
-            const uint32_t q4v = __shfl_sync(0xffffffffu, L.vq4, code), rv = __shfl_sync(0xffffffffu, L.vr, code);
-            if ((cr[i].mask >> pos) & 1) { q4 = q4v; r = rv; }
-          }
-          QB[i] += q4; R1[i] += r;
-          if (R1[i] >= w) { R1[i] -= w; QB[i] += 4u; }
-          {  // fragment charge 1
-            const uint32_t yb = Y1[i] - QB[i] - (Rt1[i] < R1[i] ? 4u : 0u);
-            MD_GATHER(accb[i], QB[i]); MD_GATHER(accy[i], yb);
-          }
-          if (NCH >= 2) {
-            const uint32_t x4 = QB[i] + K2 + (R1[i] + C.rp >= w ? 4u : 0u);
-            const uint32_t bb = ((x4 >> 1) & ~3u) + off4;
-            const uint32_t y4 = Y2[i] - QB[i] - (Rt2[i] < R1[i] ? 4u : 0u);
-            const uint32_t yb = ((y4 >> 1) & ~3u) + off4;
-            MD_GATHER(accb[i], bb); MD_GATHER(accy[i], yb);
-          }
-          if (NCH >= 3) {
-            const uint32_t x4 = QB[i] + K3 + (R1[i] + C.r2p >= w ? 4u : 0u);
-            const uint32_t bb = ((__umulhi(x4, 0xAAAAAAABu) >> 1) & ~3u) + off4;   // 4*floor(x/3) from 4*x
-            const uint32_t y4 = Y3[i] - QB[i] - (Rt3[i] < R1[i] ? 4u : 0u);
-            const uint32_t yb = ((__umulhi(y4, 0xAAAAAAABu) >> 1) & ~3u) + off4;
-            MD_GATHER(accb[i], bb); MD_GATHER(accy[i], yb);
-          }
-          if (pos + 1 == nsplit[i]) QB[i] += kStop4;   // the next residue is the last one
+        const uint32_t pos = c * 16 + k * 4 + j;
+        const uint32_t code = words[k] >> (8 * j);            // (shfl takes the source lane modulo 32; codes are < 32)
+        uint32_t q = __shfl_sync(0xffffffffu, L.q, code), r = __shfl_sync(0xffffffffu, L.r, code);
+        if (HASVAR) {
+          const uint32_t qv = __shfl_sync(0xffffffffu, L.vq, code), rv = __shfl_sync(0xffffffffu, L.vr, code);
+          if ((cr.mask >> pos) & 1) { q = qv; r = rv; }
         }
+        QB += q; R1 += r;
+        if (R1 >= w) { R1 -= w; QB++; }
+        {  // fragment charge 1
+          gather<MAPG>(accb, QB, V);
+          gather<MAPG>(accy, Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);
+        }
+        if (NCH >= 2) {
+          gather<MAPG>(accb, ((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
+          gather<MAPG>(accy, ((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
+        }
+        if (NCH >= 3) {
+          gather<MAPG>(accb, div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V);
+          gather<MAPG>(accy, div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V);
+        }
+        if (pos + 1 == nsplit) QB += kStop;   // the next residue is the last one
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NC; i++) out[i] = accb[i] + accy[i];
+  return accb + accy;
 }
 
 __device__ __forceinline__ CandRef cand_ref(const ScoreArgs& A, uint32_t s, uint32_t v, uint32_t nt, uint64_t t0c, uint32_t n_per) {
@@ -337,19 +336,12 @@ __device__ __forceinline__ void write_psm_row(const ScoreArgs& A, const ScoreCon
   A.psm[(uint64_t)s * C.top_k + r] = row;
 }
 
-// first index in [0, n) with a[i] >= x
-__device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* a, uint32_t n, int32_t x) {
-  uint32_t l = 0, h = n;
-  while (l < h) { const uint32_t m = (l + h) >> 1; if (a[m] < x) l = m + 1; else h = m; }
-  return l;
-}
 
 // One warp's share of a tile pass: units of 32 candidates in length-descending order (s_order), fetched from a
 // shared counter, so that warps stay busy until the chunk is done and every warp runs candidates of one length.
-template <int NCH, bool HASVAR>
+template <int NCH, bool HASVAR, bool MAPG>
 __device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst& C, uint32_t s, uint32_t c0, uint32_t cn, uint32_t nt, uint64_t t0c,
-                                            uint32_t tab_s, uint32_t t0, uint32_t tn, const LaneTab& L, int64_t* s_score,
-                                            const uint16_t* s_order, uint32_t* s_unit) {
+                                            const TableView& V, const LaneTab& L, int64_t* s_score, const uint16_t* s_order, uint32_t* s_unit) {
   const uint32_t lane = threadIdx.x & 31, units = (cn + 31) >> 5;
   for (;;) {
     uint32_t u = 0;
@@ -357,17 +349,16 @@ __device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst
     u = __shfl_sync(0xffffffffu, u, 0);
     if (u >= units) break;
     const uint32_t slot = u * 32 + lane;
-    CandRef cr[1];
-    cr[0].row = reinterpret_cast<const uint4*>(A.idx_rows); cr[0].len = 0; cr[0].mask = 0; cr[0].modw = 0;
+    CandRef cr;
+    cr.row = reinterpret_cast<const uint4*>(A.idx_rows); cr.len = 0; cr.mask = 0; cr.modw = 0;
     uint32_t v = 0;
     if (slot < cn) {
       v = s_order[slot];
-      cr[0] = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
+      cr = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
     }
-    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr[0].len);
-    int64_t part[1];
-    score_multi<NCH, HASVAR, 1>(cr, maxlen, tab_s, t0, tn, C, L, part);
-    if (slot < cn) s_score[v] += part[0];
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
+    const int64_t part = score_one<NCH, HASVAR, MAPG>(cr, maxlen, V, C, L);
+    if (slot < cn) s_score[v] += part;
   }
 }
 
@@ -375,32 +366,32 @@ struct SpecShared {
   uint32_t work[2];
   unsigned long long wkey[2][kScoreThreads / 32];
   unsigned long long top[kMaxTopK];
-  long long tacc[8];
   unsigned long long wtop[kScoreThreads / 32][kFastTopK];  // per-warp best keys, descending
+  long long tacc[8];
   uint32_t hist[64];        // candidates per length (counting sort of the chunk)
   uint32_t unit;            // next unit of the current tile pass
-  uint32_t tile_pa[kTileCache], tile_pb[kTileCache];  // peaks that can reach each of the first tiles
+  uint32_t nact;            // occupied table blocks of the spectrum
+  uint32_t bits[kMapCap / 32], bpre[kMapCap / 32];   // occupied-block bitmap and its exclusive popcount prefix
 };
 
 template <bool HASVAR>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C) {
   extern __shared__ __align__(16) int32_t tab[];                     // kTileBins
-  int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins + 4); // kCandChunk (tab[kTileBins] = always-zero sentinel slot)
+  int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins);    // kCandChunk
   int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // kPeakCap
   int32_t* s_yq = s_bin + kPeakCap;                                  // kPeakCap
   uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_yq + kPeakCap);    // kPeakCap + 4
   uint16_t* s_order = reinterpret_cast<uint16_t*>(s_pre + kPeakCap + 4);  // kCandChunk: chunk slots in length-descending order
+  uint16_t* s_map = s_order + kCandChunk;                            // kMapCap + 2
   __shared__ SpecShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t NW = kScoreThreads / 32;
-  // per-letter packed (q, r) tables in registers: lane = residue code
-  const LaneTab L{C.tq4[lane], C.tr[lane], C.vq4[lane], C.vr[lane]};
+  const LaneTab L{C.tq[lane], C.tr[lane], C.vq[lane], C.vr[lane]};   // per-letter (q, r) tables in registers: lane = residue code
   uint32_t my_pairs = 0, my_bytes = 0;   // per thread, summed at the end
   long long t_last = A.timing ? clock64() : 0;
   if (tid < 8) sh.tacc[tid] = 0;
 #define MD_TICK(k) do { if (A.timing && tid == 0) { const long long now_ = clock64(); sh.tacc[k] += now_ - t_last; t_last = now_; } } while (0)
 
-  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
   if (tid == 0) sh.work[0] = atomicAdd(A.work, 1u);
   __syncthreads();
   for (uint32_t it = 0;; it++) {
@@ -420,24 +411,48 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     if (nch > C.max_frag_charge) nch = C.max_frag_charge;
     if (nch < 1) nch = 1;
     const uint32_t NB = hbin >= 0 ? (uint32_t)hbin + kXcorrOffset + 1 : 0;  // table bins [0, NB)
+    const uint32_t nblk = (NB + kBlk - 1) >> kBlkShift;
     bool scored = hbin >= 0;
-    if (NB > kMaxBins || ncand > 0xFFFFFFu) { if (tid == 0) *A.error = 1; scored = false; }
+    const bool mapg = nblk > kMapCap;
+    if (NB > kMaxBins || ncand > 0xFFFFFFu || (mapg && (!A.gmap || nblk + 1 > A.gmap_stride))) { if (tid == 0) *A.error = 1; scored = false; }
+    uint16_t* map = mapg ? A.gmap + (size_t)blockIdx.x * A.gmap_stride : s_map;
+    uint32_t* bits = mapg ? A.gbits + (size_t)blockIdx.x * 2 * (A.gmap_stride / 32 + 1) : sh.bits;
+    uint32_t* bpre = mapg ? bits + (A.gmap_stride / 32 + 1) : sh.bpre;
+    const uint32_t nwords = (nblk + 31) >> 5;
 
-    // ---- stage the binned spectrum
+    // ---- stage the binned spectrum, clear the block bitmap
     const int32_t* pbin = A.pk_bin + pk0; const int32_t* pyq = A.pk_yq + pk0; const uint32_t* ppre = A.pk_pre + pk0 + s;
     if (scored && npk <= kPeakCap) {
       for (uint32_t i = tid; i < npk; i += kScoreThreads) { s_bin[i] = pbin[i]; s_yq[i] = pyq[i]; }
       for (uint32_t i = tid; i <= npk; i += kScoreThreads) s_pre[i] = ppre[i];
       pbin = s_bin; pyq = s_yq; ppre = s_pre;
     }
+    if (scored) for (uint32_t i = tid; i < nwords; i += kScoreThreads) bits[i] = 0;
     for (uint32_t r = tid; r < K; r += kScoreThreads) sh.top[r] = 0ull;
     __syncthreads();
-    // peaks whose window edges can reach each tile: bin in [t0 - 230, t0 + tn + 76)
-    if (scored && tid < kTileCache && (uint64_t)tid * kTileBins < NB) {
-      const uint32_t t0 = tid * kTileBins, tn = min(kTileBins, NB - t0);
-      sh.tile_pa[tid] = lower_bound_i32(pbin, npk, (int32_t)t0 - 230);
-      sh.tile_pb[tid] = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1);
+    // ---- occupied blocks: every bin within 75 of a peak
+    if (scored) {
+      for (uint32_t p = tid; p < npk; p += kScoreThreads) {
+        const int32_t b = pbin[p];
+        const uint32_t b0 = (uint32_t)max(b - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(b + kXcorrOffset), NB - 1) >> kBlkShift;
+        for (uint32_t k = b0; k <= b1; k++) atomicOr(&bits[k >> 5], 1u << (k & 31));
+      }
     }
+    __syncthreads();
+    if (scored && warp == 0) {   // exclusive popcount prefix over the bitmap words
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < nwords; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t c = i < nwords ? (uint32_t)__popc(bits[i]) : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (i < nwords) bpre[i] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) sh.nact = run;
+    }
+    __syncthreads();
+    const uint32_t nact = scored ? sh.nact : 0;
     MD_TICK(0);
 
     const bool fast = K <= kFastTopK && ncand <= kCandChunk;   // warp-local top-k, merged by warp 0 while the others move on
@@ -471,30 +486,37 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         }
       }
       // (visible to the scoring warps after the table-build barriers)
+      MD_TICK(1);
       if (scored && cn) {
-        for (uint32_t t0 = 0; t0 < NB; t0 += kTileBins) {
-          const uint32_t tn = min(kTileBins, NB - t0);
-          const uint32_t ti = t0 / kTileBins;
-          uint32_t pa, pb;
-          if (ti < kTileCache) { pa = sh.tile_pa[ti]; pb = sh.tile_pb[ti]; }
-          else { pa = lower_bound_i32(pbin, npk, (int32_t)t0 - 230); pb = lower_bound_i32(pbin, npk, (int32_t)(t0 + tn) + kXcorrOffset + 1); }
-          if (pa == pb) continue;  // an all-zero tile adds nothing
-          // (1) zero the tile
+        for (uint32_t cb0 = 0; cb0 < nact; cb0 += kTileBlocks) {       // tiles of occupied blocks (usually one)
+          const uint32_t cbn = min(kTileBlocks, nact - cb0);
+          // (1) block map of the tile (0 = the all-zero block), zero the occupied blocks
+          for (uint32_t k = tid; k <= nblk; k += kScoreThreads) {
+            uint32_t m = 0;
+            if (k < nblk) {
+              const uint32_t wd = bits[k >> 5];
+              if ((wd >> (k & 31)) & 1u) {
+                const uint32_t c = bpre[k >> 5] + (uint32_t)__popc(wd & ((1u << (k & 31)) - 1u));
+                if (c >= cb0 && c < cb0 + cbn) m = c - cb0 + 1u;
+              }
+            }
+            map[k] = (uint16_t)m;
+          }
           {
             uint4* z = reinterpret_cast<uint4*>(tab);
-            const uint32_t n4 = (tn + 4) >> 2;            // incl. the zero slot tab[tn] every out-of-tile gather lands on
+            const uint32_t n4 = (cbn + 1u) * (kBlk / 4);
             for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
             if (tid == 0) sh.unit = 0;
           }
           __syncthreads();
-          MD_TICK(1);
+          MD_TICK(2);
           // (2) paint -S[b], S[b] = sum of y over bins [b-75, b+75]: piecewise constant between window edges (no atomics:
           //     the value of every segment comes from the prefix sums of y).
-          //     Edge 2k   = entry of peak pa+k at x = bin-75: S = pre[p+1] - pre[lo], lo = first peak with bin >= x-75
-          //     Edge 2k+1 = exit  of peak pa+k at x = bin+76: S = pre[hi] - pre[p+1], hi = first peak with bin > x+75
-          //     and the segment runs to the next edge of either kind.  One warp per edge, coalesced stores.
-          for (uint32_t e = warp; e < 2 * (pb - pa); e += NW) {
-            const uint32_t p = pa + (e >> 1);
+          //     Edge 2p   = entry of peak p at x = bin-75: S = pre[p+1] - pre[lo], lo = first peak with bin >= x-75
+          //     Edge 2p+1 = exit  of peak p at x = bin+76: S = pre[hi] - pre[p+1], hi = first peak with bin > x+75
+          //     and the segment runs to the next edge of either kind.  One warp per edge; a segment spans <= 4 blocks.
+          for (uint32_t e = warp; e < 2 * npk; e += NW) {
+            const uint32_t p = e >> 1;
             const int32_t bp = pbin[p];
             int32_t xa, xb; uint32_t S;
             if ((e & 1) == 0) {
@@ -513,24 +535,40 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
               if (p + 1 < npk) xb = min(xb, pbin[p + 1] + kXcorrOffset + 1);     // next exit
             }
             if (S == 0) continue;
-            const int32_t a = max(xa, (int32_t)t0), b = min(xb, (int32_t)(t0 + tn));
+            const int32_t a = max(xa, 0), b = min(xb, (int32_t)NB);
+            if (b <= a) continue;
             const int32_t val = -(int32_t)S;
-            for (int32_t x = a + (int32_t)lane; x < b; x += 32) tab[x - (int32_t)t0] = val;
-          }
-          __syncthreads();
-          MD_TICK(2);
-          // (3) the peak's own bin: + 151*y
-          for (uint32_t i = tid; i < pb - pa; i += kScoreThreads) {
-            const uint32_t x = (uint32_t)pbin[pa + i] - t0;
-            if (x < tn) tab[x] += 151 * pyq[pa + i];
+            for (uint32_t k = (uint32_t)a >> kBlkShift; k <= (uint32_t)(b - 1) >> kBlkShift; k++) {
+              const uint32_t m = map[k];
+              if (!m) continue;                                                  // block of another tile
+#pragma unroll
+              for (int h = 0; h < (int)kBlk / 32; h++) {
+                const int32_t x = (int32_t)(k << kBlkShift) + h * 32 + (int32_t)lane;
+                if (x >= a && x < b) tab[(m << kBlkShift) + (uint32_t)(h * 32) + lane] = val;
+              }
+            }
           }
           __syncthreads();
           MD_TICK(3);
+          // (3) the peak's own bin: + 151*y
+          for (uint32_t p = tid; p < npk; p += kScoreThreads) {
+            const uint32_t x = (uint32_t)pbin[p];
+            const uint32_t m = map[x >> kBlkShift];
+            if (m) tab[(m << kBlkShift) + (x & (kBlk - 1u))] += 151 * pyq[p];
+          }
+          __syncthreads();
           // (4) score the chunk against the tile
-          switch (nch) {
-            case 1: score_units<1, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
-            case 2: score_units<2, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
-            default: score_units<3, HASVAR>(A, C, s, c0, cn, nt, t0c, tab_s, t0, tn, L, s_score, s_order, &sh.unit); break;
+          {
+            TableView V;
+            V.tab_s = (uint32_t)__cvta_generic_to_shared(tab); V.map_s = (uint32_t)__cvta_generic_to_shared(s_map); V.nblk = nblk; V.gmap = map;
+            switch (nch * 2 + (mapg ? 1 : 0)) {
+              case 2: score_units<1, HASVAR, false>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+              case 3: score_units<1, HASVAR, true>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+              case 4: score_units<2, HASVAR, false>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+              case 5: score_units<2, HASVAR, true>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+              case 6: score_units<3, HASVAR, false>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+              default: score_units<3, HASVAR, true>(A, C, s, c0, cn, nt, t0c, V, L, s_score, s_order, &sh.unit); break;
+            }
           }
           __syncthreads();
           MD_TICK(4);
@@ -566,7 +604,6 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           if (m == 0ull) break;   // fewer candidates than rows (uniform: every thread sees the same m)
         }
         __syncthreads();
-        MD_TICK(5);
       }
     }
     // ---- PSM rows
@@ -598,13 +635,20 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     } else {
       for (uint32_t r = tid; r < K; r += kScoreThreads) write_psm_row(A, C, pr, s, r, scored ? sh.top[r] : 0ull, nt, nd, t0c);
       __syncthreads();
-      MD_TICK(6);
+      MD_TICK(5);
     }
   }
   if (A.timing && tid == 0) for (int k = 0; k < 8; k++) atomicAdd(&A.timing[k], (unsigned long long)sh.tacc[k]);
   unsigned long long wp = my_pairs, wb = my_bytes;
   for (int o = 16; o; o >>= 1) { wp += __shfl_xor_sync(0xffffffffu, wp, o); wb += __shfl_xor_sync(0xffffffffu, wb, o); }
   if (lane == 0 && wp) { atomicAdd(&A.stat64[0], wp); atomicAdd(&A.stat64[1], wb); }
+}
+
+__global__ void k_max_i32(const int32_t* __restrict__ v, uint32_t n, int32_t* __restrict__ out) {
+  int32_t m = INT32_MIN;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 void split_qr(int64_t m, uint32_t w, uint32_t* q, uint32_t* r) {
@@ -630,11 +674,15 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_REQUIRE(p.top_k <= kMaxTopK, MD_ERR_UNSUPPORTED, "top_k > 128");
   // ---- K4a
   W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_pre.need(n_peaks + n + 2); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
-  DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(2);
-  MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 2 * sizeof(int), ctx->stream));
+  DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
+  MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 4 * sizeof(int), ctx->stream));
   MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), ctx->stream));
   MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
             W.pk_pre.p, W.pk_count.p, W.pk_hbin.p, d_flag.p);
+  // the largest table of the batch decides whether the block maps fit shared memory
+  MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
+  int h_pre[4] = {0, 0, 0, 0};
+  MD_CUDA(cudaMemcpyAsync(h_pre, d_flag.p, sizeof(h_pre), cudaMemcpyDeviceToHost, ctx->stream));
   // ---- K4
   ScoreConst C;
   memset(&C, 0, sizeof(C));
@@ -646,20 +694,22 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     int64_t m = c < MD_NCODES ? ctx->mods.mass[c] : 0;
     int64_t f = (c < MD_NCODES && ctx->mods.has_fix[c]) ? ctx->mods.fix[c] : 0;
     int64_t v = (c < MD_NCODES && ctx->mods.has_var[c]) ? ctx->mods.var[c] : 0;
-    uint32_t q, r;
-    split_qr(m + f, C.w, &q, &r);
-    MD_REQUIRE(q < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
-    C.tq4[c] = 4u * q; C.tr[c] = r;
-    split_qr(m + f + v, C.w, &q, &r);
-    MD_REQUIRE(q < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
-    C.vq4[c] = 4u * q; C.vr[c] = r;
+    split_qr(m + f, C.w, &C.tq[c], &C.tr[c]);
+    split_qr(m + f + v, C.w, &C.vq[c], &C.vr[c]);
+    MD_REQUIRE(C.tq[c] < (1u << 22) && C.vq[c] < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
     if (c < MD_NCODES && ctx->mods.has_var[c]) has_var = true;
   }
   uint64_t n_targets = 0;
-  if (want_all) {
-    MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    MD_CUDA(cudaStreamSynchronize(ctx->stream));
-    W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1);
+  if (want_all) MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  MD_REQUIRE(!h_pre[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
+  if (want_all) { W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1); }
+  const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
+  const uint32_t max_nblk = h_pre[2] >= 0 ? ((uint32_t)h_pre[2] + kXcorrOffset + 1 + kBlk - 1) / kBlk : 0;
+  uint32_t gstride = 0;
+  if (max_nblk > kMapCap && max_nblk <= (kMaxBins >> kBlkShift)) {   // block maps of this batch do not fit shared memory
+    gstride = (max_nblk + 64) & ~31u;
+    W.gmap.need((size_t)grid * gstride); W.gbits.need((size_t)grid * 2 * (gstride / 32 + 1));
   }
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
@@ -673,8 +723,9 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
   A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
   A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
-  const size_t smem = ((size_t)kTileBins + 4) * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4 + (size_t)kCandChunk * 2;
-  const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
+  A.gmap = gstride ? W.gmap.p : nullptr; A.gbits = gstride ? W.gbits.p : nullptr; A.gmap_stride = gstride;
+  const size_t smem = (size_t)kTileBins * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4 +
+                      (size_t)kCandChunk * 2 + ((size_t)kMapCap + 2) * 2;
   MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (has_var) {
     MD_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -694,11 +745,10 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     unsigned long long t[8];
     MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
     double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
-    static const char* names[6] = {"stage", "zero", "paint", "spike", "score", "topk"};
+    static const char* names[6] = {"stage+blocks", "sort", "map+zero", "paint", "spike+score", "topk"};
     fprintf(stderr, "[md_score_timing] grid=%u", grid);
     for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.1f%%", names[k], 100.0 * (double)t[k] / tot);
     fprintf(stderr, " cycles/CTA=%.0f\n", tot / grid);
   }
-  MD_REQUIRE(!h_flag[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
   MD_REQUIRE(!h_flag[1], MD_ERR_UNSUPPORTED, "a spectrum needs more than 2^26 fragment bins or has more than 2^24 candidates");
 }
