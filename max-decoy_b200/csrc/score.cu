@@ -337,17 +337,6 @@ __device__ __forceinline__ void write_psm_row(const ScoreArgs& A, const ScoreCon
 }
 
 
-__device__ __forceinline__ uint32_t scan_lo(const int32_t* pbin, uint32_t p, int32_t bp) {
-  uint32_t lo = p;
-  while (lo > 0 && pbin[lo - 1] >= bp - 2 * kXcorrOffset) lo--;
-  return lo;
-}
-__device__ __forceinline__ uint32_t scan_hi(const int32_t* pbin, uint32_t p, int32_t bp, uint32_t npk) {
-  uint32_t hi = p + 1;
-  while (hi < npk && pbin[hi] <= bp + 2 * kXcorrOffset + 1) hi++;
-  return hi;
-}
-
 // One warp's share of a tile pass: units of 32 candidates in length-descending order (s_order), fetched from a
 // shared counter, so that warps stay busy until the chunk is done and every warp runs candidates of one length.
 template <int NCH, bool HASVAR, bool MAPG>
@@ -469,6 +458,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     const bool fast = K <= kFastTopK && ncand <= kCandChunk;   // warp-local top-k, merged by warp 0 while the others move on
     for (uint32_t c0 = 0; c0 < ncand || c0 == 0; c0 += kCandChunk) {
       const uint32_t cn = min(kCandChunk, ncand - c0);
+      for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
       // counting sort of the chunk by peptide length, longest first
       if (tid < 64) sh.hist[tid] = 0;
       __syncthreads();
@@ -497,19 +487,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       }
       // (visible to the scoring warps after the table-build barriers)
       MD_TICK(1);
-      if (!(scored && cn && nact)) for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;   // nothing to score against
       if (scored && cn) {
-        // neighbourhood of every peak, worked out by one thread per peak (the partial scores' memory is free until the
-        // table is built): near[2p] = first peak with bin >= bin_p - 150, near[2p+1] = first peak with bin > bin_p + 151
-        // (single-tile spectra only: with several tiles that memory holds partial scores from the second tile on)
-        uint16_t* near = (npk <= kPeakCap && nact <= kTileBlocks) ? reinterpret_cast<uint16_t*>(s_score) : nullptr;
-        if (near) {
-          for (uint32_t q = tid; q < npk; q += kScoreThreads) {
-            const int32_t bq = pbin[q];
-            near[2 * q] = (uint16_t)scan_lo(pbin, q, bq); near[2 * q + 1] = (uint16_t)scan_hi(pbin, q, bq, npk);
-          }
-          __syncthreads();
-        }
         for (uint32_t cb0 = 0; cb0 < nact; cb0 += kTileBlocks) {       // tiles of occupied blocks (usually one)
           const uint32_t cbn = min(kTileBlocks, nact - cb0);
           // (1) block map of the tile (0 = the all-zero block), zero the occupied blocks
@@ -542,13 +520,15 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
             const int32_t bp = pbin[p];
             int32_t xa, xb; uint32_t S;
             if ((e & 1) == 0) {
-              const uint32_t lo = near ? near[2 * p] : scan_lo(pbin, p, bp);
+              uint32_t lo = p;
+              while (lo > 0 && pbin[lo - 1] >= bp - 2 * kXcorrOffset) lo--;
               S = ppre[p + 1] - ppre[lo];
               xa = bp - kXcorrOffset;
               xb = pbin[lo] + kXcorrOffset + 1;                                  // next exit
               if (p + 1 < npk) xb = min(xb, pbin[p + 1] - kXcorrOffset);         // next entry
             } else {
-              const uint32_t hi = near ? near[2 * p + 1] : scan_hi(pbin, p, bp, npk);
+              uint32_t hi = p + 1;
+              while (hi < npk && pbin[hi] <= bp + 2 * kXcorrOffset + 1) hi++;
               S = ppre[hi] - ppre[p + 1];
               xa = bp + kXcorrOffset + 1;
               xb = hi < npk ? pbin[hi] - kXcorrOffset : INT32_MAX;               // next entry
@@ -570,8 +550,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           }
           __syncthreads();
           MD_TICK(3);
-          // (3) the peak's own bin: + 151*y  (and the partial scores start at zero)
-          if (cb0 == 0) for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
+          // (3) the peak's own bin: + 151*y
           for (uint32_t p = tid; p < npk; p += kScoreThreads) {
             const uint32_t x = (uint32_t)pbin[p];
             const uint32_t m = map[x >> kBlkShift];
