@@ -376,7 +376,7 @@ def main():
         "roofline": {"kernel": "k_score (fused fragment-and-score + top-k)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": int(st["score_bytes"]), "launch_ms": st["ms_kernel_score"], "pairs_per_launch": int(st["n_pairs"]),
-                     "note": "algorithmic bytes = sum over scored pairs of (14 + peptide length); the kernel is shared-memory-gather bound, see DESIGN.md"},
+                     "note": "algorithmic bytes = sum over scored pairs of (14 + peptide length); the kernel is integer-issue / shared-memory-gather bound, see DESIGN.md section 5"},
         "stage_ms_per_step": {"lookup": st["ms_lookup"], "decoys": st["ms_decoys"], "score": st["ms_score"], "kernel_decoy_attempts": st["ms_kernel_decoy"],
                               "kernel_score": st["ms_kernel_score"], "decoy_attempts": int(st["n_attempts"])},
         "one_time": {"digest_s": t_digest, "index_build_s": t_index, "synthetic_generation_s": t_gen},
