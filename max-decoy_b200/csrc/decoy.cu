@@ -113,29 +113,78 @@ struct RngRing {
 };
 constexpr uint32_t kRngPeriod = 6;
 
-// One lane = one attempt at a time, run as a flat state machine: every pass of the kernel loop does ONE greedy step for
-// every lane that has an attempt (kSpec positions evaluated side by side against the current residual: independent
-// search chains; the first improving substitution is applied and the positions behind it are looked at again in the
-// next step), so the lanes of a warp stay in the same code although their attempts are at different tries / positions
-// / lengths (nested try/position loops would make 31 finished lanes wait for the one that runs all 100 tries).  Lanes
-// whose attempt ends (hit, or 100 tries without one) park until a quarter of the warp is free, then fetch and grow new
-// attempts together.  All residual arithmetic is 32-bit: |w - P| stays far below 2^30 uDa after the grow phase
-// (checked; reported via `overflow`).
-__global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* __restrict__ prec, const uint32_t* __restrict__ list,
-                                                           const uint32_t* __restrict__ att_off, const uint32_t* __restrict__ att_base, uint32_t n_list,
-                                                           uint32_t total, uint32_t* __restrict__ queue, uint64_t seed, const __grid_constant__ ModTables M,
-                                                           const __grid_constant__ DecoyTables T, AttemptOut O, PeptideView PV, int* __restrict__ overflow) {
-  __shared__ uint8_t sseq[MD_MAX_PEPTIDE_LEN * kThreads];
+// position masks are 32 bits wide in the narrow pass (sequences of <= 32 residues: nearly all of them) and 64 in the wide one
+template <class MaskT> struct MaskOps;
+template <> struct MaskOps<uint32_t> {
+  static constexpr uint32_t bits = 32;
+  static __device__ __forceinline__ uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }
+  static __device__ __forceinline__ uint32_t popc(uint32_t v) { return (uint32_t)__popc(v); }
+};
+template <> struct MaskOps<uint64_t> {
+  static constexpr uint32_t bits = 64;
+  static __device__ __forceinline__ uint32_t ffs(uint64_t v) { return (uint32_t)__ffsll((long long)v); }
+  static __device__ __forceinline__ uint32_t popc(uint64_t v) { return (uint32_t)__popcll(v); }
+};
+
+// try_variable_modifications (modified_peptide.rs:512-543) for one variable letter without a fixed modification, on the
+// residual d = weight - precursor: the weight depends on the subset size only, and the first subset of size n in NChooseK
+// order is the first n positions (same contract as md_try_variable_simple: on failure the last subset stays applied).
+template <class MaskT>
+__device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t delta, MaskT allpos, int32_t& d, MaskT& mask, int32_t dlo, uint32_t span) {
+  using MO = MaskOps<MaskT>;
+  const uint32_t cnt = MO::popc(allpos);
+  const uint32_t nmax = nvar < cnt ? nvar : cnt;
+  const int32_t base = d - (int32_t)MO::popc(mask) * delta;
+  MaskT first = 0, rest = allpos;
+  for (uint32_t n = 1; n <= nmax; n++) {
+    first |= rest & ((MaskT)0 - rest); rest &= rest - 1;
+    const int32_t dn = base + (int32_t)n * delta;
+    if ((uint32_t)dn - (uint32_t)dlo <= span) { d = dn; mask = first; return true; }
+  }
+  MaskT last = allpos;
+  for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;   // the nmax last positions
+  d = base + (int32_t)nmax * delta; mask = last;
+  return false;
+}
+
+struct RandomArgs {
+  const md_precursor* prec; const uint32_t* list; const uint32_t* att_off; const uint32_t* att_base;
+  uint32_t n_list, total;
+  uint32_t* queue;                       // work counter of this launch
+  const uint32_t* remap; const uint32_t* remap_n;   // wide pass: work item -> attempt (the narrow pass's spill list), or NULL
+  uint32_t* spill; uint32_t* spill_n;    // narrow pass: attempts that grew past 32 residues, left to the wide pass
+  uint64_t seed; int* overflow;
+};
+
+// One lane = one attempt at a time, run as a flat state machine: every pass of the kernel loop does ONE step for every
+// lane that has an attempt -- the first improving substitution at or behind the pass position, or, when the pass is
+// over, the random kick -- and both kinds of step end in the same "put letter c at position p" code, so the lanes of a
+// warp stay together although their attempts are at different tries / positions / lengths (nested try/position loops
+// would make 31 finished lanes wait for the one that runs all 100 tries).  Lanes whose attempt ends (hit, or 100 tries
+// without one) park until a quarter of the warp is free, then fetch and grow new attempts together.  Inside the loop an
+// attempt is its residual d = weight - precursor in 32 bits (|d| stays far below 2^30 uDa after the grow phase; checked,
+// reported via `overflow`) and the window is [dlo, dlo + span] in the same space.
+// VMODE: 0 = no variable modification can apply, 1 = one variable letter without a fixed modification (its positions are
+// tracked, try_variable_modifications needs no walk over the sequence), 2 = anything else (generic enumeration).
+template <int VMODE, class MaskT>
+__global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, const __grid_constant__ ModTables M, const __grid_constant__ DecoyTables T,
+                                                           AttemptOut O, PeptideView PV) {
+  using MO = MaskOps<MaskT>;
+  constexpr uint32_t kBits = MO::bits;
+  constexpr bool kNarrow = kBits < MD_MAX_PEPTIDE_LEN;
+  constexpr uint32_t kRows = kNarrow ? kBits : MD_MAX_PEPTIDE_LEN;
+  constexpr uint32_t kAbove = 40;       // offset of the d < 0 tables
+  __shared__ uint8_t sseq[kRows * kThreads];
   __shared__ uint32_t s_rng[8 * kThreads];
-  __shared__ uint64_t s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
+  __shared__ MaskT s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
   __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
   __shared__ int32_t s_mprime[32];      // by alphabet index
   __shared__ int32_t s_var[32];
   __shared__ uint8_t s_runmin[32];
-  __shared__ uint32_t s_gapb[32], s_gapa[32], s_maskb[33], s_maska[33];
-  if (threadIdx.x < 33) { s_maskb[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_maska[threadIdx.x] = T.maska_prefix[threadIdx.x]; }
+  __shared__ uint32_t s_gap[kAbove + 32], s_gmask[kAbove + 33];   // d > 0 tables at [0..], d < 0 tables at [kAbove..]
+  if (threadIdx.x < 33) { s_gmask[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_gmask[kAbove + threadIdx.x] = T.maska_prefix[threadIdx.x]; }
   if (threadIdx.x < 32) {
-    s_gapb[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gapa[threadIdx.x] = T.gapa_sorted[threadIdx.x];
+    s_gap[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gap[kAbove + threadIdx.x] = T.gapa_sorted[threadIdx.x];
     const int64_t sm = T.sorted_m[threadIdx.x];
     s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
     s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
@@ -143,52 +192,63 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
   }
   __syncthreads();
   TSeq seq{sseq + threadIdx.x};
-  const bool any_var = M.nvar > 0;
-  // one variable letter without a fixed modification (e.g. Met oxidation): its positions are tracked in `vpos`, and
-  // try_variable_modifications needs no walk over the sequence
-  const int va = M.var_simple_code >= 0 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
+  const int va = VMODE == 1 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
+  const int32_t vdelta = VMODE == 1 ? (int32_t)M.var[M.var_simple_code] : 0;
+  const uint32_t total = A.remap ? *A.remap_n : A.total;
 
-  bool busy = false, drained = false, fm_stale = true;
+  bool busy = false, drained = false;
   uint32_t pending = 0;           // 1 = hit, 2 = gave up: the result is written when the free lanes refill together
-  uint32_t fm = 0, present = 0;   // letters with an improving substitution at the current d / letters in the sequence
-  uint64_t* pm = s_pm + threadIdx.x;
-  auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= 1ULL << i; present |= 1u << a; };
-  auto del_letter = [&](uint32_t a, uint32_t i) { const uint64_t v = pm[a * kThreads] & ~(1ULL << i); pm[a * kThreads] = v; if (v == 0) present &= ~(1u << a); };
-  uint32_t wi = 0, L = 0, pos = 0, tries = 0;
-  int64_t w = 0, P = 0, lo = 0, hi = 0;
-  int32_t d = 0;
-  uint64_t mask = 0, vpos = 0;
-  RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(seed, 0, 0);
+  uint32_t present = 0;           // letters in the sequence
+  MaskT* pm = s_pm + threadIdx.x;
+  auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= (MaskT)1 << i; present |= 1u << a; };
+  auto del_letter = [&](uint32_t a, uint32_t i) { const MaskT v = pm[a * kThreads] & ~((MaskT)1 << i); pm[a * kThreads] = v; if (v == 0) present &= ~(1u << a); };
+  uint32_t wi = 0, L = 0, pos = 0, tries = 0, span = 0, flags = 0;
+  int64_t P = 0;
+  int32_t d = 0, dlo = 0;
+  MaskT mask = 0, vpos = 0, lmask = 0;
+  RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(A.seed, 0, 0);
 
   for (uint32_t it = 0;; it++) {
     // ---- refill: when at least 8 lanes are free (or nobody works), they fetch and grow new attempts together
     const uint32_t free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
     const uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
     if (free_m && (__popc(free_m) >= 8 || busy_m == 0)) {
-      if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, mask, w, T, PV); pending = 0; }
+      if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, (uint64_t)mask, P + d, T, PV); pending = 0; }
       if (!busy && !drained) {
-        wi = atomicAdd(queue, 1u);
-        if (wi >= total) drained = true;
+        const uint32_t q = atomicAdd(A.queue, 1u);
+        if (q >= total) drained = true;
         else {
-          const uint32_t li = find_entry(att_off, n_list, wi);
-          const md_precursor pr = prec[list[li]];
-          P = pr.mass; lo = pr.lo; hi = pr.hi;
-          rng.start(seed, pr.spectrum_id, att_base[li] + (wi - att_off[li]));
+          wi = A.remap ? A.remap[q] : q;
+          const uint32_t li = find_entry(A.att_off, A.n_list, wi);
+          const md_precursor pr = A.prec[A.list[li]];
+          P = pr.mass;
+          rng.start(A.seed, pr.spectrum_id, A.att_base[li] + (wi - A.att_off[li]));
           // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
-          w = MD_WATER_UDA; L = 0; mask = 0; vpos = 0; present = 0; bool dead = false;
+          int64_t w = MD_WATER_UDA;
+          L = 0; mask = 0; vpos = 0; present = 0; bool dead = false;
           for (int a = 0; a < MD_ALPHABET_SIZE; a++) pm[a * kThreads] = 0;
           for (;;) {
             const uint32_t a = rng.below(MD_ALPHABET_SIZE);
             if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
-            if ((int)a == va) vpos |= 1ULL << L;
-            add_letter(a, L); seq.at(L++) = (uint8_t)a;
+            if (!kNarrow || L < kBits) {
+              if (VMODE == 1 && (int)a == va) vpos |= (MaskT)1 << L;
+              add_letter(a, L); seq.at(L) = (uint8_t)a;
+            }
+            L++;
             w += s_mprime[a];
-            if (w > hi) break;
+            if (w > pr.hi) break;
           }
-          const int64_t dd = w - P;
-          if (!dead && (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF)) { *overflow = 2; dead = true; }
-          if (dead) store_attempt(O, wi, seq, 0, 0, 0, T, PV);
-          else { busy = true; tries = 0; pos = 0; d = (int32_t)dd; fm_stale = true; }
+          if (kNarrow && !dead && L > kBits) {
+            A.spill[atomicAdd(A.spill_n, 1u)] = wi;       // the wide pass runs this attempt (same RNG stream, same slot)
+          } else {
+            const int64_t dd = w - P, dl = pr.lo - P, sp = pr.hi - pr.lo;
+            if (!dead && (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF || dl > 0x3FFFFFFF || dl < -0x3FFFFFFF || sp < 0 || sp > 0x7FFFFFFF)) { flags |= 2u; dead = true; }
+            if (dead) store_attempt(O, wi, seq, 0, 0, 0, T, PV);
+            else {
+              busy = true; tries = 0; pos = 0; d = (int32_t)dd; dlo = (int32_t)dl; span = (uint32_t)sp;
+              lmask = L >= kBits ? ~(MaskT)0 : (((MaskT)1 << L) - 1);
+            }
+          }
         }
       }
     }
@@ -198,43 +258,43 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
     }
     // ---- keep the random-number rings topped up, all lanes together
     if (it % kRngPeriod == 0) { if (busy && rng.count <= 4) rng.produce(); }
-    // ---- one greedy step (modified_peptide.rs:454-487) of every busy lane.  Which LETTERS have a substitution that
-    //      strictly reduces |d| follows from d alone (`fm`, see DecoyTables); per-letter position masks then give the
-    //      first position of the pass that can improve, and only there the full nearest-mass search runs.
     if (busy) {
-      if (fm_stale) {
-        const uint32_t x = 2u * (uint32_t)(d < 0 ? -d : d);
-        const uint32_t* g = d > 0 ? s_gapb : s_gapa;
+      // ---- which LETTERS have a substitution that strictly reduces |d| follows from d alone (see DecoyTables) ...
+      uint32_t fm;
+      {
+        const uint32_t ad = (uint32_t)(d < 0 ? -d : d), x = 2u * ad;
+        const uint32_t gofs = d > 0 ? 0u : kAbove;
+        const uint32_t* g = s_gap + gofs;
         uint32_t k = 0;
         if (g[k + 15] < x) k += 16;
         if (g[k + 7] < x) k += 8;
         if (g[k + 3] < x) k += 4;
         if (g[k + 1] < x) k += 2;
         if (g[k] < x) k += 1;
-        fm = d == 0 ? 0u : (d > 0 ? s_maskb[k] : s_maska[k]);
-        fm_stale = false;
+        fm = s_gmask[gofs + k];                                          // d == 0: x == 0, k == 0, empty prefix
       }
-      // first position at or behind `pos` whose letter can improve (none: the rest of the pass is a no-op): OR of the
-      // position masks of the qualifying letters -- or, when most letters qualify (right after a kick), the complement
-      // of the OR over the few that do not (every position holds exactly one of the present letters).
-      uint32_t found = L;
+      // ---- ... and the per-letter position masks give the first position of the pass that can improve: OR of the masks of
+      //      the qualifying letters -- or, when most letters qualify (right after a kick), the complement of the OR over
+      //      the few that do not (every position holds exactly one of the present letters).
+      MaskT cand;
       {
         const uint32_t m0 = fm & present, n0 = present & ~fm;
         const bool inv = __popc(n0) < __popc(m0);
-        uint64_t acc = 0;
+        MaskT acc = 0;
         for (uint32_t m = inv ? n0 : m0; m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
-        uint64_t cand = inv ? ~acc & ((1ULL << L) - 1ULL) : acc;      // L <= 60
-        cand &= ~0ULL << pos;                                          // pos < L
-        if (cand) found = (uint32_t)__ffsll((long long)cand) - 1;
+        cand = inv ? ~acc & lmask : acc;
+        cand = pos < L ? cand & (~(MaskT)0 << pos) : (MaskT)0;           // pos == L: the pass ended with a substitution
       }
-      bool hit = false;
-      if (found < L) {
-        pos = found;
-        const uint32_t cur = seq.at(pos);
-        const int32_t best = d < 0 ? -d : d;
-        // best single substitution = letter whose (mass+fixed) is closest to mprime[cur] - d; strict improvement,
+      // ---- the step: substitution at the first improving position (modified_peptide.rs:454-487), else the kick (:489-505)
+      const bool sub = cand != 0;
+      uint32_t p;
+      if (sub) p = MO::ffs(cand) - 1u; else p = rng.below(L);
+      const uint32_t old = seq.at(p);
+      uint32_t c;
+      if (sub) {
+        // best single substitution = letter whose (mass+fixed) is closest to mprime[old] - d; strict improvement,
         // ties by alphabet order (the reference follows HashMap order there)
-        const int32_t target = s_mprime[cur] - d;
+        const int32_t target = s_mprime[old] - d;
         uint32_t k = 0;
         if (s_sorted[k + 15] < target) k += 16;
         if (s_sorted[k + 7] < target) k += 8;
@@ -242,55 +302,51 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const md_precursor* _
         if (s_sorted[k + 1] < target) k += 2;
         if (s_sorted[k] < target) k += 1;
         // candidates: sorted[k-1] (< target) and sorted[k] (>= target)
-        const int64_t dist_hi = (k < MD_ALPHABET_SIZE) ? (int64_t)s_sorted[k] - target : INT64_MAX;
-        const int64_t dist_lo = (k > 0) ? (int64_t)target - s_sorted[k - 1] : INT64_MAX;
-        const uint32_t a_hi = (k < MD_ALPHABET_SIZE) ? s_runmin[k] : 255u;
-        const uint32_t a_lo = (k > 0) ? s_runmin[k - 1] : 255u;
-        int64_t cd; uint32_t a0;
-        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; a0 = a_lo; } else { cd = dist_hi; a0 = a_hi; }
-        if (cd < (int64_t)best && a0 != cur) {
-          // remove_modification_at + swap + fixed mod of the new letter (:470-482)
-          if ((mask >> pos) & 1) { w -= s_var[cur]; mask &= ~(1ULL << pos); }
-          w += s_mprime[a0] - s_mprime[cur];
-          seq.at(pos) = (uint8_t)a0; del_letter(cur, pos); add_letter(a0, pos);
-          vpos = (vpos & ~(1ULL << pos)) | ((int)a0 == va ? 1ULL << pos : 0ULL);
-          if (md_in_window(w, lo, hi)) hit = true;
-          else if (any_var) {
-            if (va >= 0) {
-              if (vpos) hit = md_try_variable_simple(M, vpos, w - (int64_t)__popcll(mask) * M.var[M.var_simple_code], w, mask, lo, hi);
-            } else {
-              TSeqCode sc{seq, T.code_of_a};
-              if (md_try_variable(M, sc, L, w, mask, lo, hi, overflow)) hit = true;
-            }
-          }
-          const int64_t dd = w - P;
-          if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
-          d = (int32_t)dd; fm_stale = true;
-        } else {
-          *overflow = 3;   // the letter filter and the search disagree: cannot happen (reported as an internal error)
-        }
-        pos += 1;
+        const uint32_t dist_hi = k < MD_ALPHABET_SIZE ? (uint32_t)s_sorted[k] - (uint32_t)target : 0xFFFFFFFFu;
+        const uint32_t dist_lo = k > 0 ? (uint32_t)target - (uint32_t)s_sorted[k - 1] : 0xFFFFFFFFu;
+        const uint32_t a_hi = k < MD_ALPHABET_SIZE ? s_runmin[k] : 255u;
+        const uint32_t a_lo = k > 0 ? s_runmin[k - 1] : 255u;
+        uint32_t cd;
+        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; c = a_lo; } else { cd = dist_hi; c = a_hi; }
+        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+        if (!(cd < ad && c != old)) { flags |= 4u; c = old; }   // the letter filter and the search disagree: cannot happen
       } else {
-        pos = L;
+        c = rng.below(MD_ALPHABET_SIZE);
       }
+      // ---- put letter c at position p: remove_modification_at + swap + fixed modification of the new letter (:470-482)
+      {
+        const MaskT bit = (MaskT)1 << p;
+        if (VMODE != 0) { if (mask & bit) { d -= s_var[old]; mask &= ~bit; } }
+        d += s_mprime[c] - s_mprime[old];
+        seq.at(p) = (uint8_t)c; del_letter(old, p); add_letter(c, p);
+        if (VMODE == 1) vpos = (vpos & ~bit) | ((int)c == va ? bit : (MaskT)0);
+      }
+      bool hit = false;
+      if (sub) {
+        hit = (uint32_t)d - (uint32_t)dlo <= span;
+        if (VMODE == 1) {
+          if (!hit && vpos) hit = try_variable_simple_d<MaskT>(M.nvar, vdelta, vpos, d, mask, dlo, span);
+        } else if (VMODE == 2) {
+          if (!hit) {
+            TSeqCode sc{seq, T.code_of_a};
+            int64_t w = P + d; uint64_t m64 = (uint64_t)mask;
+            const int64_t lo = P + dlo;
+            if (md_try_variable(M, sc, L, w, m64, lo, lo + (int64_t)span, A.overflow)) hit = true;
+            const int64_t dd = w - P;
+            if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) flags |= 2u;
+            d = (int32_t)dd; mask = (MaskT)m64;
+          }
+        }
+        pos = p + 1;
+      } else {
+        pos = 0; tries++;
+      }
+      if ((uint32_t)d + 0x3FFFFFFFu > 0x7FFFFFFEu) flags |= 2u;
       if (hit) { pending = 1; busy = false; }
-      else if (pos >= L) {
-        // random kick (:489-505)
-        const uint32_t i = rng.below(L);
-        const uint32_t c = rng.below(MD_ALPHABET_SIZE);
-        const uint32_t old = seq.at(i);
-        if ((mask >> i) & 1) { w -= s_var[old]; mask &= ~(1ULL << i); }
-        w += s_mprime[c] - s_mprime[old];
-        seq.at(i) = (uint8_t)c; del_letter(old, i); add_letter(c, i);
-        vpos = (vpos & ~(1ULL << i)) | ((int)c == va ? 1ULL << i : 0ULL);
-        const int64_t dd = w - P;
-        if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) *overflow = 2;
-        d = (int32_t)dd; fm_stale = true;
-        pos = 0;
-        if (++tries == 100) { pending = 2; busy = false; }
-      }
+      else if (!sub && tries == 100) { pending = 2; busy = false; }
     }
   }
+  if (flags) atomicMax(A.overflow, (flags & 4u) ? 3 : 2);
 }
 
 // vary_targets (decoy_generator.rs:265-296), counter-based: attempt a shuffles target (a mod T) of the spectrum
@@ -478,6 +534,21 @@ __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restr
   if (threadIdx.x == 0) dec_count[s] = min(n_per, have + s_base);
 }
 
+template <class MaskT>
+void launch_random(md_ctx* ctx, int vmode, uint32_t grid, const RandomArgs& RA, const DecoyTables& T, const AttemptOut& O, const PeptideView& PV) {
+  if (vmode == 0) MD_LAUNCH(ctx, (k_decoy_random<0, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
+  else if (vmode == 1) MD_LAUNCH(ctx, (k_decoy_random<1, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
+  else MD_LAUNCH(ctx, (k_decoy_random<2, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
+}
+template <class MaskT>
+int random_occupancy(int vmode) {
+  int occ = 0;
+  if (vmode == 0) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<0, MaskT>, kThreads, 0));
+  else if (vmode == 1) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<1, MaskT>, kThreads, 0));
+  else MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<2, MaskT>, kThreads, 0));
+  return occ > 0 ? occ : 1;
+}
+
 DecoyTables make_tables(const ModTables& M) {
   DecoyTables T;
   memset(&T, 0, sizeof(T));
@@ -566,9 +637,19 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     if (mode == MD_DECOY_PERMUTE_TARGET) c = std::min<uint64_t>(c, (h_cand_off[s + 1] - h_cand_off[s]) * 1000ull);
     cap[s] = (uint32_t)c;
   }
+  // how try_variable_modifications runs inside the repair loop (see k_decoy_random)
+  int vmode = 0, occ_narrow = 1, occ_wide = 1;
+  const bool wide_only = getenv("MD_DECOY_WIDE_ONLY") != nullptr;   // debugging: skip the 32-bit pass
+  if (mode == MD_DECOY_REFERENCE_RANDOM) {
+    bool any_var_letter = false;
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++) any_var_letter |= T.has_var_a[a] != 0;
+    if (ctx->mods.nvar > 0 && any_var_letter)
+      vmode = (ctx->mods.var_simple_code >= 0 && md_alpha_of_code((uint32_t)ctx->mods.var_simple_code) >= 0) ? 1 : 2;
+    occ_narrow = random_occupancy<uint32_t>(vmode); occ_wide = random_occupancy<uint64_t>(vmode);
+  }
   DevBuf<uint32_t>& d_list = W.t_list; DevBuf<uint32_t>& d_off = W.t_off; DevBuf<uint32_t>& d_base = W.t_base; DevBuf<uint32_t>& d_queue = W.t_queue;
   DevBuf<int>& d_ovf = W.t_ovf;
-  d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(1); d_ovf.need(1);
+  d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(4); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   std::vector<uint32_t> list, off, base;
   for (int round = 0; round < 64; round++) {
@@ -595,9 +676,21 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaMemcpyAsync(d_base.p, base.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (mode == MD_DECOY_REFERENCE_RANDOM) {
-      MD_CUDA(cudaMemsetAsync(d_queue.p, 0, sizeof(uint32_t), ctx->stream));
-      uint32_t grid = std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * 8u);
-      MD_LAUNCH(ctx, k_decoy_random, grid, kThreads, 0, W.prec.p, d_list.p, d_off.p, d_base.p, n_list, total, d_queue.p, seed, ctx->mods, T, O, PV, d_ovf.p);
+      // narrow pass (32-bit position masks) over every attempt, then the wide pass over those that grew past 32 residues
+      MD_CUDA(cudaMemsetAsync(d_queue.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+      W.t_spill.need((size_t)total + 1);
+      RandomArgs RA;
+      RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total;
+      RA.seed = seed; RA.overflow = d_ovf.p;
+      if (!wide_only) {
+        RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = W.t_spill.p; RA.spill_n = d_queue.p + 1;
+        launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, O, PV);
+        RA.queue = d_queue.p + 2; RA.remap = W.t_spill.p; RA.remap_n = d_queue.p + 1; RA.spill = nullptr; RA.spill_n = nullptr;
+        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, O, PV);
+      } else {
+        RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = nullptr; RA.spill_n = nullptr;
+        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, O, PV);
+      }
     } else {
       MD_LAUNCH(ctx, k_decoy_permute, blocks(total, kThreads), kThreads, 0, W.prec.p, d_list.p, d_off.p, d_base.p, n_list, total, seed, T, W.cand_off.p,
                 W.cand_desc.p, W.cand_mask.p, W.cand_w.p, ctx->index.rows.p, O, PV);

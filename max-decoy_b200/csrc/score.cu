@@ -14,7 +14,7 @@
 //
 // Kernel design (B200): one persistent CTA of 768 threads per SM (spectra from a global queue).  T[b] is non-zero only
 // within 75 bins of a peak, i.e. on a few hundred 64-bin blocks of the 100k+ bins a 0.02-Da table spans, so the CTA keeps
-// a BLOCK-COMPRESSED table in shared memory: a 16-bit block map (bin >> 6 -> compressed block, 0 = the all-zero block)
+// a BLOCK-COMPRESSED table in shared memory: a 16-bit block map (bin >> 6 -> compressed block << 6 | 63, 0 = the all-zero block)
 // plus up to 719 dense 64-bin blocks (180 KiB of int32).  A centroided MS2 spectrum (~100-400 peaks above the 5 %
 // threshold) fits whole, so every candidate is walked ONCE; denser spectra fall back to several tiles of compressed
 // blocks.  Build: peaks mark their blocks in a bitmap (shared-memory atomicOr), a warp scan numbers the blocks, the
@@ -41,6 +41,7 @@ constexpr int kScoreThreads = MD_SCORE_THREADS;
 constexpr uint32_t kBlkShift = 6, kBlk = 1u << kBlkShift;      // table block = 64 bins
 constexpr uint32_t kTileBins = 46080;      // 180 KiB of int32 per CTA = 720 blocks, block 0 is the all-zero block
 constexpr uint32_t kTileBlocks = kTileBins / kBlk - 1;          // usable blocks per tile
+static_assert(kTileBlocks < (1u << (16 - kBlkShift)), "a block-map entry holds the compressed block in its upper 10 bits");
 constexpr uint32_t kMapCap = 6144;         // block-map entries staged in shared memory (393k bins; larger tables use an HBM map)
 constexpr uint32_t kCandChunk = 1536;      // candidates whose partial scores stay in shared memory across tiles
 constexpr uint32_t kPeakCap = 1024;        // binned peaks staged in shared memory (larger spectra read them from HBM)
@@ -225,10 +226,14 @@ __device__ __forceinline__ void acc_wide(int64_t& acc, int32_t v) {  // acc += v
 struct TableView { uint32_t tab_s, map_s, nblk; const uint16_t* gmap; };
 // one fragment: bin -> block (clamped onto the map's zero entry) -> compressed block -> table entry; branch-free
 template <bool MAPG>
-__device__ __forceinline__ void gather(int64_t& acc, uint32_t bin, const TableView& V) {
+__device__ __forceinline__ int32_t gather(uint32_t bin, const TableView& V) {
   const uint32_t blk = min(bin >> kBlkShift, V.nblk);
-  const uint32_t c = MAPG ? (uint32_t)V.gmap[blk] : lds_u16(V.map_s + 2u * blk);
-  acc_wide(acc, lds_s32(V.tab_s + (c << (kBlkShift + 2)) + ((bin & (kBlk - 1u)) << 2)));
+  const uint32_t e = MAPG ? (uint32_t)V.gmap[blk] : lds_u16(V.map_s + 2u * blk);
+  // e = (compressed block << 6) | 63, or 0: one AND yields the table index, and every fragment that misses reads the
+  // same word (entry 0 of the all-zero block), which the shared-memory pipe serves as one broadcast instead of a
+  // bank-conflicting random access
+  const uint32_t t = e & (bin | ~(kBlk - 1u));
+  return lds_s32(V.tab_s + (t << 2));
 }
 struct LaneTab { uint32_t q, r, vq, vr; };      // lane = residue code
 constexpr uint32_t kStop = 1u << 30;            // added to the running bin at the last residue: every later bin misses
@@ -257,7 +262,7 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   uint32_t QB = C.qp + 1u, R1 = C.rp;         // X = B_k + proton
   const uint32_t nsplit = cr.len > 0 ? cr.len - 1 : 0;   // residues 0..len-2 are followed by a split
   if (nsplit == 0) QB += kStop;
-  int64_t accb = 0, accy = 0;
+  int64_t acc = 0;
   for (uint32_t c = 0; c * 4 < nword; c++) {
     const uint4 v = __ldg(cr.row + c);
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
@@ -275,23 +280,22 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         }
         QB += q; R1 += r;
         if (R1 >= w) { R1 -= w; QB++; }
-        {  // fragment charge 1
-          gather<MAPG>(accb, QB, V);
-          gather<MAPG>(accy, Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);
-        }
+        // |T| <= 151 * 50 * 2^16 < 2^29: up to four entries add up in 32 bits, then one IMAD.WIDE into the 64-bit score
+        int32_t s4 = gather<MAPG>(QB, V) + gather<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);                // fragment charge 1
         if (NCH >= 2) {
-          gather<MAPG>(accb, ((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
-          gather<MAPG>(accy, ((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
+          s4 += gather<MAPG>(((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
+          s4 += gather<MAPG>(((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
         }
+        acc_wide(acc, s4);
         if (NCH >= 3) {
-          gather<MAPG>(accb, div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V);
-          gather<MAPG>(accy, div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V);
+          acc_wide(acc, gather<MAPG>(div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V) +
+                            gather<MAPG>(div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V));
         }
         if (pos + 1 == nsplit) QB += kStop;   // the next residue is the last one
       }
     }
   }
-  return accb + accy;
+  return acc;
 }
 
 __device__ __forceinline__ CandRef cand_ref(const ScoreArgs& A, uint32_t s, uint32_t v, uint32_t nt, uint64_t t0c, uint32_t n_per) {
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
                 if (c >= cb0 && c < cb0 + cbn) m = c - cb0 + 1u;
               }
             }
-            map[k] = (uint16_t)m;
+            map[k] = (uint16_t)(m ? (m << kBlkShift) | (kBlk - 1u) : 0u);
           }
           {
             uint4* z = reinterpret_cast<uint4*>(tab);
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
             if (b <= a) continue;
             const int32_t val = -(int32_t)S;
             for (uint32_t k = (uint32_t)a >> kBlkShift; k <= (uint32_t)(b - 1) >> kBlkShift; k++) {
-              const uint32_t m = map[k];
+              const uint32_t m = (uint32_t)map[k] >> kBlkShift;
               if (!m) continue;                                                  // block of another tile
 #pragma unroll
               for (int h = 0; h < (int)kBlk / 32; h++) {
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           // (3) the peak's own bin: + 151*y
           for (uint32_t p = tid; p < npk; p += kScoreThreads) {
             const uint32_t x = (uint32_t)pbin[p];
-            const uint32_t m = map[x >> kBlkShift];
+            const uint32_t m = (uint32_t)map[x >> kBlkShift] >> kBlkShift;
             if (m) tab[(m << kBlkShift) + (x & (kBlk - 1u))] += 151 * pyq[p];
           }
           __syncthreads();

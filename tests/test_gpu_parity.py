@@ -104,6 +104,26 @@ def test_decoys_random_bit_exact(gpu, cpu, mods, nvar):
     assert len(dg["attempt"]) > 0
 
 
+@pytest.mark.parametrize("mods,nvar", [((synth.CAM,), 0), ((synth.CAM, synth.OXM), 3)])
+def test_decoys_random_long_sequences_bit_exact(gpu, cpu, mods, nvar, monkeypatch):
+    """Heavy precursors: attempts grow past 32 residues, which the kernel hands from its 32-bit-mask pass to the 64-bit
+    one; sequences near the 60-residue cap are dropped.  Also: the 64-bit pass alone gives the same decoys."""
+    for e in (gpu, cpu):
+        _setup(e, 300, 2, mods, nvar)
+    pre = []
+    for i, m in enumerate((1_700_800_000, 2_900_400_000, 3_600_700_000, 4_300_100_000, 5_200_900_000, 6_400_300_000)):
+        tol = m // 100_000
+        pre.append((m, m - tol, m + tol, 2 + i % 3, 500 + i))
+    dc = cpu.generate_decoys(pre, 120, maxdecoy.DECOY_REFERENCE_RANDOM, seed=3)
+    dg = gpu.generate_decoys(pre, 120, maxdecoy.DECOY_REFERENCE_RANDOM, seed=3)
+    assert_tables_equal(dg, dc)
+    lens = np.diff(dg["seq_off"])
+    assert lens.max() > 32 and lens.min() <= 32
+    monkeypatch.setenv("MD_DECOY_WIDE_ONLY", "1")
+    dw = gpu.generate_decoys(pre, 120, maxdecoy.DECOY_REFERENCE_RANDOM, seed=3)
+    assert_tables_equal(dw, dc)
+
+
 def test_decoys_permute_bit_exact(gpu, cpu):
     for e in (gpu, cpu):
         _setup(e, 300, 2, (synth.CAM,), 0)

@@ -1,11 +1,16 @@
-# quick iteration: identify parity tests, one bench line, one ncu capture of k_score
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "identify or golden" 2>&1 | tail -5
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
-python - <<'PY'
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/t_parity.log 2>&1; echo "parity rc=$?" 
+tail -15 gpurun_out/t_parity.log
+MD_SCORE_TIMING=1 timeout 300 python bench.py --config c2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_c2.json 2> gpurun_out/b_c2.err; echo "c2 rc=$?"
+grep md_score_timing gpurun_out/b_c2.err | tail -1
+timeout 300 python bench.py --config c3 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_c3.json 2> gpurun_out/b_c3.err; echo "c3 rc=$?"
+MD_DECOY_WIDE_ONLY=1 timeout 300 python bench.py --config c2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_c2_wide.json 2> gpurun_out/b_c2_wide.err; echo "c2w rc=$?"
+python - <<'P'
 import json
-d=json.load(open('gpurun_out/bench.json'))
-print('value',d['value'],'e2e',d['e2e']['value'],'ms/step',d['ms_per_step'],'roof',d['roofline']['frac'],'kscore ms',d['roofline']['launch_ms'],d['stage_ms_per_step'])
-PY
-B="python bench.py --config c2 --spectra 2000 --steps 1 --warmup 3 --no-cpu-baseline"
-$B > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_score} -s ${NCU_SKIP:-1} -c 1 -o gpurun_out/prof_iter $B > gpurun_out/ncu_iter.log 2>&1
-tail -1 gpurun_out/ncu_iter.log
+for f in ['b_c2','b_c3','b_c2_wide']:
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
+        print(f, d['value'], d['ms_per_step'], d['stage_ms_per_step'], d['roofline']['frac'])
+    except Exception as e: print(f, 'ERR', e)
+P
