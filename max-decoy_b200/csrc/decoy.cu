@@ -23,6 +23,7 @@ constexpr int kThreads = 128;          // lanes per CTA of the attempt kernels
 constexpr int kMaxRoundAttempts = 4096;  // per spectrum per round (bounds the selection kernel's shared memory)
 
 // letter tables in alphabet-index space, built once per call on the host
+constexpr uint32_t kGapTab = 512, kNnTab = 1024;
 struct DecoyTables {
   int64_t mprime[32];      // residue mass + fixed delta, by alphabet index (0..20)
   int64_t sorted_m[32];    // mprime sorted ascending (ties by alphabet index), padded with INT64_MAX
@@ -36,6 +37,18 @@ struct DecoyTables {
   // (d > 0) / heavier (d < 0) distinct mass is < 2|d|.  Gaps sorted ascending + the letter set of every prefix.
   uint32_t gapb_sorted[32], gapa_sorted[32];   // padded with 0xFFFFFFFF
   uint32_t maskb_prefix[33], maska_prefix[33];
+  // bucket tables that replace the binary searches of the repair loop (a short residual scan finishes each lookup):
+  // gap_tab[sign][min(x >> gap_shift, kGapTab-1)] = number of sorted gaps below the bucket's first x
+  uint8_t gap_tab[2][kGapTab];
+  uint32_t gap_shift;
+  // nearest (mass + fixed delta) to a target t: distinct masses u[0..n), letter of each (lowest alphabet index of an
+  // equal-mass run), thresholds in doubled space thr2[j] between u[j] and u[j+1] (ties to the lower alphabet index):
+  // nearest = #{j : 2t > thr2[j]}; nn_tab[(clamp(t) - nn_lo) >> nn_shift] = that count at the bucket's first t
+  uint8_t nn_tab[kNnTab];
+  int32_t nn_thr2[32];        // padded with INT32_MAX
+  uint8_t nn_letter[32];
+  int32_t nn_lo, nn_hi;
+  uint32_t nn_shift;
 };
 
 struct TSeq {  // a lane's working sequence in shared memory (alphabet indices), transposed for conflict-free access
@@ -82,14 +95,18 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ att_
 // Philox4x32-10 output stream of one attempt, buffered in a per-lane shared-memory ring so that the block function runs
 // for the whole warp at once (every kRngPeriod steps of the kernel loop) instead of as a divergent tail behind whichever
 // lane happens to run dry.  The stream is exactly Philox4::next()'s: blocks c0 = 0, 1, 2, ... in order, four words each.
+#ifndef MD_RNG_RING
+#define MD_RNG_RING 8
+#endif
+constexpr uint32_t kRing = MD_RNG_RING;   // words per lane (power of two)
 struct RngRing {
-  uint32_t* buf;                 // 8 words, stride kThreads
+  uint32_t* buf;                 // kRing words, stride kThreads
   uint32_t k0, k1, c0, c1, c2;   // key, next block, attempt, spectrum
   uint32_t head, count;
   __device__ __forceinline__ void start(uint64_t seed, uint32_t spectrum_id, uint32_t attempt) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); c0 = 0; c1 = attempt; c2 = spectrum_id; head = 0; count = 0;
   }
-  __device__ __forceinline__ void produce() {   // one block -> 4 words into the ring (needs count <= 4)
+  __device__ __forceinline__ void produce() {   // one block -> 4 words into the ring (needs count <= kRing - 4)
     uint32_t a = c0, b = c1, c = c2, d = MD_TAG_RANDOM, x = k0, y = k1;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -100,18 +117,25 @@ struct RngRing {
       x += 0x9E3779B9u; y += 0xBB67AE85u;
     }
     const uint32_t t = head + count;
-    buf[((t + 0) & 7) * kThreads] = a; buf[((t + 1) & 7) * kThreads] = b; buf[((t + 2) & 7) * kThreads] = c; buf[((t + 3) & 7) * kThreads] = d;
+    buf[((t + 0) & (kRing - 1)) * kThreads] = a; buf[((t + 1) & (kRing - 1)) * kThreads] = b; buf[((t + 2) & (kRing - 1)) * kThreads] = c; buf[((t + 3) & (kRing - 1)) * kThreads] = d;
     c0++; count += 4;
   }
   __device__ __forceinline__ uint32_t next() {
     if (count == 0) produce();
-    const uint32_t v = buf[(head & 7) * kThreads];
+    const uint32_t v = buf[(head & (kRing - 1)) * kThreads];
     head++; count--;
     return v;
   }
   __device__ __forceinline__ uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
 };
-constexpr uint32_t kRngPeriod = 6;
+#ifndef MD_RNG_PERIOD
+#define MD_RNG_PERIOD 4
+#endif
+constexpr uint32_t kRngPeriod = MD_RNG_PERIOD;
+#ifndef MD_REFILL_MIN
+#define MD_REFILL_MIN 8
+#endif
+constexpr int kRefillMin = MD_REFILL_MIN;   // free lanes of a warp that trigger a refill
 
 // position masks are 32 bits wide in the narrow pass (sequences of <= 32 residues: nearly all of them) and 64 in the wide one
 template <class MaskT> struct MaskOps;
@@ -175,13 +199,17 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
   constexpr uint32_t kRows = kNarrow ? kBits : MD_MAX_PEPTIDE_LEN;
   constexpr uint32_t kAbove = 40;       // offset of the d < 0 tables
   __shared__ uint8_t sseq[kRows * kThreads];
-  __shared__ uint32_t s_rng[8 * kThreads];
+  __shared__ uint32_t s_rng[kRing * kThreads];
   __shared__ MaskT s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
   __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
   __shared__ int32_t s_mprime[32];      // by alphabet index
   __shared__ int32_t s_var[32];
   __shared__ uint8_t s_runmin[32];
   __shared__ uint32_t s_gap[kAbove + 32], s_gmask[kAbove + 33];   // d > 0 tables at [0..], d < 0 tables at [kAbove..]
+  __shared__ uint8_t s_gtab[2 * kGapTab], s_nntab[kNnTab], s_nnletter[32];
+  __shared__ int32_t s_thr2[32];
+  for (uint32_t i = threadIdx.x; i < 2 * kGapTab; i += kThreads) s_gtab[i] = T.gap_tab[i / kGapTab][i % kGapTab];
+  for (uint32_t i = threadIdx.x; i < kNnTab; i += kThreads) s_nntab[i] = T.nn_tab[i];
   if (threadIdx.x < 33) { s_gmask[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_gmask[kAbove + threadIdx.x] = T.maska_prefix[threadIdx.x]; }
   if (threadIdx.x < 32) {
     s_gap[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gap[kAbove + threadIdx.x] = T.gapa_sorted[threadIdx.x];
@@ -189,9 +217,12 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
     s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
     s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
     s_runmin[threadIdx.x] = T.run_min_a[threadIdx.x];
+    s_thr2[threadIdx.x] = T.nn_thr2[threadIdx.x]; s_nnletter[threadIdx.x] = T.nn_letter[threadIdx.x];
   }
   __syncthreads();
   TSeq seq{sseq + threadIdx.x};
+  const uint32_t gap_shift = T.gap_shift, nn_shift = T.nn_shift;
+  const int32_t nn_lo = T.nn_lo, nn_hi = T.nn_hi;
   const int va = VMODE == 1 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
   const int32_t vdelta = VMODE == 1 ? (int32_t)M.var[M.var_simple_code] : 0;
   const uint32_t total = A.remap ? *A.remap_n : A.total;
@@ -208,11 +239,13 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
   MaskT mask = 0, vpos = 0, lmask = 0;
   RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(A.seed, 0, 0);
 
-  for (uint32_t it = 0;; it++) {
+  uint32_t rng_timer = 1;
+  for (;;) {
     // ---- refill: when at least 8 lanes are free (or nobody works), they fetch and grow new attempts together
-    const uint32_t free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
-    const uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
-    if (free_m && (__popc(free_m) >= 8 || busy_m == 0)) {
+    uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
+    uint32_t free_m = 0;
+    if (__popc(busy_m) <= 32 - kRefillMin) free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
+    if (free_m && (__popc(free_m) >= kRefillMin || busy_m == 0)) {
       if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, (uint64_t)mask, P + d, T, PV); pending = 0; }
       if (!busy && !drained) {
         const uint32_t q = atomicAdd(A.queue, 1u);
@@ -251,13 +284,14 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
           }
         }
       }
+      busy_m = __ballot_sync(0xffffffffu, busy);
     }
-    if (__ballot_sync(0xffffffffu, busy) == 0) {
+    if (busy_m == 0) {
       if (__ballot_sync(0xffffffffu, !drained || pending) == 0) break;
       continue;
     }
     // ---- keep the random-number rings topped up, all lanes together
-    if (it % kRngPeriod == 0) { if (busy && rng.count <= 4) rng.produce(); }
+    if (--rng_timer == 0) { rng_timer = kRngPeriod; if (busy && rng.count <= kRing - 4) rng.produce(); }
     if (busy) {
       // ---- which LETTERS have a substitution that strictly reduces |d| follows from d alone (see DecoyTables) ...
       uint32_t fm;
@@ -265,12 +299,8 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
         const uint32_t ad = (uint32_t)(d < 0 ? -d : d), x = 2u * ad;
         const uint32_t gofs = d > 0 ? 0u : kAbove;
         const uint32_t* g = s_gap + gofs;
-        uint32_t k = 0;
-        if (g[k + 15] < x) k += 16;
-        if (g[k + 7] < x) k += 8;
-        if (g[k + 3] < x) k += 4;
-        if (g[k + 1] < x) k += 2;
-        if (g[k] < x) k += 1;
+        uint32_t k = s_gtab[(d > 0 ? 0u : kGapTab) + min(x >> gap_shift, kGapTab - 1u)];
+        for (uint32_t gk = g[k]; gk < x; gk = g[k]) k++;                 // number of gaps below x (padding: 0xFFFFFFFF)
         fm = s_gmask[gofs + k];                                          // d == 0: x == 0, k == 0, empty prefix
       }
       // ---- ... and the per-letter position masks give the first position of the pass that can improve: OR of the masks of
@@ -281,7 +311,15 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
         const uint32_t m0 = fm & present, n0 = present & ~fm;
         const bool inv = __popc(n0) < __popc(m0);
         MaskT acc = 0;
+#ifdef MD_PM_UNROLL2
+        for (uint32_t m = inv ? n0 : m0; m;) {
+          MaskT v = pm[(__ffs(m) - 1) * kThreads]; m &= m - 1;
+          if (m) { v |= pm[(__ffs(m) - 1) * kThreads]; m &= m - 1; }
+          acc |= v;
+        }
+#else
         for (uint32_t m = inv ? n0 : m0; m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
+#endif
         cand = inv ? ~acc & lmask : acc;
         cand = pos < L ? cand & (~(MaskT)0 << pos) : (MaskT)0;           // pos == L: the pass ended with a substitution
       }
@@ -294,22 +332,13 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
       if (sub) {
         // best single substitution = letter whose (mass+fixed) is closest to mprime[old] - d; strict improvement,
         // ties by alphabet order (the reference follows HashMap order there)
-        const int32_t target = s_mprime[old] - d;
-        uint32_t k = 0;
-        if (s_sorted[k + 15] < target) k += 16;
-        if (s_sorted[k + 7] < target) k += 8;
-        if (s_sorted[k + 3] < target) k += 4;
-        if (s_sorted[k + 1] < target) k += 2;
-        if (s_sorted[k] < target) k += 1;
-        // candidates: sorted[k-1] (< target) and sorted[k] (>= target)
-        const uint32_t dist_hi = k < MD_ALPHABET_SIZE ? (uint32_t)s_sorted[k] - (uint32_t)target : 0xFFFFFFFFu;
-        const uint32_t dist_lo = k > 0 ? (uint32_t)target - (uint32_t)s_sorted[k - 1] : 0xFFFFFFFFu;
-        const uint32_t a_hi = k < MD_ALPHABET_SIZE ? s_runmin[k] : 255u;
-        const uint32_t a_lo = k > 0 ? s_runmin[k - 1] : 255u;
-        uint32_t cd;
-        if (dist_lo < dist_hi || (dist_lo == dist_hi && a_lo < a_hi)) { cd = dist_lo; c = a_lo; } else { cd = dist_hi; c = a_hi; }
-        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-        if (!(cd < ad && c != old)) { flags |= 4u; c = old; }   // the letter filter and the search disagree: cannot happen
+        const int32_t target = min(max(s_mprime[old] - d, nn_lo), nn_hi);
+        const int32_t t2 = 2 * target;
+        uint32_t k = s_nntab[(uint32_t)(target - nn_lo) >> nn_shift];
+        for (int32_t th = s_thr2[k]; t2 > th; th = s_thr2[k]) k++;       // nearest distinct mass (padding: INT32_MAX)
+        c = s_nnletter[k];
+        const int32_t nd = d + s_mprime[c] - s_mprime[old];
+        if (!((uint32_t)(nd < 0 ? -nd : nd) < (uint32_t)(d < 0 ? -d : d) && c != old)) { flags |= 4u; c = old; }   // filter and search disagree: cannot happen
       } else {
         c = rng.below(MD_ALPHABET_SIZE);
       }
@@ -591,6 +620,37 @@ DecoyTables make_tables(const ModTables& M) {
       T.gapa_sorted[k] = ga[k].g; T.maska_prefix[k + 1] = T.maska_prefix[k] | (ga[k].g == 0xFFFFFFFFu ? 0u : 1u << ga[k].a);
     }
     for (int k = MD_ALPHABET_SIZE + 1; k < 33; k++) { T.maskb_prefix[k] = T.maskb_prefix[MD_ALPHABET_SIZE]; T.maska_prefix[k] = T.maska_prefix[MD_ALPHABET_SIZE]; }
+    // bucket table over x = 2|d|: the last bucket takes every larger x (the residual scan finishes the count)
+    uint32_t gmax = 1;
+    for (int k = 0; k < MD_ALPHABET_SIZE; k++) { if (gb[k].g != 0xFFFFFFFFu) gmax = std::max(gmax, gb[k].g); if (ga[k].g != 0xFFFFFFFFu) gmax = std::max(gmax, ga[k].g); }
+    T.gap_shift = 0;
+    while (((uint64_t)gmax >> T.gap_shift) >= kGapTab - 1) T.gap_shift++;
+    for (int sgn = 0; sgn < 2; sgn++) {
+      const uint32_t* g = sgn == 0 ? T.gapb_sorted : T.gapa_sorted;
+      for (uint32_t b = 0; b < kGapTab; b++) {
+        const uint64_t x0 = (uint64_t)b << T.gap_shift;   // first x of the bucket: gaps < x0 are below every x of the bucket
+        uint32_t c = 0;
+        while (c < MD_ALPHABET_SIZE && (uint64_t)g[c] < x0) c++;
+        T.gap_tab[sgn][b] = (uint8_t)c;
+      }
+    }
+  }
+  // nearest-mass tables
+  {
+    int n = 0; int64_t u[32]; uint8_t rep[32];
+    for (int k = 0; k < MD_ALPHABET_SIZE; k++)
+      if (n == 0 || v[k].m != u[n - 1]) { u[n] = v[k].m; rep[n] = T.run_min_a[k]; n++; }
+    for (int j = 0; j < 32; j++) { T.nn_thr2[j] = INT32_MAX; T.nn_letter[j] = j < n ? rep[j] : rep[n - 1]; }
+    for (int j = 0; j + 1 < n; j++) T.nn_thr2[j] = (int32_t)(u[j] + u[j + 1] - (rep[j] < rep[j + 1] ? 0 : 1));
+    T.nn_lo = (int32_t)(u[0] - 1); T.nn_hi = (int32_t)(u[n - 1] + 1);
+    T.nn_shift = 0;
+    while ((((uint64_t)(T.nn_hi - T.nn_lo)) >> T.nn_shift) >= kNnTab) T.nn_shift++;
+    for (uint32_t b = 0; b < kNnTab; b++) {
+      const int64_t t0 = (int64_t)T.nn_lo + ((int64_t)b << T.nn_shift);   // first t of the bucket
+      uint32_t c = 0;
+      while (c + 1 < (uint32_t)n && 2 * t0 > (int64_t)T.nn_thr2[c]) c++;
+      T.nn_tab[b] = (uint8_t)c;
+    }
   }
   return T;
 }
@@ -654,6 +714,12 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   std::vector<uint32_t> list, off, base;
   for (int round = 0; round < 64; round++) {
     list.clear(); off.assign(1, 0); base.clear();
+    // How many attempts each unfinished spectrum gets this round.  A spectrum's decoys are its first n distinct successes
+    // in attempt order, so asking for too many only wastes work; asking for too few costs another round, and a round
+    // never takes less than one 100-try attempt (~0.3 ms) however small it is.  Round 0 asks for n/0.8; later rounds use
+    // the spectrum's own yield with 30 % head room, and rounds too small to fill the GPU ask for up to 4x that.
+    std::vector<uint32_t> wants;
+    uint64_t sum = 0;
     for (uint32_t si = 0; si < n; si++) {
       const uint32_t s = by_mass[si];
       if (count[s] >= n_per || used[s] >= cap[s]) continue;
@@ -661,12 +727,20 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       if (used[s] == 0) want = n_per + n_per / 4 + 32;
       else {
         double yield = std::max(0.02, (double)count[s] / (double)used[s]);
-        want = (uint32_t)((double)(n_per - count[s]) / yield * 1.15) + 8;
+        want = (uint32_t)((double)(n_per - count[s]) / yield * 1.3) + 48;
       }
       want = std::min<uint32_t>({want, (uint32_t)kMaxRoundAttempts, cap[s] - used[s]});
-      if (off.back() + (uint64_t)want > 0x7FFFFFFFull) break;  // the rest waits for the next round
-      list.push_back(s); base.push_back(used[s]); off.push_back(off.back() + want);
+      list.push_back(s); wants.push_back(want); sum += want;
     }
+    const double boost = round == 0 || sum == 0 ? 1.0 : std::min(4.0, std::max(1.0, 300000.0 / (double)sum));
+    size_t kept = 0;
+    for (size_t i = 0; i < list.size(); i++) {
+      const uint32_t s = list[i];
+      const uint32_t want = std::min<uint32_t>({(uint32_t)((double)wants[i] * boost), (uint32_t)kMaxRoundAttempts, cap[s] - used[s]});
+      if (off.back() + (uint64_t)want > 0x7FFFFFFFull) break;  // the rest waits for the next round
+      base.push_back(used[s]); off.push_back(off.back() + want); kept++;
+    }
+    list.resize(kept);
     if (list.empty()) break;
     const uint32_t n_list = (uint32_t)list.size(), total = off.back();
     W.att_rows.need((size_t)total * MD_DECOY_ROW + 64); W.att_len.need(total + 1); W.att_mask.need(total + 1); W.att_w.need(total + 1); W.att_hash.need(total + 1);
@@ -715,7 +789,8 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->mark("  select");
     for (uint32_t i = 0; i < n_list; i++) used[list[i]] += off[i + 1] - off[i];
-    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total; }
+    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total;
+      if (ctx->trace) fprintf(stderr, "[md_trace]   decoy round %d: spectra=%u attempts=%u kernel=%.3f ms\n", round, n_list, total, ms); }
   }
   const int ovf = d2h_scalar(ctx, d_ovf.p);
   MD_REQUIRE(ovf != 3, MD_ERR_DEVICE, "decoy generation: internal error (substitution filter disagrees with the mass search)");

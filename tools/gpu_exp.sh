@@ -1,1 +1,3 @@
-for e in ${EXPS:-0 1 2 4 7}; do echo "exp=$e"; MD_SCORE_EXP=$e MD_SCORE_TIMING=1 timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --decoys ${DECOYS:-1000} 2>&1 | grep md_score_timing | tail -1; done
+MD_TRACE=1 timeout 300 python bench.py --config c2 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err
+grep "decoy round" gpurun_out/bench_trace.err | tail -12
+CFGS=c2 bash tools/gpu_variants.sh
