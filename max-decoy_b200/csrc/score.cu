@@ -18,8 +18,10 @@
 // plus up to 719 dense 64-bin blocks (180 KiB of int32).  A centroided MS2 spectrum (~100-400 peaks above the 5 %
 // threshold) fits whole, so every candidate is walked ONCE; denser spectra fall back to several tiles of compressed
 // blocks.  Build: peaks mark their blocks in a bitmap (shared-memory atomicOr), a warp scan numbers the blocks, the
-// occupied blocks are zeroed with vectorised stores, one warp per window edge paints the piecewise-constant -sum(y)
-// segments (values from the prefix sums of y: no atomics), one thread per peak adds the 151*y spike.  Scoring: the
+// occupied blocks are zeroed with vectorised stores, every peak drops its window as a difference pair (+y at bin-75, -y
+// at bin+76) and its spike as (-151y, +151y) with shared-memory atomics, and one block-wide inclusive scan straight over
+// the compressed blocks turns the differences into -T (the running sum is 0 at the end of every run of occupied blocks,
+// so the scan needs no notion of where the runs are).  Scoring: the
 // candidates are counting-sorted by length into 32-candidate units that warps pull from a shared counter; a thread
 // scores one candidate: 128-bit row loads, the per-letter (q, r) mass table in registers read by warp shuffle, a
 // division-free running (Q, R) prefix, two shared-memory loads per fragment (block map, then table), a stop offset at
@@ -375,6 +377,8 @@ struct SpecShared {
   uint32_t hist[64];        // candidates per length (counting sort of the chunk)
   uint32_t unit;            // next unit of the current tile pass
   uint32_t nact;            // occupied table blocks of the spectrum
+  uint32_t x0; int32_t cin; // first bin of the current tile, running sum in front of it
+  uint32_t wsum[kScoreThreads / 32];
   uint32_t bits[kMapCap / 32], bpre[kMapCap / 32];   // occupied-block bitmap and its exclusive popcount prefix
 };
 
@@ -434,11 +438,11 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     if (scored) for (uint32_t i = tid; i < nwords; i += kScoreThreads) bits[i] = 0;
     for (uint32_t r = tid; r < K; r += kScoreThreads) sh.top[r] = 0ull;
     __syncthreads();
-    // ---- occupied blocks: every bin within 75 of a peak
+    // ---- occupied blocks: every bin within 75 of a peak, and the bin behind (where the window's difference entry goes)
     if (scored) {
       for (uint32_t p = tid; p < npk; p += kScoreThreads) {
         const int32_t b = pbin[p];
-        const uint32_t b0 = (uint32_t)max(b - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(b + kXcorrOffset), NB - 1) >> kBlkShift;
+        const uint32_t b0 = (uint32_t)max(b - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(b + kXcorrOffset + 1), NB - 1) >> kBlkShift;
         for (uint32_t k = b0; k <= b1; k++) atomicOr(&bits[k >> 5], 1u << (k & 31));
       }
     }
@@ -466,12 +470,19 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       // counting sort of the chunk by peptide length, longest first
       if (tid < 64) sh.hist[tid] = 0;
       __syncthreads();
+      static_assert(kCandChunk <= 2 * kScoreThreads, "a thread sorts at most two candidates of a chunk");
+      uint32_t len2[2] = {0, 0};
       if (scored) {
-        for (uint32_t v = tid; v < cn; v += kScoreThreads) {
-          const uint32_t u = c0 + v;
-          const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
-          atomicAdd(&sh.hist[63u - min(len, 63u)], 1u);
-          my_pairs++; my_bytes += 14 + len;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t v = tid + h * kScoreThreads;
+          if (v < cn) {
+            const uint32_t u = c0 + v;
+            const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
+            len2[h] = len;
+            atomicAdd(&sh.hist[63u - min(len, 63u)], 1u);
+            my_pairs++; my_bytes += 14 + len;
+          }
         }
       }
       __syncthreads();
@@ -483,10 +494,10 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       }
       __syncthreads();
       if (scored) {
-        for (uint32_t v = tid; v < cn; v += kScoreThreads) {
-          const uint32_t u = c0 + v;
-          const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
-          s_order[atomicAdd(&sh.hist[63u - min(len, 63u)], 1u)] = (uint16_t)v;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t v = tid + h * kScoreThreads;
+          if (v < cn) s_order[atomicAdd(&sh.hist[63u - min(len2[h], 63u)], 1u)] = (uint16_t)v;
         }
       }
       // (visible to the scoring warps after the table-build barriers)
@@ -505,60 +516,65 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
               }
             }
             map[k] = (uint16_t)(m ? (m << kBlkShift) | (kBlk - 1u) : 0u);
+            if (m == 1u) sh.x0 = k << kBlkShift;                              // first bin of the tile
           }
           {
             uint4* z = reinterpret_cast<uint4*>(tab);
             const uint32_t n4 = (cbn + 1u) * (kBlk / 4);
             for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) sh.unit = 0;
+            if (tid == 0) { sh.unit = 0; sh.cin = 0; }
           }
           __syncthreads();
           MD_TICK(2);
-          // (2) paint -S[b], S[b] = sum of y over bins [b-75, b+75]: piecewise constant between window edges (no atomics:
-          //     the value of every segment comes from the prefix sums of y).
-          //     Edge 2p   = entry of peak p at x = bin-75: S = pre[p+1] - pre[lo], lo = first peak with bin >= x-75
-          //     Edge 2p+1 = exit  of peak p at x = bin+76: S = pre[hi] - pre[p+1], hi = first peak with bin > x+75
-          //     and the segment runs to the next edge of either kind.  One warp per edge; a segment spans <= 4 blocks.
-          for (uint32_t e = warp; e < 2 * npk; e += NW) {
-            const uint32_t p = e >> 1;
-            const int32_t bp = pbin[p];
-            int32_t xa, xb; uint32_t S;
-            if ((e & 1) == 0) {
-              uint32_t lo = p;
-              while (lo > 0 && pbin[lo - 1] >= bp - 2 * kXcorrOffset) lo--;
-              S = ppre[p + 1] - ppre[lo];
-              xa = bp - kXcorrOffset;
-              xb = pbin[lo] + kXcorrOffset + 1;                                  // next exit
-              if (p + 1 < npk) xb = min(xb, pbin[p + 1] - kXcorrOffset);         // next entry
-            } else {
-              uint32_t hi = p + 1;
-              while (hi < npk && pbin[hi] <= bp + 2 * kXcorrOffset + 1) hi++;
-              S = ppre[hi] - ppre[p + 1];
-              xa = bp + kXcorrOffset + 1;
-              xb = hi < npk ? pbin[hi] - kXcorrOffset : INT32_MAX;               // next entry
-              if (p + 1 < npk) xb = min(xb, pbin[p + 1] + kXcorrOffset + 1);     // next exit
+          // (2) T as a difference array: every peak adds +y at the first bin of its window (bin-75), -y behind its last
+          //     (bin+76), and its own 151*y spike as -151*y at bin / +151*y at bin+1, so that the running sum over the
+          //     bins is R[b] = S[b] - 151*y[b] = -T[b].  All four bins lie in occupied blocks (the marking covers
+          //     [bin-75, bin+76]), R is 0 at the end of every run of occupied blocks, and the compressed blocks are in
+          //     bin order: one inclusive scan straight over the compressed table yields -T.  Integer adds commute, so
+          //     the shared-memory atomics keep the table exact.  A later tile starts from the sum of the differences
+          //     at the bins in front of it (sh.cin).
+          {
+            const uint32_t X0 = sh.x0;
+            int32_t cin = 0;
+            for (uint32_t p = tid; p < npk; p += kScoreThreads) {
+              const int32_t bp = pbin[p], y = pyq[p];
+              const uint32_t xa = (uint32_t)max(bp - kXcorrOffset, 0), xe = (uint32_t)(bp + kXcorrOffset + 1), xs = (uint32_t)bp;
+              const int32_t spike = 151 * y;
+              uint32_t m;
+              m = (uint32_t)map[xa >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xa & (kBlk - 1u))], y);
+              // (xe == NB for the last peak: the bins of the last block behind the table's end must read 0 too)
+              if (xe < (nblk << kBlkShift)) { m = (uint32_t)map[xe >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xe & (kBlk - 1u))], -y); }
+              m = (uint32_t)map[xs >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xs & (kBlk - 1u))], -spike);
+              m = (uint32_t)map[(xs + 1u) >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + ((xs + 1u) & (kBlk - 1u))], spike);
+              if (cb0 > 0) cin += (xa < X0 ? y : 0) - (xe < X0 ? y : 0) - (xs < X0 ? spike : 0) + (xs + 1u < X0 ? spike : 0);
             }
-            if (S == 0) continue;
-            const int32_t a = max(xa, 0), b = min(xb, (int32_t)NB);
-            if (b <= a) continue;
-            const int32_t val = -(int32_t)S;
-            for (uint32_t k = (uint32_t)a >> kBlkShift; k <= (uint32_t)(b - 1) >> kBlkShift; k++) {
-              const uint32_t m = (uint32_t)map[k] >> kBlkShift;
-              if (!m) continue;                                                  // block of another tile
-#pragma unroll
-              for (int h = 0; h < (int)kBlk / 32; h++) {
-                const int32_t x = (int32_t)(k << kBlkShift) + h * 32 + (int32_t)lane;
-                if (x >= a && x < b) tab[(m << kBlkShift) + (uint32_t)(h * 32) + lane] = val;
-              }
-            }
+            if (cb0 > 0 && cin != 0) atomicAdd(&sh.cin, cin);
           }
           __syncthreads();
           MD_TICK(3);
-          // (3) the peak's own bin: + 151*y
-          for (uint32_t p = tid; p < npk; p += kScoreThreads) {
-            const uint32_t x = (uint32_t)pbin[p];
-            const uint32_t m = (uint32_t)map[x >> kBlkShift] >> kBlkShift;
-            if (m) tab[(m << kBlkShift) + (x & (kBlk - 1u))] += 151 * pyq[p];
+          // (3) the scan, in place, negated: every warp owns a contiguous range of 16-byte words; pass A adds up the
+          //     ranges, pass B rescans each range from the sum of the ranges in front of it
+          {
+            uint4* t4 = reinterpret_cast<uint4*>(tab) + kBlk / 4;            // entry 0 = first occupied block
+            const uint32_t N4 = cbn * (kBlk / 4);
+            const uint32_t per = (((N4 + NW - 1) / NW) + 31u) & ~31u;
+            const uint32_t s0 = min(warp * per, N4), s1 = min(s0 + per, N4);
+            uint32_t part = 0;
+            for (uint32_t i = s0 + lane; i < s1; i += 32) { const uint4 v = t4[i]; part += v.x + v.y + v.z + v.w; }
+            part = __reduce_add_sync(0xffffffffu, part);
+            if (lane == 0) sh.wsum[warp] = part;
+            __syncthreads();
+            uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? sh.wsum[lane] : 0u) + (uint32_t)sh.cin;
+            for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
+              const uint32_t i = i0 + lane;
+              uint4 v = i < s1 ? t4[i] : make_uint4(0, 0, 0, 0);
+              v.y += v.x; v.z += v.y; v.w += v.z;
+              uint32_t incl = v.w;
+              for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+              const uint32_t ex = run + incl - v.w;
+              if (i < s1) t4[i] = make_uint4(0u - (ex + v.x), 0u - (ex + v.y), 0u - (ex + v.z), 0u - (ex + v.w));
+              run += __shfl_sync(0xffffffffu, incl, 31);
+            }
           }
           __syncthreads();
           // (4) score the chunk against the tile
@@ -749,7 +765,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     unsigned long long t[8];
     MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
     double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
-    static const char* names[6] = {"stage+blocks", "sort", "map+zero", "paint", "spike+score", "topk"};
+    static const char* names[6] = {"stage+blocks", "sort", "map+zero", "differences", "scan+score", "topk"};
     fprintf(stderr, "[md_score_timing] grid=%u", grid);
     for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.1f%%", names[k], 100.0 * (double)t[k] / tot);
     fprintf(stderr, " cycles/CTA=%.0f\n", tot / grid);
