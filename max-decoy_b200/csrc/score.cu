@@ -46,7 +46,7 @@ constexpr uint32_t kTileBlocks = kTileBins / kBlk - 1;          // usable blocks
 static_assert(kTileBlocks < (1u << (16 - kBlkShift)), "a block-map entry holds the compressed block in its upper 10 bits");
 constexpr uint32_t kMapCap = 6144;         // block-map entries staged in shared memory (393k bins; larger tables use an HBM map)
 constexpr uint32_t kCandChunk = 1536;      // candidates whose partial scores stay in shared memory across tiles
-constexpr uint32_t kPeakCap = 1024;        // binned peaks staged in shared memory (larger spectra read them from HBM)
+constexpr uint32_t kPeakCap = 512;         // binned peaks staged in shared memory, double-buffered (larger spectra read them from HBM)
 constexpr uint32_t kMaxBins = 1u << 26;    // table bins per spectrum (bins must stay far below kStop)
 constexpr uint32_t kMaxTopK = 128;
 constexpr uint32_t kFastTopK = 8;
@@ -368,52 +368,152 @@ __device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst
   }
 }
 
+// What the prefetch warp leaves for the next spectrum of the CTA (double-buffered with the staged peaks, the block bitmap
+// and the sorted candidate order).
+struct SpecMeta {
+  md_precursor pr;
+  uint64_t t0c, pk0;
+  uint32_t s, nt, nd, npk, nact;
+  int32_t hbin;
+  uint32_t pre_blocks;               // peaks, bitmap and block numbering are already in shared memory
+};
+
+struct FinRecord { md_precursor pr; uint64_t t0c; uint32_t s, nt, nd, pending, ranked; };
+
 struct SpecShared {
-  uint32_t work[2];
+  SpecMeta meta[2];
   unsigned long long wkey[2][kScoreThreads / 32];
   unsigned long long top[kMaxTopK];
-  unsigned long long wtop[kScoreThreads / 32][kFastTopK];  // per-warp best keys, descending
+  unsigned long long wtop[2][kScoreThreads / 32][kFastTopK];  // per-warp best keys of a spectrum, descending
+  FinRecord fin[2];         // what the finish warp needs to write that spectrum's PSM rows
   long long tacc[8];
-  uint32_t hist[64];        // candidates per length (counting sort of the chunk)
+  uint32_t hist[64];        // candidates per length (counting sort of a chunk by the whole CTA)
   uint32_t unit;            // next unit of the current tile pass
   uint32_t nact;            // occupied table blocks of the spectrum
   uint32_t x0; int32_t cin; // first bin of the current tile, running sum in front of it
   uint32_t wsum[kScoreThreads / 32];
-  uint32_t bits[kMapCap / 32], bpre[kMapCap / 32];   // occupied-block bitmap and its exclusive popcount prefix
+  uint32_t bits[2][kMapCap / 32], bpre[2][kMapCap / 32];   // occupied-block bitmap and its exclusive popcount prefix
 };
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cand_len(const ScoreArgs& A, uint32_t s, uint32_t u, uint32_t nt, uint64_t t0c, uint32_t n_per) {
+  return u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * n_per + (u - nt)];
+}
+
+// Run by ONE warp while the others score: take the CTA's next spectrum from the queue and leave in shared memory what
+// its iteration would otherwise wait for -- the precursor and candidate ranges, the binned peaks (cp.async) and the
+// occupied-block bitmap with its numbering.
+__device__ __noinline__ void prefetch_spectrum(const ScoreArgs& A, SpecShared& sh, uint32_t slot, int32_t* s_bin, int32_t* s_yq) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t sn = 0;
+  if (lane == 0) sn = atomicAdd(A.work, 1u);
+  sn = __shfl_sync(0xffffffffu, sn, 0);
+  SpecMeta m;
+  m.s = sn; m.pre_blocks = 0; m.nact = 0; m.nt = 0; m.nd = 0; m.npk = 0; m.hbin = -1; m.t0c = 0; m.pk0 = 0;
+  m.pr.mass = 0; m.pr.lo = 0; m.pr.hi = 0; m.pr.charge = 0; m.pr.spectrum_id = 0;
+  if (sn < A.n_spec) {
+    m.pr = A.prec[sn];
+    m.t0c = A.cand_off[sn];
+    m.nt = (uint32_t)(A.cand_off[sn + 1] - m.t0c);
+    m.nd = A.dec_count ? A.dec_count[sn] : 0;
+    m.hbin = A.pk_hbin[sn]; m.npk = A.pk_count[sn]; m.pk0 = A.peak_off[sn];
+    const uint32_t NB = m.hbin >= 0 ? (uint32_t)m.hbin + kXcorrOffset + 1 : 0;
+    const uint32_t nblk = (NB + kBlk - 1) >> kBlkShift, nwords = (nblk + 31) >> 5;
+    const uint32_t ncand = m.nt + m.nd;
+    const bool scored = m.hbin >= 0 && NB <= kMaxBins && ncand <= 0xFFFFFFu;
+    if (scored && m.npk <= kPeakCap && nblk <= kMapCap) {
+      const int32_t* gb = A.pk_bin + m.pk0; const int32_t* gy = A.pk_yq + m.pk0;
+      int32_t* sb = s_bin + slot * kPeakCap; int32_t* sy = s_yq + slot * kPeakCap;
+      for (uint32_t i = lane; i < m.npk; i += 32) { cp_async4(sb + i, gb + i); cp_async4(sy + i, gy + i); }
+      uint32_t* bits = sh.bits[slot]; uint32_t* bpre = sh.bpre[slot];
+      for (uint32_t i = lane; i < nwords; i += 32) bits[i] = 0;
+      cp_async_wait_all();
+      __syncwarp();
+      for (uint32_t p = lane; p < m.npk; p += 32) {     // every bin within 75 of a peak, and the bin behind
+        const int32_t b = sb[p];
+        const uint32_t b0 = (uint32_t)max(b - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(b + kXcorrOffset + 1), NB - 1) >> kBlkShift;
+        for (uint32_t k = b0; k <= b1; k++) atomicOr(&bits[k >> 5], 1u << (k & 31));
+      }
+      __syncwarp();
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < nwords; base += 32) {   // exclusive popcount prefix over the bitmap words
+        const uint32_t i = base + lane;
+        const uint32_t c = i < nwords ? (uint32_t)__popc(bits[i]) : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (i < nwords) bpre[i] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      m.nact = run; m.pre_blocks = 1;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) sh.meta[slot] = m;
+}
+
+// Run by ONE warp while the others score the next spectrum: merge the per-warp top-k lists of spectrum fin[slot] (lane r
+// ends up with its r-th best key) and write its PSM rows.
+__device__ __noinline__ void finish_spectrum(const ScoreArgs& A, const ScoreConst& C, SpecShared& sh, uint32_t slot) {
+  const FinRecord f = sh.fin[slot];
+  if (!f.pending) return;
+  const uint32_t lane = threadIdx.x & 31, K = C.top_k;
+  constexpr uint32_t NW = kScoreThreads / 32;
+  unsigned long long mine = 0ull;
+  if (f.ranked) {
+    uint32_t idx = 0;
+    for (uint32_t r = 0; r < K; r++) {
+      const unsigned long long head = (lane < NW && idx < K) ? sh.wtop[slot][lane][idx] : 0ull;
+      const unsigned long long wm = warp_max_u64(head);
+      if (wm != 0ull && head == wm) idx++;
+      if (lane == r) mine = wm;
+    }
+  }
+  if (lane < K) write_psm_row(A, C, f.pr, f.s, lane, mine, f.nt, f.nd, f.t0c);
+}
 
 template <bool HASVAR>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C) {
   extern __shared__ __align__(16) int32_t tab[];                     // kTileBins
   int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins);    // kCandChunk
-  int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // kPeakCap
-  int32_t* s_yq = s_bin + kPeakCap;                                  // kPeakCap
-  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_yq + kPeakCap);    // kPeakCap + 4
-  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_pre + kPeakCap + 4);  // kCandChunk: chunk slots in length-descending order
+  int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // 2 x kPeakCap
+  int32_t* s_yq = s_bin + 2 * kPeakCap;                              // 2 x kPeakCap
+  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_yq + 2 * kPeakCap);   // kCandChunk: chunk slots in length-descending order
   uint16_t* s_map = s_order + kCandChunk;                            // kMapCap + 2
   __shared__ SpecShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t NW = kScoreThreads / 32;
+  // two warps start every scoring phase with a side job: one fetches the CTA's next spectrum, the other merges the
+  // per-warp top-k lists of the previous spectrum and writes its PSM rows -- both off the critical path
+  constexpr uint32_t kPrefetchWarp = NW - 1, kFinishWarp = NW - 2;
   const LaneTab L{C.tq[lane], C.tr[lane], C.vq[lane], C.vr[lane]};   // per-letter (q, r) tables in registers: lane = residue code
   uint32_t my_pairs = 0, my_bytes = 0;   // per thread, summed at the end
   long long t_last = A.timing ? clock64() : 0;
   if (tid < 8) sh.tacc[tid] = 0;
 #define MD_TICK(k) do { if (A.timing && tid == 0) { const long long now_ = clock64(); sh.tacc[k] += now_ - t_last; t_last = now_; } } while (0)
 
-  if (tid == 0) sh.work[0] = atomicAdd(A.work, 1u);
-  __syncthreads();
+  if (warp == kPrefetchWarp) prefetch_spectrum(A, sh, 0, s_bin, s_yq);
+  if (tid < 2) sh.fin[tid].pending = 0;
   for (uint32_t it = 0;; it++) {
-    const uint32_t s = sh.work[it & 1];
-    if (s >= A.n_spec) break;
-    if (tid == 0) sh.work[(it + 1) & 1] = atomicAdd(A.work, 1u);     // next spectrum, read after this one's barriers
-    const md_precursor pr = A.prec[s];
-    const uint64_t t0c = A.cand_off[s];
-    const uint32_t nt = (uint32_t)(A.cand_off[s + 1] - t0c);
-    const uint32_t nd = A.dec_count ? A.dec_count[s] : 0;
+    const uint32_t slot = it & 1;
+    __syncthreads();                  // this spectrum's prefetch is visible; the other slot's buffers are free again
+    const SpecMeta mt = sh.meta[slot];
+    const uint32_t s = mt.s;
+    if (s >= A.n_spec) {
+      if (warp == kFinishWarp && it > 0) finish_spectrum(A, C, sh, slot ^ 1u);     // the CTA's last spectrum
+      break;
+    }
+    bool side_done = false;           // (helper warps) this iteration's side job is done
+    const md_precursor pr = mt.pr;
+    const uint64_t t0c = mt.t0c;
+    const uint32_t nt = mt.nt, nd = mt.nd;
     const uint32_t ncand = nt + nd;
-    const int32_t hbin = A.pk_hbin[s];
-    const uint32_t npk = A.pk_count[s];
-    const uint64_t pk0 = A.peak_off[s];
+    const int32_t hbin = mt.hbin;
+    const uint32_t npk = mt.npk;
+    const uint64_t pk0 = mt.pk0;
     const uint32_t K = C.top_k;
     uint32_t nch = pr.charge > 1 ? pr.charge - 1 : 1;
     if (nch > C.max_frag_charge) nch = C.max_frag_charge;
@@ -424,43 +524,38 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     const bool mapg = nblk > kMapCap;
     if (NB > kMaxBins || ncand > 0xFFFFFFu || (mapg && (!A.gmap || nblk + 1 > A.gmap_stride))) { if (tid == 0) *A.error = 1; scored = false; }
     uint16_t* map = mapg ? A.gmap + (size_t)blockIdx.x * A.gmap_stride : s_map;
-    uint32_t* bits = mapg ? A.gbits + (size_t)blockIdx.x * 2 * (A.gmap_stride / 32 + 1) : sh.bits;
-    uint32_t* bpre = mapg ? bits + (A.gmap_stride / 32 + 1) : sh.bpre;
+    uint32_t* bits = mapg ? A.gbits + (size_t)blockIdx.x * 2 * (A.gmap_stride / 32 + 1) : sh.bits[slot];
+    uint32_t* bpre = mapg ? bits + (A.gmap_stride / 32 + 1) : sh.bpre[slot];
     const uint32_t nwords = (nblk + 31) >> 5;
-
-    // ---- stage the binned spectrum, clear the block bitmap
-    const int32_t* pbin = A.pk_bin + pk0; const int32_t* pyq = A.pk_yq + pk0; const uint32_t* ppre = A.pk_pre + pk0 + s;
-    if (scored && npk <= kPeakCap) {
-      for (uint32_t i = tid; i < npk; i += kScoreThreads) { s_bin[i] = pbin[i]; s_yq[i] = pyq[i]; }
-      for (uint32_t i = tid; i <= npk; i += kScoreThreads) s_pre[i] = ppre[i];
-      pbin = s_bin; pyq = s_yq; ppre = s_pre;
-    }
-    if (scored) for (uint32_t i = tid; i < nwords; i += kScoreThreads) bits[i] = 0;
+    const int32_t* pbin = A.pk_bin + pk0; const int32_t* pyq = A.pk_yq + pk0;
+    if (npk <= kPeakCap && mt.pre_blocks) { pbin = s_bin + slot * kPeakCap; pyq = s_yq + slot * kPeakCap; }
     for (uint32_t r = tid; r < K; r += kScoreThreads) sh.top[r] = 0ull;
-    __syncthreads();
-    // ---- occupied blocks: every bin within 75 of a peak, and the bin behind (where the window's difference entry goes)
-    if (scored) {
-      for (uint32_t p = tid; p < npk; p += kScoreThreads) {
+
+    if (scored && !mt.pre_blocks) {
+      // ---- (spectra the prefetch warp left alone: more peaks or table blocks than the shared-memory staging holds)
+      for (uint32_t i = tid; i < nwords; i += kScoreThreads) bits[i] = 0;
+      __syncthreads();
+      for (uint32_t p = tid; p < npk; p += kScoreThreads) {   // every bin within 75 of a peak, and the bin behind
         const int32_t b = pbin[p];
         const uint32_t b0 = (uint32_t)max(b - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(b + kXcorrOffset + 1), NB - 1) >> kBlkShift;
         for (uint32_t k = b0; k <= b1; k++) atomicOr(&bits[k >> 5], 1u << (k & 31));
       }
-    }
-    __syncthreads();
-    if (scored && warp == 0) {   // exclusive popcount prefix over the bitmap words
-      uint32_t run = 0;
-      for (uint32_t base = 0; base < nwords; base += 32) {
-        const uint32_t i = base + lane;
-        const uint32_t c = i < nwords ? (uint32_t)__popc(bits[i]) : 0u;
-        uint32_t incl = c;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-        if (i < nwords) bpre[i] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
+      __syncthreads();
+      if (warp == 0) {   // exclusive popcount prefix over the bitmap words
+        uint32_t run = 0;
+        for (uint32_t base = 0; base < nwords; base += 32) {
+          const uint32_t i = base + lane;
+          const uint32_t c = i < nwords ? (uint32_t)__popc(bits[i]) : 0u;
+          uint32_t incl = c;
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+          if (i < nwords) bpre[i] = run + incl - c;
+          run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) sh.nact = run;
       }
-      if (lane == 0) sh.nact = run;
+      __syncthreads();
     }
-    __syncthreads();
-    const uint32_t nact = scored ? sh.nact : 0;
+    const uint32_t nact = scored ? (mt.pre_blocks ? mt.nact : sh.nact) : 0;
     MD_TICK(0);
 
     const bool fast = K <= kFastTopK && ncand <= kCandChunk;   // warp-local top-k, merged by warp 0 while the others move on
@@ -468,36 +563,37 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       const uint32_t cn = min(kCandChunk, ncand - c0);
       for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
       // counting sort of the chunk by peptide length, longest first
-      if (tid < 64) sh.hist[tid] = 0;
-      __syncthreads();
-      static_assert(kCandChunk <= 2 * kScoreThreads, "a thread sorts at most two candidates of a chunk");
-      uint32_t len2[2] = {0, 0};
-      if (scored) {
+      {
+        if (tid < 64) sh.hist[tid] = 0;
+        __syncthreads();
+        static_assert(kCandChunk <= 2 * kScoreThreads, "a thread sorts at most two candidates of a chunk");
+        uint32_t len2[2] = {0, 0};
+        if (scored) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t v = tid + h * kScoreThreads;
-          if (v < cn) {
-            const uint32_t u = c0 + v;
-            const uint32_t len = u < nt ? (uint32_t)(A.cand_desc[t0c + u] >> 40) & 0xFF : A.dec_len[(uint64_t)s * C.n_per + (u - nt)];
-            len2[h] = len;
-            atomicAdd(&sh.hist[63u - min(len, 63u)], 1u);
-            my_pairs++; my_bytes += 14 + len;
+          for (int h = 0; h < 2; h++) {
+            const uint32_t v = tid + h * kScoreThreads;
+            if (v < cn) {
+              const uint32_t len = cand_len(A, s, c0 + v, nt, t0c, C.n_per);
+              len2[h] = len;
+              atomicAdd(&sh.hist[63u - min(len, 63u)], 1u);
+              my_pairs++; my_bytes += 14 + len;
+            }
           }
         }
-      }
-      __syncthreads();
-      if (warp == 0) {  // exclusive prefix over the 64 buckets
-        const uint32_t h0 = sh.hist[2 * lane], h1 = sh.hist[2 * lane + 1];
-        uint32_t incl = h0 + h1;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-        sh.hist[2 * lane] = incl - h0 - h1; sh.hist[2 * lane + 1] = incl - h1;
-      }
-      __syncthreads();
-      if (scored) {
+        __syncthreads();
+        if (warp == 0) {  // exclusive prefix over the 64 buckets
+          const uint32_t h0 = sh.hist[2 * lane], h1 = sh.hist[2 * lane + 1];
+          uint32_t incl = h0 + h1;
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+          sh.hist[2 * lane] = incl - h0 - h1; sh.hist[2 * lane + 1] = incl - h1;
+        }
+        __syncthreads();
+        if (scored) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t v = tid + h * kScoreThreads;
-          if (v < cn) s_order[atomicAdd(&sh.hist[63u - min(len2[h], 63u)], 1u)] = (uint16_t)v;
+          for (int h = 0; h < 2; h++) {
+            const uint32_t v = tid + h * kScoreThreads;
+            if (v < cn) s_order[atomicAdd(&sh.hist[63u - min(len2[h], 63u)], 1u)] = (uint16_t)v;
+          }
         }
       }
       // (visible to the scoring warps after the table-build barriers)
@@ -552,32 +648,34 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           }
           __syncthreads();
           MD_TICK(3);
-          // (3) the scan, in place, negated: every warp owns a contiguous range of 16-byte words; pass A adds up the
-          //     ranges, pass B rescans each range from the sum of the ranges in front of it
+          // (3) the scan, in place, negated: every thread owns a contiguous range of 16-byte words (an odd number of them:
+          //     the 128-bit accesses of a quarter warp then fall into distinct banks); pass A adds up the ranges, a warp scan
+          //     and the per-warp sums give every thread its start value, pass B rescans the range
           {
             uint4* t4 = reinterpret_cast<uint4*>(tab) + kBlk / 4;            // entry 0 = first occupied block
             const uint32_t N4 = cbn * (kBlk / 4);
-            const uint32_t per = (((N4 + NW - 1) / NW) + 31u) & ~31u;
-            const uint32_t s0 = min(warp * per, N4), s1 = min(s0 + per, N4);
+            const uint32_t c4 = ((N4 + kScoreThreads - 1) / kScoreThreads) | 1u;
+            const uint32_t s0 = min(tid * c4, N4), s1 = min(s0 + c4, N4);
             uint32_t part = 0;
-            for (uint32_t i = s0 + lane; i < s1; i += 32) { const uint4 v = t4[i]; part += v.x + v.y + v.z + v.w; }
-            part = __reduce_add_sync(0xffffffffu, part);
-            if (lane == 0) sh.wsum[warp] = part;
+            for (uint32_t i = s0; i < s1; i++) { const uint4 v = t4[i]; part += v.x + v.y + v.z + v.w; }
+            uint32_t incl = part;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            if (lane == 31) sh.wsum[warp] = incl;
             __syncthreads();
-            uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? sh.wsum[lane] : 0u) + (uint32_t)sh.cin;
-            for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
-              const uint32_t i = i0 + lane;
-              uint4 v = i < s1 ? t4[i] : make_uint4(0, 0, 0, 0);
-              v.y += v.x; v.z += v.y; v.w += v.z;
-              uint32_t incl = v.w;
-              for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-              const uint32_t ex = run + incl - v.w;
-              if (i < s1) t4[i] = make_uint4(0u - (ex + v.x), 0u - (ex + v.y), 0u - (ex + v.z), 0u - (ex + v.w));
-              run += __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? sh.wsum[lane] : 0u) + (uint32_t)sh.cin + incl - part;
+            for (uint32_t i = s0; i < s1; i++) {
+              uint4 v = t4[i];
+              v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w;
+              t4[i] = make_uint4(0u - v.x, 0u - v.y, 0u - v.z, 0u - v.w);
             }
           }
           __syncthreads();
-          // (4) score the chunk against the tile
+          // (4) score the chunk against the tile; one warp first fetches the CTA's next spectrum
+          if (!side_done) {
+            if (warp == kPrefetchWarp) prefetch_spectrum(A, sh, slot ^ 1u, s_bin, s_yq);
+            if (warp == kFinishWarp && it > 0) finish_spectrum(A, C, sh, slot ^ 1u);
+            side_done = true;
+          }
           {
             TableView V;
             V.tab_s = (uint32_t)__cvta_generic_to_shared(tab); V.map_s = (uint32_t)__cvta_generic_to_shared(s_map); V.nblk = nblk; V.gmap = map;
@@ -626,34 +724,30 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         __syncthreads();
       }
     }
+    if (!side_done) {   // (nothing was scored)
+      if (warp == kPrefetchWarp) prefetch_spectrum(A, sh, slot ^ 1u, s_bin, s_yq);
+      if (warp == kFinishWarp && it > 0) finish_spectrum(A, C, sh, slot ^ 1u);
+    }
     // ---- PSM rows
     if (fast) {
+      // per-warp top-k lists; the finish warp merges them and writes the rows during the next scoring phase
       if (scored && K) {
         unsigned long long k0 = tid < ncand ? psm_key(s_score[tid], tid) : 0ull;
         unsigned long long k1 = tid + kScoreThreads < ncand ? psm_key(s_score[tid + kScoreThreads], tid + kScoreThreads) : 0ull;
         for (uint32_t r = 0; r < K; r++) {
           const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
           if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
-          if (lane == 0) sh.wtop[warp][r] = wm;
+          if (lane == 0) sh.wtop[slot][warp][r] = wm;
         }
       }
-      __syncthreads();
+      if (tid == 0) {
+        FinRecord f; f.pr = pr; f.t0c = t0c; f.s = s; f.nt = nt; f.nd = nd; f.pending = 1; f.ranked = (scored && K) ? 1u : 0u;
+        sh.fin[slot] = f;
+      }
       MD_TICK(5);
-      if (warp == 0) {
-        unsigned long long mine = 0ull;      // lane r ends up with the r-th best key of the spectrum
-        if (scored && K) {
-          uint32_t idx = 0;
-          for (uint32_t r = 0; r < K; r++) {
-            const unsigned long long head = (lane < NW && idx < K) ? sh.wtop[lane][idx] : 0ull;
-            const unsigned long long wm = warp_max_u64(head);
-            if (wm != 0ull && head == wm) idx++;
-            if (lane == r) mine = wm;
-          }
-        }
-        if (lane < K) write_psm_row(A, C, pr, s, lane, mine, nt, nd, t0c);
-      }
     } else {
       for (uint32_t r = tid; r < K; r += kScoreThreads) write_psm_row(A, C, pr, s, r, scored ? sh.top[r] : 0ull, nt, nd, t0c);
+      if (tid == 0) sh.fin[slot].pending = 0;
       __syncthreads();
       MD_TICK(5);
     }
@@ -744,8 +838,8 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
   A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
   A.gmap = gstride ? W.gmap.p : nullptr; A.gbits = gstride ? W.gbits.p : nullptr; A.gmap_stride = gstride;
-  const size_t smem = (size_t)kTileBins * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + (size_t)kPeakCap * 8 + ((size_t)kPeakCap + 4) * 4 +
-                      (size_t)kCandChunk * 2 + ((size_t)kMapCap + 2) * 2;
+  const size_t smem = (size_t)kTileBins * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + 2 * (size_t)kPeakCap * 8 + (size_t)kCandChunk * 2 +
+                      ((size_t)kMapCap + 2) * 2;
   MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (has_var) {
     MD_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
