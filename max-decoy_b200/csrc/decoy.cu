@@ -129,7 +129,7 @@ struct RngRing {
   __device__ __forceinline__ uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
 };
 #ifndef MD_RNG_PERIOD
-#define MD_RNG_PERIOD 4
+#define MD_RNG_PERIOD 8
 #endif
 constexpr uint32_t kRngPeriod = MD_RNG_PERIOD;
 #ifndef MD_REFILL_MIN
@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
       // ---- the step: substitution at the first improving position (modified_peptide.rs:454-487), else the kick (:489-505)
       const bool sub = cand != 0;
       uint32_t p;
-      if (sub) p = MO::ffs(cand) - 1u; else p = rng.below(L);
+      // the kick takes ONE word r of the attempt's stream: position = high half of r*L, letter = high half of low32(r*L)*21
+      uint32_t kick_lo = 0;
+      if (sub) p = MO::ffs(cand) - 1u;
+      else { const uint64_t rl = (uint64_t)rng.next() * L; p = (uint32_t)(rl >> 32); kick_lo = (uint32_t)rl; }
       const uint32_t old = seq.at(p);
       uint32_t c;
       if (sub) {
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
         const int32_t nd = d + s_mprime[c] - s_mprime[old];
         if (!((uint32_t)(nd < 0 ? -nd : nd) < (uint32_t)(d < 0 ? -d : d) && c != old)) { flags |= 4u; c = old; }   // filter and search disagree: cannot happen
       } else {
-        c = rng.below(MD_ALPHABET_SIZE);
+        c = (uint32_t)(((uint64_t)kick_lo * MD_ALPHABET_SIZE) >> 32);
       }
       // ---- put letter c at position p: remove_modification_at + swap + fixed modification of the new letter (:470-482)
       {

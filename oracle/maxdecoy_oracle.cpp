@@ -363,8 +363,11 @@ bool random_attempt(const ModSet& M, const md_precursor& pr, uint64_t seed, uint
         if (try_variable(M, st, pr.lo, pr.hi)) return true;       // :484
       }
     }
-    uint32_t i = rng.below(L);                          // random kick (:489-505)
-    int c = (int)rng.below(MD_ALPHABET_SIZE);
+    // random kick (:489-505): position and letter are both uniform draws; here they come from ONE word r of the
+    // attempt's stream (position = high half of r*L, letter = high half of low32(r*L)*21)
+    const uint64_t rl = (uint64_t)rng.next() * L;
+    uint32_t i = (uint32_t)(rl >> 32);
+    int c = (int)(((uint64_t)(uint32_t)rl * MD_ALPHABET_SIZE) >> 32);
     replace_at(M, st, i, c);
   }
   return false;
