@@ -423,26 +423,33 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
 // earlier success), in attempt order, until the spectrum has n_per decoys (HashSet<Decoy>, decoy_generator.rs:40,164).
 // Linear time: accepted decoys and successes go into a shared-memory hash set keyed by the 64-bit sequence hash, each
 // entry remembering the lowest ordinal (accepted decoys first, then attempts in order) that carried the key; a success
-// is kept iff it is that first carrier.  (Sequences are identified by their 64-bit hash here.)
+// is kept iff it is that first carrier.  (Sequences are identified by their 64-bit hash here.)  The attempt hashes are
+// read from HBM once (staged in shared memory); the kept rows are copied by the whole CTA, four lanes per 64-byte row.
 __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
-                                                      const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, AttemptOut A,
+                                                      const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, uint32_t max_na, AttemptOut A,
                                                       uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
                                                       int64_t* __restrict__ dec_w, uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt,
                                                       uint32_t* __restrict__ dec_count) {
-  extern __shared__ __align__(16) unsigned long long s_key[];   // slots (0 = empty)
-  uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_key + slots);   // slots
-  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_ord + slots);    // kMaxRoundAttempts
-  __shared__ uint32_t s_scan[256];
-  __shared__ uint32_t s_base;
+  extern __shared__ __align__(16) unsigned long long s_key[];     // slots (0 = empty)
+  unsigned long long* s_hash = s_key + slots;                     // max_na: hash of a success (0 -> 1), 0 = failed attempt
+  uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_hash + max_na); // slots
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_ord + slots);  // max_na: kept attempts, in order
+  __shared__ uint32_t s_wsum[8];
   const uint32_t li = blockIdx.x, s = list[li];
   const uint32_t a0 = att_off[li], na = att_off[li + 1] - a0;
   const uint32_t have = dec_count[s];
   const uint64_t dbase = (uint64_t)s * n_per;
   const uint32_t smask = slots - 1;
-  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) { s_key[i] = 0ULL; s_ord[i] = 0xFFFFFFFFu; }
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < slots; i += 256) { s_key[i] = 0ULL; s_ord[i] = 0xFFFFFFFFu; }
+#pragma unroll 4
+  for (uint32_t a = tid; a < na; a += 256) {
+    const uint32_t L = A.len[a0 + a];
+    unsigned long long h = __ldg(reinterpret_cast<const unsigned long long*>(A.hash) + a0 + a);
+    s_hash[a] = L ? (h ? h : 1ULL) : 0ULL;
+  }
   __syncthreads();
   auto insert = [&](unsigned long long h, uint32_t ord) {
-    if (h == 0ULL) h = 1ULL;
     uint32_t slot = (uint32_t)h & smask;
     for (;;) {
       const unsigned long long prev = atomicCAS(&s_key[slot], 0ULL, h);
@@ -450,49 +457,49 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
       slot = (slot + 1) & smask;
     }
   };
-  for (uint32_t j = threadIdx.x; j < have; j += blockDim.x) insert(dec_hash[dbase + j], j);
-  for (uint32_t a = threadIdx.x; a < na; a += blockDim.x) if (A.len[a0 + a]) insert(A.hash[a0 + a], have + a);
+  for (uint32_t j = tid; j < have; j += 256) { const unsigned long long h = dec_hash[dbase + j]; insert(h ? h : 1ULL, j); }
+  for (uint32_t a = tid; a < na; a += 256) { const unsigned long long h = s_hash[a]; if (h) insert(h, have + a); }
   __syncthreads();
-  for (uint32_t a = threadIdx.x; a < na; a += blockDim.x) {
-    bool keep = A.len[a0 + a] != 0;
+  // keep flags + ordered compaction: thread t owns the contiguous chunk [t*per, (t+1)*per), per <= 16
+  const uint32_t per = (na + 255u) / 256u;
+  const uint32_t cb = tid * per, ce = min(cb + per, na);
+  uint32_t keepbits = 0, c = 0;
+  for (uint32_t a = cb; a < ce; a++) {
+    const unsigned long long h = s_hash[a];
+    bool keep = h != 0ULL;
     if (keep) {
-      unsigned long long h = A.hash[a0 + a];
-      if (h == 0ULL) h = 1ULL;
       uint32_t slot = (uint32_t)h & smask;
       while (s_key[slot] != h) slot = (slot + 1) & smask;
       keep = s_ord[slot] == have + a;
     }
-    s_keep[a] = keep ? 1 : 0;
+    if (keep) { keepbits |= 1u << (a - cb); c++; }
+  }
+  uint32_t incl = c;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t before = incl - c, total = 0;
+  for (uint32_t w = 0; w < 8; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; total += v; }
+  const uint32_t room = n_per > have ? n_per - have : 0u;
+  const uint32_t nk = min(total, room);
+  {
+    uint32_t o = before;
+    for (uint32_t m = keepbits; m; m &= m - 1) { if (o < nk) s_list[o] = (uint16_t)(cb + (uint32_t)__ffs(m) - 1u); o++; }
   }
   __syncthreads();
-  // ordered compaction: thread t owns the contiguous chunk [t*per, (t+1)*per)
-  const uint32_t per = (na + blockDim.x - 1) / blockDim.x;
-  const uint32_t b = threadIdx.x * per, e = min(b + per, na);
-  uint32_t c = 0;
-  for (uint32_t a = b; a < e; a++) c += s_keep[a];
-  s_scan[threadIdx.x] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (uint32_t t = 0; t < blockDim.x; t++) { uint32_t v = s_scan[t]; s_scan[t] = run; run += v; }
-    s_base = run;
+  // copy the kept rows (four lanes per row) and their scalars
+  for (uint32_t t = tid; t < nk * 4u; t += 256) {
+    const uint32_t r = t >> 2, q = t & 3u;
+    const uint64_t src = a0 + s_list[r], dst = dbase + have + r;
+    reinterpret_cast<uint4*>(dec_rows + dst * MD_DECOY_ROW)[q] = __ldg(reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW) + q);
   }
-  __syncthreads();
-  uint32_t o = have + s_scan[threadIdx.x];
-  for (uint32_t a = b; a < e; a++) {
-    if (!s_keep[a]) continue;
-    if (o < n_per) {
-      const uint64_t src = a0 + a, dst = dbase + o;
-      const uint4* sr = reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW);
-      uint4* dr = reinterpret_cast<uint4*>(dec_rows + dst * MD_DECOY_ROW);
-      dr[0] = sr[0]; dr[1] = sr[1]; dr[2] = sr[2]; dr[3] = sr[3];
-      dec_len[dst] = A.len[src]; dec_mask[dst] = A.mask[src]; dec_w[dst] = A.w[src]; dec_hash[dst] = A.hash[src];
-      dec_attempt[dst] = att_base[li] + a;
-    }
-    o++;
+  for (uint32_t r = tid; r < nk; r += 256) {
+    const uint32_t a = s_list[r];
+    const uint64_t src = a0 + a, dst = dbase + have + r;
+    dec_len[dst] = A.len[src]; dec_mask[dst] = A.mask[src]; dec_w[dst] = A.w[src]; dec_hash[dst] = A.hash[src];
+    dec_attempt[dst] = att_base[li] + a;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) dec_count[s] = min(n_per, have + s_base);
+  if (tid == 0) dec_count[s] = have + nk;
 }
 
 // Fallback of k_decoy_select for tables that do not fit shared memory (quadratic scan, exact sequence compare).
@@ -775,13 +782,14 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->mark("  attempts");
     {
-      uint32_t need = 1;                                    // most (accepted + attempted) of one spectrum in this round
-      for (uint32_t i = 0; i < n_list; i++) need = std::max(need, count[list[i]] + (off[i + 1] - off[i]));
-      uint32_t slots = 1024; while (slots < 2 * need) slots <<= 1;
-      const size_t smem = (size_t)slots * 12 + kMaxRoundAttempts;
-      if (smem <= 200 * 1024) {
+      uint32_t need = 1, max_na = 1;                        // most (accepted + attempted) / attempted of one spectrum in this round
+      for (uint32_t i = 0; i < n_list; i++) { need = std::max(need, count[list[i]] + (off[i + 1] - off[i])); max_na = std::max(max_na, off[i + 1] - off[i]); }
+      uint32_t slots = 1024; while ((uint64_t)slots * 3 < (uint64_t)need * 4) slots <<= 1;   // load factor <= 0.75 even if every attempt succeeded
+      max_na = (max_na + 7u) & ~7u;
+      const size_t smem = (size_t)slots * 12 + (size_t)max_na * 10;
+      if (smem <= 220 * 1024) {
         MD_CUDA(cudaFuncSetAttribute(k_decoy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, max_na, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
                   W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       } else {
         MD_LAUNCH(ctx, k_decoy_select_n2, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
