@@ -58,6 +58,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.mark_at = 0
+
+    def mark(self):
+        """Start of the timed region: samples from here on are the ones reported (the sampler itself is started before
+        the warm-up, because nvidia-smi needs longer than a short timed region to deliver its first line)."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
@@ -82,7 +88,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.mark_at:]
+        where = "timed region"
+        if not lines:   # timed region shorter than one sampling period: the samples under load just before it (warm-up)
+            lines, where = self.lines[-5:], "warm-up (timed region shorter than one sample)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -96,7 +106,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled_during": where}
 
 
 def make_workload(cfg, rank, n_spectra):
@@ -310,12 +320,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     with torch.cuda.stream(ext):
         for _ in range(args.warmup):
             step_device()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     wall0 = time.time()
     ms_dev, st = timed(step_device, args.steps)
     barrier()

@@ -124,6 +124,28 @@ def test_decoys_random_long_sequences_bit_exact(gpu, cpu, mods, nvar, monkeypatc
     assert_tables_equal(dw, dc)
 
 
+def test_decoys_random_degenerate_masses_bit_exact(gpu, cpu):
+    """Modification sets that make letters collide: G+14.01565 equals A to the micro-dalton (an equal-mass run: ties go to
+    the lower alphabet index), S+12.03637 lands 10 uDa under V and T+27.04728 lands 1 uDa above K (near-ties on either side of
+    a midpoint), plus two variable letters, one of them also fixed (the generic variable-modification path).  The
+    substitution search of the kernel (bucket tables) must agree with the oracle's literal 20-way scan."""
+    from maxdecoy import Modification
+    fix_g = Modification("x:1", "GtoA", "A", True, "G", 14.015650)
+    fix_s = Modification("x:2", "StoV", "A", True, "S", 12.036370)
+    fix_t = Modification("x:3", "TtoK", "A", True, "T", 27.047280)
+    var_m = Modification("unimod:35", "Oxidation", "A", False, "M", 15.994915)
+    var_g = Modification("x:4", "Gvar", "A", False, "G", 0.984016)
+    sp, _ = wl.spectra(300, 16, 2)
+    for mods, nvar in (((synth.CAM, fix_g, fix_s, fix_t), 0), ((synth.CAM, fix_g, fix_s, var_m, var_g), 2)):
+        for e in (gpu, cpu):
+            _setup(e, 300, 2, mods, nvar)
+        pre = wl.precursors_of(cpu, sp)
+        dg = gpu.generate_decoys(pre, 150, maxdecoy.DECOY_REFERENCE_RANDOM, seed=17)
+        dc = cpu.generate_decoys(pre, 150, maxdecoy.DECOY_REFERENCE_RANDOM, seed=17)
+        assert_tables_equal(dg, dc)
+        assert len(dg["attempt"]) > 0
+
+
 def test_decoys_permute_bit_exact(gpu, cpu):
     for e in (gpu, cpu):
         _setup(e, 300, 2, (synth.CAM,), 0)
