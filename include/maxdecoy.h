@@ -207,6 +207,18 @@ typedef struct md_decoy_table {
   int64_t* mod_weight;  /* weight incl. modifications; lo <= mod_weight <= hi */
   uint32_t* attempt;    /* attempt / enumeration ordinal that produced it */
 } md_decoy_table;
+/* Stored decoys: the `decoys` table (db/schema.sql:163-192; Decoy::find_where, models/peptides/decoy.rs:118-153).
+ * identification_task looks persisted decoys up with the same window/count queries as the targets, passes them
+ * through the same ModifiedPeptide filter and reuses them before it generates new ones
+ * (tasks/identification.rs:259-283).  md_decoy_store_set replaces the ctx's store with `n` sequences over MD_ALPHABET
+ * (length 1..60; duplicates are dropped; n = 0 clears it); the store is indexed by W* by md_index_build, or at once if
+ * an index is already built.  With a non-empty store, MD_DECOY_REFERENCE_RANDOM first takes, per spectrum, the stored
+ * decoys that pass the filter in store-index order (W*, then (weight, sequence hash, sequence)) up to the requested
+ * number -- reported with `attempt` = MD_DECOY_STORED -- and generates only the remainder (the reference's order is
+ * the database's row order, i.e. unspecified).  The other modes ignore the store. */
+#define MD_DECOY_STORED 0xFFFFFFFFu
+MD_API int md_decoy_store_set(md_ctx* ctx, const uint8_t* seq, const uint64_t* seq_off, uint64_t n);
+
 MD_API int md_generate_decoys(md_ctx* ctx, const md_precursor* precursors, uint32_t n_spectra,
                               uint32_t n_per_spectrum, int mode, uint64_t seed,
                               md_decoy_table* out);

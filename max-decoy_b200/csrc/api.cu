@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of include/maxdecoy.h on top of the CUDA subsystems (digest / index / decoy / score).
+#include <algorithm>
 #include <cctype>
 #include <chrono>
 #include <cmath>
@@ -248,7 +249,7 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
       if (M.has_var[code]) { n_var_letters++; var_code = (int)code; }
     }
     if (n_var_letters == 1 && !M.has_fix[var_code]) M.var_simple_code = var_code;
-    ctx->mods = M; ctx->mods_set = true; ctx->index.ready = false;
+    ctx->mods = M; ctx->mods_set = true; ctx->index.ready = false; ctx->dindex.ready = false;
   });
 }
 
@@ -355,6 +356,59 @@ void md_candidate_table_free(md_candidate_table* t) {
   if (!t) return;
   free(t->off); free(t->peptide_id); free(t->var_mask); free(t->mod_weight);
   memset(t, 0, sizeof(*t));
+}
+
+// Stored decoys (the `decoys` table): validated, deduplicated and put into canonical order (weight, sequence hash, sequence)
+// on the host -- a one-time upload, not on the hot path -- then laid out like the peptide store so that the same index
+// build, window search and filter kernels serve it.
+int md_decoy_store_set(md_ctx* ctx, const uint8_t* seq, const uint64_t* off, uint64_t n) {
+  if (!ctx || (n && (!seq || !off))) return fail(ctx, MD_ERR_INVALID, "md_decoy_store_set: null argument");
+  return guarded(ctx, [&] {
+    struct E { int64_t w; uint64_t h; uint64_t o; uint32_t len; };
+    std::vector<E> v; v.reserve(n);
+    for (uint64_t i = 0; i < n; i++) {
+      MD_REQUIRE(off[i + 1] >= off[i], MD_ERR_INVALID, "md_decoy_store_set: offsets not monotone");
+      const uint64_t L = off[i + 1] - off[i];
+      MD_REQUIRE(L >= 1 && L <= MD_MAX_PEPTIDE_LEN, MD_ERR_INVALID, "md_decoy_store_set: sequence length must be 1..60");
+      int64_t w = MD_WATER_UDA; uint64_t h = md_hash_init();
+      for (uint64_t k = 0; k < L; k++) {
+        const uint8_t c = seq[off[i] + k];
+        MD_REQUIRE(md_alpha_of_code(md_code_of(c)) >= 0, MD_ERR_INVALID, "md_decoy_store_set: letter outside the decoy alphabet " MD_ALPHABET);
+        w += kResidueMassByCode[md_code_of(c)]; h = md_hash_step(h, c);
+      }
+      v.push_back({w, md_hash_fin(h, (uint32_t)L), off[i], (uint32_t)L});
+    }
+    auto cmp_seq = [&](const E& a, const E& b) {
+      const int c = memcmp(seq + a.o, seq + b.o, std::min(a.len, b.len));
+      return c != 0 ? c : (int)a.len - (int)b.len;
+    };
+    std::sort(v.begin(), v.end(), [&](const E& a, const E& b) { return a.w != b.w ? a.w < b.w : a.h != b.h ? a.h < b.h : cmp_seq(a, b) < 0; });
+    std::vector<uint8_t> h_seq, h_len; std::vector<uint32_t> h_off{0}; std::vector<int64_t> h_w; std::vector<int16_t> h_cnt; std::vector<uint64_t> h_hash;
+    for (size_t i = 0; i < v.size(); i++) {
+      if (i && v[i].len == v[i - 1].len && memcmp(seq + v[i].o, seq + v[i - 1].o, v[i].len) == 0) continue;   // UNIQUE (aa_sequence, weight)
+      int16_t cnt[MD_ALPHABET_SIZE] = {};
+      for (uint32_t k = 0; k < v[i].len; k++) { const uint8_t c = seq[v[i].o + k]; h_seq.push_back(c); cnt[md_alpha_of_code(md_code_of(c))]++; }
+      h_off.push_back((uint32_t)h_seq.size()); h_len.push_back((uint8_t)v[i].len); h_w.push_back(v[i].w); h_hash.push_back(v[i].h);
+      h_cnt.insert(h_cnt.end(), cnt, cnt + MD_ALPHABET_SIZE);
+    }
+    PeptideStore& D = ctx->dstore;
+    D.ready = false; ctx->dindex.ready = false;
+    const size_t m = h_len.size();
+    D.n = m; D.seq_bytes = h_seq.size(); D.n_assoc = 0;
+    if (m) {
+      D.seq.need(h_seq.size() + 1); D.seq_off.need(m + 1); D.len.need(m); D.mc.need(m); D.weight.need(m); D.counts.need(m * MD_ALPHABET_SIZE); D.hash.need(m);
+      MD_CUDA(cudaMemcpyAsync(D.seq.p, h_seq.data(), h_seq.size(), cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaMemcpyAsync(D.seq_off.p, h_off.data(), (m + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaMemcpyAsync(D.len.p, h_len.data(), m, cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaMemsetAsync(D.mc.p, 0, m, ctx->stream));
+      MD_CUDA(cudaMemcpyAsync(D.weight.p, h_w.data(), m * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaMemcpyAsync(D.counts.p, h_cnt.data(), m * MD_ALPHABET_SIZE * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaMemcpyAsync(D.hash.p, h_hash.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+      MD_CUDA(cudaStreamSynchronize(ctx->stream));
+      D.ready = true;
+    }
+    if (ctx->index.ready) index_build_store(ctx);
+  });
 }
 
 int md_generate_decoys(md_ctx* ctx, const md_precursor* pr, uint32_t n_spec, uint32_t n_per, int mode, uint64_t seed, md_decoy_table* out) {

@@ -90,6 +90,9 @@ struct md_ctx {
   // stores
   PeptideStore peps;
   MassIndex index;
+  // stored decoys (the `decoys` table): same layout and index as the peptides, no protein associations / hash table
+  PeptideStore dstore;
+  MassIndex dindex;
   IdentifyWorkspace ws;
   LastDecoys last;
   uint64_t launches = 0;   // hand-written kernels launched by the current call
@@ -117,6 +120,11 @@ struct md_ctx {
 void digest_run(md_ctx* ctx, const uint8_t* residues, const uint64_t* off, uint32_t n_prot, const md_digest_params& p);
 void digest_export(md_ctx* ctx, md_peptide_table* out);
 void index_build_run(md_ctx* ctx);
+// (re)index the stored decoys with the current modifications (no-op without a store)
+void index_build_store(md_ctx* ctx);
+// stored decoys that pass the ModifiedPeptide filter, in store-index order, into the first decoy slots of each of the n
+// precursors in ws.prec (ws.dec_* must be allocated); sets ws.dec_count
+void decoys_reuse_dev(md_ctx* ctx, uint32_t n, uint32_t n_per);
 void index_window_search_dev(md_ctx* ctx, const md_precursor* prec_dev, uint32_t n, uint64_t* begin_dev, uint64_t* end_dev);
 // fills ws.cand_* and ws.cand_off for the n precursors in ws.prec; returns total accepted
 uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n);

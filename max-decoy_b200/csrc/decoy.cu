@@ -693,6 +693,12 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   }
   // per spectrum bookkeeping on the host
   std::vector<uint32_t> used(n, 0), count(n, 0), cap(n);
+  // stored decoys come first (tasks/identification.rs:259-283); only the remainder is generated
+  if (mode == MD_DECOY_REFERENCE_RANDOM && ctx->dindex.ready && ctx->dindex.n > 0) {
+    decoys_reuse_dev(ctx, n, n_per);
+    MD_CUDA(cudaMemcpyAsync(count.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   // spectra in ascending precursor mass: neighbouring attempts grow sequences of similar length (lockstep passes)
   std::vector<uint32_t> by_mass(n);
   {
@@ -734,7 +740,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       const uint32_t s = by_mass[si];
       if (count[s] >= n_per || used[s] >= cap[s]) continue;
       uint32_t want;
-      if (used[s] == 0) want = n_per + n_per / 4 + 32;
+      if (used[s] == 0) { const uint32_t rem = n_per - count[s]; want = rem + rem / 4 + 32; }
       else {
         double yield = std::max(0.02, (double)count[s] / (double)used[s]);
         want = (uint32_t)((double)(n_per - count[s]) / yield * 1.3) + 48;

@@ -171,6 +171,38 @@ __global__ void k_scatter_candidates(const uint64_t* __restrict__ flat_off, cons
   cand_desc[o] = idx_desc[i]; cand_mask[o] = emask[e]; cand_w[o] = ew[e]; cand_pep[o] = idx_pep[i];
 }
 
+// accepted window entries of the decoy store -> the first decoy slots of their spectrum (rank within the spectrum < n_per)
+__global__ void k_scatter_stored_decoys(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, uint32_t n_spec, uint64_t n_entries,
+                                        const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, const uint64_t* __restrict__ emask,
+                                        const int64_t* __restrict__ ew, const uint32_t* __restrict__ idx_pep, const uint64_t* __restrict__ idx_desc,
+                                        const uint8_t* __restrict__ rows, const uint64_t* __restrict__ store_hash, uint32_t n_per,
+                                        uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
+                                        int64_t* __restrict__ dec_w, uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries || !flag[e]) return;
+  uint32_t lo = 0, hi = n_spec;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
+  const uint32_t s = lo;
+  const uint32_t rank = pos[e] - pos[flat_off[s]];
+  if (rank >= n_per) return;
+  const uint64_t i = rbegin[s] + (e - flat_off[s]);
+  const uint64_t d = idx_desc[i];
+  const uint8_t* src = rows + (d & 0xFFFFFFFFFFull) * 16;
+  const uint32_t L = (uint32_t)(d >> 40) & 0xFF;
+  const uint64_t slot = (uint64_t)s * n_per + rank;
+  uint8_t* dst = dec_rows + slot * MD_DECOY_ROW;
+  for (uint32_t k = 0; k < MD_DECOY_ROW; k++) dst[k] = k < L ? src[k] : (uint8_t)MD_CODE_OTHER;
+  dec_len[slot] = (uint8_t)L; dec_mask[slot] = emask[e]; dec_w[slot] = ew[e]; dec_hash[slot] = store_hash[idx_pep[i]];
+  dec_attempt[slot] = MD_DECOY_STORED;
+}
+
+__global__ void k_stored_counts(const uint64_t* __restrict__ flat_off, const uint32_t* __restrict__ pos, uint32_t n_spec, uint32_t n_per,
+                                uint32_t* __restrict__ dec_count) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_spec) return;
+  dec_count[s] = min(n_per, pos[flat_off[s + 1]] - pos[flat_off[s]]);
+}
+
 __global__ void k_cand_offsets(const uint64_t* __restrict__ flat_off, const uint32_t* __restrict__ pos, uint32_t n_spec, uint64_t* __restrict__ cand_off) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > n_spec) return;
@@ -179,10 +211,7 @@ __global__ void k_cand_offsets(const uint64_t* __restrict__ flat_off, const uint
 
 }  // namespace
 
-void index_build_run(md_ctx* ctx) {
-  PeptideStore& P = ctx->peps; MassIndex& X = ctx->index;
-  MD_REQUIRE(P.ready, MD_ERR_STATE, "md_index_build: md_digest first");
-  MD_REQUIRE(ctx->mods_set, MD_ERR_STATE, "md_index_build: md_set_modifications first");
+static void index_build_for(md_ctx* ctx, PeptideStore& P, MassIndex& X) {
   X.ready = false;
   const uint32_t n = (uint32_t)P.n;
   X.n = n; X.row_bytes = 0; X.min_key = X.max_key = 0;
@@ -206,16 +235,31 @@ void index_build_run(md_ctx* ctx) {
   X.ready = true;
 }
 
+void index_build_run(md_ctx* ctx) {
+  MD_REQUIRE(ctx->peps.ready, MD_ERR_STATE, "md_index_build: md_digest first");
+  MD_REQUIRE(ctx->mods_set, MD_ERR_STATE, "md_index_build: md_set_modifications first");
+  index_build_for(ctx, ctx->peps, ctx->index);
+  index_build_store(ctx);
+}
+
+void index_build_store(md_ctx* ctx) {
+  ctx->dindex.ready = false;
+  if (!ctx->dstore.ready || !ctx->mods_set) return;
+  index_build_for(ctx, ctx->dstore, ctx->dindex);
+}
+
 void index_window_search_dev(md_ctx* ctx, const md_precursor* prec_dev, uint32_t n, uint64_t* begin_dev, uint64_t* end_dev) {
   if (!n) return;
   MD_LAUNCH(ctx, k_window_search, blocks((uint64_t)n * 32, 128), 128, 0, ctx->index.key.p, ctx->index.n, prec_dev, n, begin_dev, end_dev);
 }
 
-uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
-  IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->index;
-  W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2); W.cand_off.need(n + 2);
-  if (!n) return 0;
-  index_window_search_dev(ctx, W.prec.p, n, W.rbegin.p, W.rend.p);
+// Window search + ModifiedPeptide filter of the n precursors in ws.prec against one index: leaves the flattened windows
+// (ws.rbegin, ws.flat_off), the per-entry results (t_flag, emask, ew) and the exclusive scan of the flags (t_pos, E+1
+// entries) in the workspace; returns the number of window entries E and the number of accepted ones.
+static uint64_t filter_windows(md_ctx* ctx, const MassIndex& X, const int16_t* counts, uint32_t n, uint32_t* total_out) {
+  IdentifyWorkspace& W = ctx->ws;
+  W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2);
+  MD_LAUNCH(ctx, k_window_search, blocks((uint64_t)n * 32, 128), 128, 0, X.key.p, X.n, W.prec.p, n, W.rbegin.p, W.rend.p);
   ctx->mark("  window_search");
   DevBuf<uint64_t>& d_size = W.t_size; d_size.need(n + 1);
   MD_LAUNCH(ctx, k_range_sizes, blocks(n + 1), 256, 0, W.rbegin.p, W.rend.p, n, d_size.p);
@@ -232,19 +276,43 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   ctx->mark("  alloc");
   if (E) {
     MD_LAUNCH(ctx, k_filter, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, W.prec.p, n, E, X.pep.p, X.wfix.p, X.varpos.p, X.desc.p, X.rows.p,
-              ctx->peps.counts.p, d_K.p, ctx->mods, d_flag.p, W.emask.p, W.ew.p, d_ovf.p);
+              counts, d_K.p, ctx->mods, d_flag.p, W.emask.p, W.ew.p, d_ovf.p);
   }
   ctx->mark("  filter");
   cubx_exclusive_sum(ctx, d_flag.p, d_pos.p, E + 1);
-  const uint32_t total = d2h_scalar(ctx, d_pos.p + E);
+  *total_out = d2h_scalar(ctx, d_pos.p + E);
   const int ovf = d2h_scalar(ctx, d_ovf.p);
   MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "variable-modification placement enumeration exceeds 2^22 subsets for one peptide");
+  return E;
+}
+
+uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
+  IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->index;
+  W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2); W.cand_off.need(n + 2);
+  if (!n) return 0;
+  uint32_t total = 0;
+  const uint64_t E = filter_windows(ctx, X, ctx->peps.counts.p, n, &total);
   W.cand_desc.need(total + 1); W.cand_mask.need(total + 1); W.cand_w.need(total + 1); W.cand_pep.need(total + 1);
   if (E) {
-    MD_LAUNCH(ctx, k_scatter_candidates, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, d_flag.p, d_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
+    MD_LAUNCH(ctx, k_scatter_candidates, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, W.t_flag.p, W.t_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
               W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
   }
-  MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, d_pos.p, n, W.cand_off.p);
+  MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, W.t_pos.p, n, W.cand_off.p);
   ctx->mark("  scatter");
   return total;
+}
+
+// Decoy reuse (tasks/identification.rs:259-283): the stored decoys of each precursor's window that pass the filter, in
+// store-index order, become the first decoys of the spectrum.
+void decoys_reuse_dev(md_ctx* ctx, uint32_t n, uint32_t n_per) {
+  IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->dindex;
+  if (!n || !n_per || !X.ready || X.n == 0) return;
+  uint32_t total = 0;
+  const uint64_t E = filter_windows(ctx, X, ctx->dstore.counts.p, n, &total);
+  if (E) {
+    MD_LAUNCH(ctx, k_scatter_stored_decoys, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, W.t_flag.p, W.t_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
+              X.rows.p, ctx->dstore.hash.p, n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p, W.dec_attempt.p);
+  }
+  MD_LAUNCH(ctx, k_stored_counts, blocks(n), 256, 0, W.flat_off.p, W.t_pos.p, n, n_per, W.dec_count.p);
+  ctx->mark("  reuse");
 }

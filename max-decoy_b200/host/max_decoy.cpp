@@ -410,7 +410,7 @@ int cmd_identification(int argc, char** argv) {
                                  {"d", "number-of-decoys", "decoys"}, {"l", "lower-mass-tolerance", "lower"}, {"u", "upper-mass-tolerance", "upper"},
                                  {"", "fragmentation-tolerance", "fragtol"}, {"t", "thread-count", "threads"}, {"", "max-time-for-decoy-generation", "maxtime"},
                                  {"r", "comet-revision", "rev"}, {"", "fasta", "fasta"}, {"c", "number-of-missed-cleavages", "mc"}, {"o", "out", "out"},
-                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}});
+                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}, {"", "stored-decoys", "stored"}});
   if (!a.has("mods") || !a.has("spectra") || !a.has("fasta")) die("identification: -m, -s and --fasta are required");
   const std::vector<Mod> mods = read_mods(a.get("mods"));
   const Fasta f = read_fasta(a.get("fasta"));
@@ -420,6 +420,25 @@ int cmd_identification(int argc, char** argv) {
   digest_into(ctx, f, (uint32_t)a.num("mc", 2), 5, 50);
   auto am = to_abi(mods);
   check(ctx, md_set_modifications(ctx, am.data(), (uint32_t)am.size(), (uint32_t)nvar), "md_set_modifications");
+  if (a.has("stored")) {
+    // the `decoys` table as CSV (id, aa_sequence, ...) or one sequence per line: reused before new decoys are generated
+    // (tasks/identification.rs:259-283)
+    std::ifstream in(a.get("stored"));
+    if (!in) die("identification: cannot read " + a.get("stored"));
+    std::string line, blob; std::vector<uint64_t> off{0};
+    while (std::getline(in, line)) {
+      std::string q = line;
+      const size_t c0 = line.find(',');
+      if (c0 != std::string::npos) { const size_t c1 = line.find(',', c0 + 1); q = line.substr(c0 + 1, (c1 == std::string::npos ? line.size() : c1) - c0 - 1); }
+      std::string t;
+      for (char ch : q) if (ch != '"' && ch != ' ' && ch != '\r' && ch != '\t') t.push_back(ch);
+      bool ok = !t.empty();
+      for (char ch : t) if (ch < 'A' || ch > 'Z') ok = false;
+      if (!ok) continue;
+      blob += t; off.push_back(blob.size());
+    }
+    check(ctx, md_decoy_store_set(ctx, (const uint8_t*)blob.data(), off.data(), off.size() - 1), "md_decoy_store_set");
+  }
   check(ctx, md_index_build(ctx), "md_index_build");
   md_search_params p;
   std::memset(&p, 0, sizeof p);

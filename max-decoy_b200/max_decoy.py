@@ -51,6 +51,19 @@ def cmd_digest(args):
     print("%d proteins, %d unique peptides -> %s" % (len(seqs), n, args.out))
 
 
+def _read_stored_decoys(path):
+    """The `decoys` table as CSV (`pgexport.decoys_csv`: id, aa_sequence, ...) or one sequence per line: the decoys the
+    reference would find in its database and reuse (tasks/identification.rs:259-283)."""
+    out = []
+    with open(path) as fh:
+        for line in fh:
+            f = [x.strip().strip('"') for x in line.strip().split(",")]
+            q = f[1] if len(f) > 1 else f[0]
+            if q and q.isalpha() and q.isupper():
+                out.append(q)
+    return out
+
+
 def cmd_identification(args):
     """`identification` (src/main.rs:397-485, tasks/identification.rs:160-370) for every MS2 spectrum of the file."""
     import maxdecoy
@@ -61,6 +74,8 @@ def cmd_identification(args):
     eng = _engine(args)
     eng.digest(seqs, args.missed, args.min_len, args.max_len)
     eng.set_modifications(mods, args.nvar)
+    if args.stored_decoys:
+        eng.set_decoy_store(_read_stored_decoys(args.stored_decoys))
     eng.index_build()
     prm = maxdecoy.SearchParams(args.lower, args.upper, fragment_tolerance=args.fragmentation_tolerance, n_decoys=args.decoys,
                                 decoy_mode=args.decoy_mode, seed=args.seed, top_k=args.top_k)
@@ -76,6 +91,8 @@ def cmd_identification(args):
             return raw[int(so[i]):int(so[i + 1])].decode()
         return table_seqs[int(row["candidate"]) - 1]
     pm = [eng.precursor_window(float(spectra.precursor_mz[i]), int(spectra.charge[i]), args.lower, args.upper)[0] for i in range(len(spectra))]
+    with open(os.path.join(args.out, "decoys.csv"), "w") as fh:       # rows of table `decoys`: what a later run can reuse (--stored-decoys)
+        fh.write(pgexport.decoys_csv(dec))
     with open(os.path.join(args.out, "psms.csv"), "w") as fh:
         fh.write(pgexport.psms_csv(psms, ids, seq_of, lambda s, row: outputs.modification_summary(seq_of(s, row), mods, int(row["var_mask"])), pm))
     print("%d spectra, %d targets, %d decoys scored, %d spectra with fewer decoys than requested -> %s"
@@ -177,6 +194,7 @@ def main(argv=None):
     p.add_argument("--minimum-peptide_length", dest="min_len", type=int, default=5)
     p.add_argument("--maximum-peptide_length", dest="max_len", type=int, default=50)
     p.add_argument("--top-k", type=int, default=5)
+    p.add_argument("--stored-decoys", default="", help="CSV of the `decoys` table (or one sequence per line): reused before new decoys are generated")
     p.add_argument("-o", "--out", default="identification_out")
     p.set_defaults(fn=cmd_identification)
 

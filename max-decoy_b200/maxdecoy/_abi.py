@@ -18,6 +18,7 @@ STATUS_NAMES = {0: "MD_OK", -1: "MD_ERR_INVALID", -2: "MD_ERR_STATE", -3: "MD_ER
 DECOY_REFERENCE_RANDOM = 0
 DECOY_EXHAUSTIVE = 1
 DECOY_PERMUTE_TARGET = 2
+DECOY_STORED = 0xFFFFFFFF   # `attempt` of a decoy taken from the store (md_decoy_store_set)
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -128,6 +129,7 @@ SYMBOLS = {
     "md_index_export": (C.c_int, [ctx_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "md_candidates": (C.c_int, [ctx_p, C.POINTER(md_precursor), C.c_uint32, C.POINTER(md_candidate_table)]),
     "md_candidate_table_free": (None, [C.POINTER(md_candidate_table)]),
+    "md_decoy_store_set": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "md_generate_decoys": (C.c_int, [ctx_p, C.POINTER(md_precursor), C.c_uint32, C.c_uint32, C.c_int,
                                      C.c_uint64, C.POINTER(md_decoy_table)]),
     "md_decoy_table_free": (None, [C.POINTER(md_decoy_table)]),

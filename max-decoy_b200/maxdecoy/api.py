@@ -321,6 +321,12 @@ class Engine:
             self.lib.md_decoy_table_free(C.byref(t))
         return out
 
+    def set_decoy_store(self, sequences):
+        """The `decoys` table: decoys persisted by earlier runs, reused before new ones are generated
+        (tasks/identification.rs:259-283; models/peptides/decoy.rs:118-153).  An empty list clears the store."""
+        buf, off = pack_proteins(sequences)
+        self._ck(self.lib.md_decoy_store_set(self.h, _ptr(buf), _ptr(off), len(off) - 1))
+
     def generate_decoys(self, precursors, n_per_spectrum, mode=_abi.DECOY_REFERENCE_RANDOM, seed=0):
         """DecoyGenerator::generate_decoys (decoy_generator.rs:108-219) for many spectra at once."""
         arr = self._precursors(precursors)

@@ -157,6 +157,17 @@ struct Index {
   std::vector<uint32_t> pep;  // 0-based peptide ordinal
 };
 
+// Decoys persisted by earlier runs (the `decoys` table, db/schema.sql; Decoy::find_where, models/peptides/decoy.rs:118-153):
+// unique sequences in canonical order (weight, hash, bytes) + their index by W* (same key as the peptides).
+struct DecoyStore {
+  std::vector<std::string> seq;
+  std::vector<int64_t> weight;
+  std::vector<int16_t> counts;  // n*21
+  bool indexed = false;
+  std::vector<int64_t> key;
+  std::vector<uint32_t> ord;
+};
+
 struct Candidate { uint32_t pep; uint64_t mask; int64_t w; };
 struct Decoy { std::string seq; uint64_t mask; int64_t weight; int64_t w; uint32_t attempt; };
 
@@ -168,6 +179,7 @@ struct md_ctx {
   ModSet mods;
   Peptides peps;
   Index index;
+  DecoyStore store;
   std::vector<std::vector<Decoy>> last_decoys;
   bool have_last_decoys = false;
 };
@@ -381,11 +393,33 @@ void substitution_map(const ModSet& M, int64_t* out) {  // decoy_generator.rs:30
 uint32_t attempt_cap(uint32_t n) { return 16u * n + 1024u; }
 
 
+// Stored decoys first (tasks/identification.rs:259-283): the same window/count queries as the targets
+// (Decoy::find_where), the same ModifiedPeptide filter (from_decoy + try_variable_modifications), until n decoys.
+// The reference takes them in database row order; here: in store-index order (W*, then canonical store order).
+void decoys_reuse(const md_ctx* ctx, const md_precursor& pr, uint32_t n, std::vector<Decoy>* out) {
+  const DecoyStore& D = ctx->store; const ModSet& M = ctx->mods;
+  if (!D.indexed || D.seq.empty()) return;
+  size_t b = std::lower_bound(D.key.begin(), D.key.end(), pr.lo) - D.key.begin();
+  size_t e = std::upper_bound(D.key.begin(), D.key.end(), pr.hi) - D.key.begin();
+  ModState st;
+  for (size_t i = b; i < e && out->size() < n; i++) {
+    uint32_t d = D.ord[i];
+    if (!fanout_admits(M, &D.counts[(size_t)d * MD_ALPHABET_SIZE], pr.mass, pr.lo)) continue;
+    const std::string& q = D.seq[d];
+    from_string(M, (const uint8_t*)q.data(), (uint32_t)q.size(), &st);
+    bool ok = in_window(st.w, pr.lo, pr.hi);
+    if (!ok) ok = try_variable(M, &st, pr.lo, pr.hi);
+    if (ok) out->push_back({q, var_mask_of(st), D.weight[d], st.w, MD_DECOY_STORED});
+  }
+}
+
 void decoys_random(const md_ctx* ctx, const md_precursor& pr, uint32_t n, uint64_t seed,
                    std::vector<Decoy>* out) {
   int64_t delta[MD_ALPHABET_SIZE * MD_ALPHABET_SIZE];
   substitution_map(ctx->mods, delta);
+  decoys_reuse(ctx, pr, n, out);
   std::unordered_set<std::string> seen;
+  for (const Decoy& d : *out) seen.insert(d.seq);       // a generated decoy equal to a reused one is a duplicate
   ModState st;
   const uint32_t cap = attempt_cap(n);
   for (uint32_t a = 0; a < cap && out->size() < n; a++) {
@@ -691,7 +725,7 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
   for (uint8_t c : M.letter_chars) M.letters.push_back(alpha_index(c));
   M.set = true;
   ctx->mods = M;
-  ctx->index.ready = false;
+  ctx->index.ready = false; ctx->store.indexed = false;
   return MD_OK;
 }
 
@@ -784,6 +818,23 @@ void md_peptide_table_free(md_peptide_table* t) {
   std::memset(t, 0, sizeof(*t));
 }
 
+namespace {
+void index_store(md_ctx* ctx) {
+  DecoyStore& D = ctx->store; const ModSet& M = ctx->mods;
+  const size_t n = D.seq.size();
+  std::vector<std::pair<int64_t, uint32_t>> kv(n);
+  for (size_t i = 0; i < n; i++) {
+    int64_t k = D.weight[i];
+    for (int a : M.letters) k += (int64_t)D.counts[i * MD_ALPHABET_SIZE + a] * M.merged(a);
+    kv[i] = {k, (uint32_t)i};
+  }
+  std::sort(kv.begin(), kv.end());
+  D.key.resize(n); D.ord.resize(n);
+  for (size_t i = 0; i < n; i++) { D.key[i] = kv[i].first; D.ord[i] = kv[i].second; }
+  D.indexed = true;
+}
+}  // namespace
+
 int md_index_build(md_ctx* ctx) {
   if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_index_build: null ctx");
   if (!ctx->peps.ready) return fail(ctx, MD_ERR_STATE, "md_index_build: md_digest first");
@@ -800,6 +851,31 @@ int md_index_build(md_ctx* ctx) {
   ctx->index.key.resize(n); ctx->index.pep.resize(n);
   for (size_t i = 0; i < n; i++) { ctx->index.key[i] = kv[i].first; ctx->index.pep[i] = kv[i].second; }
   ctx->index.ready = true;
+  index_store(ctx);
+  return MD_OK;
+}
+
+int md_decoy_store_set(md_ctx* ctx, const uint8_t* seq, const uint64_t* off, uint64_t n) {
+  if (!ctx || (n && (!seq || !off))) return fail(ctx, MD_ERR_INVALID, "md_decoy_store_set: null argument");
+  struct E { int64_t w; uint64_t h; std::string s; };
+  std::vector<E> v; v.reserve(n);
+  for (uint64_t i = 0; i < n; i++) {
+    if (off[i + 1] < off[i]) return fail(ctx, MD_ERR_INVALID, "md_decoy_store_set: offsets not monotone");
+    const uint64_t L = off[i + 1] - off[i];
+    if (L == 0 || L > MD_MAX_PEPTIDE_LEN) return fail(ctx, MD_ERR_INVALID, "md_decoy_store_set: sequence length must be 1..60");
+    std::string q((const char*)seq + off[i], (size_t)L);
+    for (char c : q) if (alpha_index((uint8_t)c) < 0) return fail(ctx, MD_ERR_INVALID, "md_decoy_store_set: letter outside the decoy alphabet " MD_ALPHABET);
+    v.push_back({sequence_weight((const uint8_t*)q.data(), (uint32_t)L), hash64((const uint8_t*)q.data(), (uint32_t)L), q});
+  }
+  std::sort(v.begin(), v.end(), [](const E& a, const E& b) { return a.w != b.w ? a.w < b.w : a.h != b.h ? a.h < b.h : a.s < b.s; });
+  DecoyStore D;
+  for (size_t i = 0; i < v.size(); i++) {
+    if (i && v[i].s == v[i - 1].s) continue;              // UNIQUE (aa_sequence, weight)
+    D.seq.push_back(v[i].s); D.weight.push_back(v[i].w);
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++) D.counts.push_back((int16_t)std::count(v[i].s.begin(), v[i].s.end(), kAlphabet[a]));
+  }
+  ctx->store = std::move(D);
+  if (ctx->index.ready) index_store(ctx);
   return MD_OK;
 }
 

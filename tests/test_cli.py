@@ -75,6 +75,19 @@ def test_digest_and_identification_end_to_end(tmp_path):
     assert a == (tmp_path / "out" / "1.comet.params").read_text()
     rows_native = (tmp_path / "out_native" / "psms.csv").read_text().splitlines()
     assert [r.split(",")[:10] for r in rows_native] == [r.split(",")[:10] for r in rows]
+    # a later run finds the first run's decoys in its store (the `decoys` table) and reuses them before generating new ones
+    # (tasks/identification.rs:259-283); both hosts agree again
+    stored = {ln.split(",")[1] for ln in (tmp_path / "out" / "decoys.csv").read_text().splitlines()}
+    assert len(stored) > 300
+    common = ["identification", "-m", str(tmp_path / "mods.csv"), "-s", str(tmp_path / "run.mgf"), "--fasta", str(tmp_path / "db.fasta"),
+              "-n", "3", "-d", "40", "-l", "10", "-u", "10", "--seed", "3", "--stored-decoys", str(tmp_path / "out" / "decoys.csv")]
+    subprocess.check_call(CLI + common + ["-o", str(tmp_path / "out2")])
+    subprocess.check_call(_native_host() + common + ["-o", str(tmp_path / "out2_native")])
+    for name in ("1.fasta", "7.fasta", "12.fasta"):
+        text = (tmp_path / "out2" / name).read_text()
+        assert (tmp_path / "out2_native" / name).read_text() == text, name
+        decoys = [ln for ln, prev in zip(text.splitlines()[1:], text.splitlines()) if prev.startswith(">DECOY_")]
+        assert len(decoys) == 40 and set(decoys) <= stored, name
     subprocess.check_call(_native_host() + ["digest", "-i", str(tmp_path / "db.fasta"), "-c", "2", "-l", "5", "-h", "50", "-o", str(tmp_path / "dig_native")])
     assert (tmp_path / "dig_native" / "peptides.csv").read_text() == (tmp_path / "dig" / "peptides.csv").read_text()
     assert (tmp_path / "dig_native" / "peptides_proteins.csv").read_text() == (tmp_path / "dig" / "peptides_proteins.csv").read_text()

@@ -146,6 +146,40 @@ def test_decoys_random_degenerate_masses_bit_exact(gpu, cpu):
         assert len(dg["attempt"]) > 0
 
 
+@pytest.mark.parametrize("mods,nvar", [((synth.CAM,), 0), ((synth.CAM, synth.OXM), 3)])
+def test_stored_decoys_bit_exact(gpu, cpu, mods, nvar):
+    """Decoy reuse (tasks/identification.rs:259-283): same stored decoys taken, in the same order, the same remainder
+    generated -- through md_generate_decoys and through md_identify (scores of the reused decoys included)."""
+    for e in (gpu, cpu):
+        _setup(e, 300, 2, mods, nvar)
+        e.set_decoy_store([])
+    sp, _ = wl.spectra(300, 24, 2, with_ox=len(mods) > 1)
+    pre = wl.precursors_of(cpu, sp)
+    seqs = wl.decoy_strings(cpu.generate_decoys(pre, 80, maxdecoy.DECOY_REFERENCE_RANDOM, seed=21))
+    store = seqs[::3] + seqs[1::7] + ["GGGGG", "AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"]
+    try:
+        for e in (gpu, cpu):
+            e.set_decoy_store(store)
+        for n in (10, 80, 200):
+            dg = gpu.generate_decoys(pre, n, maxdecoy.DECOY_REFERENCE_RANDOM, seed=21)
+            dc = cpu.generate_decoys(pre, n, maxdecoy.DECOY_REFERENCE_RANDOM, seed=21)
+            assert_tables_equal(dg, dc)
+            assert np.any(dg["attempt"] == maxdecoy.DECOY_STORED)
+        prm = SearchParams(10, 10, n_decoys=60, decoy_mode=0, seed=21, top_k=5)
+        pg, stg, scg, offg = gpu.identify(sp, prm, want_all_scores=True)
+        pc, stc, scc, offc = cpu.identify(sp, prm, want_all_scores=True)
+        assert np.array_equal(offg, offc) and np.array_equal(scg, scc)
+        for k in pg.dtype.names:
+            if k != "_pad":
+                assert np.array_equal(pg[k], pc[k]), k
+        # the other modes ignore the store
+        de = gpu.generate_decoys(pre[:4], 20, maxdecoy.DECOY_EXHAUSTIVE, seed=0)
+        assert not np.any(de["attempt"] == maxdecoy.DECOY_STORED)
+    finally:
+        for e in (gpu, cpu):
+            e.set_decoy_store([])
+
+
 def test_decoys_permute_bit_exact(gpu, cpu):
     for e in (gpu, cpu):
         _setup(e, 300, 2, (synth.CAM,), 0)

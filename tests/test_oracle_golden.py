@@ -219,6 +219,57 @@ def test_random_decoy_properties(cpu, mods, nvar):
     assert wl.decoy_strings(d4) != seqs
 
 
+@pytest.mark.parametrize("mods,nvar", [((synth.CAM,), 0), ((synth.CAM, synth.OXM), 3)])
+def test_stored_decoys_are_reused_before_new_ones(cpu, mods, nvar):
+    """tasks/identification.rs:259-283: decoys of the `decoys` table that the target queries retrieve and the ModifiedPeptide
+    filter accepts are taken first; only the remainder is generated.  Checked against the literal query-by-query Python
+    execution (pyref.candidates_sql) over the stored sequences."""
+    cpu.digest(list(wl.proteins(150)), 2, 5, 50)
+    cpu.set_modifications(list(mods), nvar)
+    cpu.index_build()
+    cpu.set_decoy_store([])
+    sp, _ = wl.spectra(150, 10, 2, with_ox=len(mods) > 1)
+    pre = wl.precursors_of(cpu, sp)
+    fresh = cpu.generate_decoys(pre, 60, maxdecoy.DECOY_REFERENCE_RANDOM, seed=9)
+    seqs = wl.decoy_strings(fresh)
+    assert not np.any(fresh["attempt"] == maxdecoy.DECOY_STORED)
+    # the store: every second decoy of the first run, twice (duplicates are dropped), plus sequences that match nothing
+    store = seqs[::2] + seqs[::2] + ["GGGGG", "WWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWW"]
+    cpu.set_decoy_store(store)
+    pm = pyref.Mods(mods, nvar)
+    uniq = sorted(set(store))
+    table = [(q, pyref.sequence_weight(q), pyref.counts21(q)) for q in uniq]
+    got = cpu.generate_decoys(pre, 60, maxdecoy.DECOY_REFERENCE_RANDOM, seed=9)
+    gs = wl.decoy_strings(got)
+    for s, (P, lo, hi, z, sid) in enumerate(pre):
+        a, b = int(got["off"][s]), int(got["off"][s + 1])
+        mine, att = gs[a:b], got["attempt"][a:b]
+        assert len(set(mine)) == len(mine)
+        stored = [i for i in range(b - a) if att[i] == maxdecoy.DECOY_STORED]
+        assert stored == list(range(len(stored)))                          # stored decoys come first
+        want = {uniq[i]: wm for i, wm in pyref.candidates_sql(pm, table, P, lo, hi).items()}
+        assert len(stored) == min(60, len(want))
+        for i in stored:
+            assert mine[i] in want
+            assert (int(got["mod_weight"][a + i]), int(got["var_mask"][a + i])) == want[mine[i]]
+            assert int(got["weight"][a + i]) == pyref.sequence_weight(mine[i])
+        if len(want) <= 60:
+            assert {mine[i] for i in stored} == set(want)
+        # the generated remainder: the attempts of the first run in order, minus the sequences already taken from the store
+        fa, fb = int(fresh["off"][s]), int(fresh["off"][s + 1])
+        rest = [q for q in seqs[fa:fb] if q not in set(mine[:len(stored)])]
+        assert mine[len(stored):] == rest[:len(mine) - len(stored)]
+    assert np.any(got["attempt"] == maxdecoy.DECOY_STORED)
+    # changing the modifications re-indexes the store; clearing it restores the first run
+    cpu.set_decoy_store([])
+    again = cpu.generate_decoys(pre, 60, maxdecoy.DECOY_REFERENCE_RANDOM, seed=9)
+    assert all(np.array_equal(fresh[k], again[k]) for k in fresh)
+    with pytest.raises(maxdecoy.MaxDecoyError):
+        cpu.set_decoy_store(["PEPTIDEB"])                                  # B is not in the decoy alphabet
+    with pytest.raises(maxdecoy.MaxDecoyError):
+        cpu.set_decoy_store([""])
+
+
 def test_permuted_target_decoys(cpu):
     """vary_targets (decoy_generator.rs:265-296): a shuffled target, same composition, not a peptide."""
     cpu.digest(list(wl.proteins(150)), 2, 5, 50)
