@@ -62,6 +62,7 @@ extern "C" {
     pub fn md_candidates(ctx: *mut md_ctx, p: *const md_precursor, n: u32, out: *mut md_candidate_table) -> c_int;
     pub fn md_candidate_table_free(t: *mut md_candidate_table);
     pub fn md_decoy_store_set(ctx: *mut md_ctx, seq: *const u8, seq_off: *const u64, n: u64) -> c_int;
+    pub fn md_set_variable_mode(ctx: *mut md_ctx, mode: c_int) -> c_int;
     pub fn md_generate_decoys(ctx: *mut md_ctx, p: *const md_precursor, n_spectra: u32, n_per_spectrum: u32, mode: c_int,
                               seed: u64, out: *mut md_decoy_table) -> c_int;
     pub fn md_decoy_table_free(t: *mut md_decoy_table);

@@ -156,6 +156,23 @@ MD_API int md_window_search(md_ctx* ctx, const int64_t* lo, const int64_t* hi, u
 MD_API int md_index_export(md_ctx* ctx, uint64_t begin, uint64_t count, uint64_t* peptide_id,
                            int64_t* key);
 
+/* How a target peptide's variable modifications are placed (md_candidates / md_identify*; decoys always follow the
+ * reference's repair loop).
+ *  MD_VARMOD_REFERENCE: the reference's procedure (tasks/identification.rs:242-257 +
+ *    ModifiedPeptide::try_variable_modifications, models/peptides/modified_peptide.rs:512-543): the SQL fan-out only
+ *    retrieves peptides whose FULLY modified weight W* lies in the window, and the first placement that hits wins, so a
+ *    peptide is found with all of its variable-modifiable residues modified or not at all.
+ *  MD_VARMOD_EXPANDED (not in the reference): every (peptide, set S of variable-modifiable residues,
+ *    |S| <= max_variable_mods) whose weight incl. fixed modifications + the deltas of S lies in the window is a candidate
+ *    of its own -- partial occupancy is found, and every placement is scored.  A residue whose letter also has a fixed
+ *    modification is not variable-modifiable (modified_peptide.rs:355,532).  Candidate order per spectrum: count
+ *    vectors (k_a over the variable letters in alphabetical order, sum <= max_variable_mods, ascending as mixed-radix
+ *    numbers with the last letter fastest), then ascending fixed-modification weight (ties: index order), then
+ *    placements with the last letter fastest, each letter's subsets in NChooseK order (utility/combinations/n_choose_k.rs:12-49).
+ * Changing the mode invalidates the index (md_index_build again). */
+typedef enum md_varmod_mode { MD_VARMOD_REFERENCE = 0, MD_VARMOD_EXPANDED = 1 } md_varmod_mode;
+MD_API int md_set_variable_mode(md_ctx* ctx, int mode);
+
 typedef struct md_precursor {
   int64_t mass;         /* P  */
   int64_t lo;           /* lower tolerance limit */

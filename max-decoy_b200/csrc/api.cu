@@ -253,6 +253,13 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
   });
 }
 
+int md_set_variable_mode(md_ctx* ctx, int mode) {
+  if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_set_variable_mode: null ctx");
+  if (mode != MD_VARMOD_REFERENCE && mode != MD_VARMOD_EXPANDED) return fail(ctx, MD_ERR_INVALID, "md_set_variable_mode: unknown mode");
+  if (mode != ctx->var_mode) { ctx->var_mode = mode; ctx->index.ready = false; ctx->dindex.ready = false; }
+  return MD_OK;
+}
+
 int md_substitution_map(md_ctx* ctx, int64_t* out) {
   if (!ctx || !out) return fail(ctx, MD_ERR_INVALID, "md_substitution_map: null argument");
   ModTables M = ctx->mods;

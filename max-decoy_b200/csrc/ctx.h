@@ -33,6 +33,9 @@ struct MassIndex {
   DevBuf<uint64_t> varpos;  // positions whose letter has a variable modification
   DevBuf<uint64_t> desc;    // score-row descriptor: row offset/16 | len << 40
   DevBuf<uint8_t> rows;     // residue codes, 16-byte padded rows, index order
+  // MD_VARMOD_EXPANDED: the same entries ordered by wfix (stable over index order)
+  DevBuf<int64_t> fkey;     // wfix, ascending
+  DevBuf<uint32_t> fent;    // index entry of that key
   uint64_t row_bytes = 0;
   int64_t min_key = 0, max_key = 0;
 };
@@ -65,6 +68,7 @@ struct IdentifyWorkspace {
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
   DevBuf<uint64_t> t_size; DevBuf<int16_t> t_K; DevBuf<uint32_t> t_flag, t_pos; DevBuf<int> t_ovf, t_unsorted;
   DevBuf<uint32_t> t_list, t_off, t_base, t_queue, t_spill;
+  DevBuf<md_precursor> t_win;        // MD_VARMOD_EXPANDED: shifted windows, one per (spectrum, count vector)
   // exhaustive mode
   DevBuf<int32_t> ex_comp; DevBuf<uint64_t> ex_cum; DevBuf<uint32_t> ex_ncomp;
 };
@@ -87,6 +91,7 @@ struct md_ctx {
   // modifications
   bool mods_set = false;
   ModTables mods;          // host copy (passed to kernels by value)
+  int var_mode = 0;        // md_varmod_mode
   // stores
   PeptideStore peps;
   MassIndex index;

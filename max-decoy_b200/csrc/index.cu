@@ -203,6 +203,117 @@ __global__ void k_stored_counts(const uint64_t* __restrict__ flat_off, const uin
   dec_count[s] = min(n_per, pos[flat_off[s + 1]] - pos[flat_off[s]]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// MD_VARMOD_EXPANDED: every placement of up to nvar variable modifications is a candidate of its own
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxVarLetters = 6, kMaxVarCombos = 96;
+struct VarCombos {
+  int n_letters, n_combos;
+  uint8_t code[kMaxVarLetters];              // residue codes of the variable-modifiable letters, ascending
+  int64_t delta[kMaxVarLetters];
+  uint8_t k[kMaxVarCombos][kMaxVarLetters];  // count vectors, sum <= nvar
+  int64_t shift[kMaxVarCombos];              // sum k_a * delta_a
+};
+
+__global__ void k_iota(uint32_t* __restrict__ v, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
+
+// window (s, q) on the fixed-modification weight: [lo - shift_q, hi - shift_q]
+__global__ void k_shifted_windows(const md_precursor* __restrict__ prec, uint32_t n, const __grid_constant__ VarCombos V, md_precursor* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint32_t)V.n_combos) return;
+  const uint32_t s = t / V.n_combos, q = t % V.n_combos;
+  md_precursor p = prec[s];
+  p.lo -= V.shift[q]; p.hi -= V.shift[q];
+  out[t] = p;
+}
+
+__device__ __forceinline__ uint64_t binom_capped(uint32_t n, uint32_t k) {   // C(n, k), n <= 60; capped at 2^32
+  if (k > n) return 0;
+  uint64_t r = 1;
+  for (uint32_t i = 1; i <= k; i++) { r = r * (n - k + i) / i; if (r > 0xFFFFFFFFull) return 0x100000000ull; }
+  return r;
+}
+
+// placements of window entry e: prod_a C(count_a, k_a)
+__global__ void k_expand_count(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, uint32_t n_win, uint64_t n_entries,
+                               const uint32_t* __restrict__ fent, const uint64_t* __restrict__ idx_desc, const uint8_t* __restrict__ rows,
+                               const __grid_constant__ VarCombos V, uint32_t* __restrict__ count, int* __restrict__ overflow) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  uint32_t lo = 0, hi = n_win;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
+  const uint32_t q = lo % V.n_combos;
+  const uint32_t ent = fent[rbegin[lo] + (e - flat_off[lo])];
+  const uint64_t d = idx_desc[ent];
+  const uint8_t* r = rows + (d & 0xFFFFFFFFFFull) * 16;
+  const uint32_t L = (uint32_t)(d >> 40) & 0xFF;
+  uint64_t total = 1;
+  for (int a = 0; a < V.n_letters; a++) {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < L; i++) c += r[i] == V.code[a];
+    total *= binom_capped(c, V.k[q][a]);
+    if (total > 0xFFFFFull) { *overflow = 1; total = 0; break; }   // more than 2^20 placements of one peptide
+  }
+  count[e] = (uint32_t)total;
+}
+
+// the count-th .. placements of entry e, odometer over the letters (last letter fastest), each letter's subsets in NChooseK order
+__global__ void k_expand_scatter(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, uint32_t n_win, uint64_t n_entries,
+                                 const uint32_t* __restrict__ count, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ fent,
+                                 const int64_t* __restrict__ fkey, const uint32_t* __restrict__ idx_pep, const uint64_t* __restrict__ idx_desc,
+                                 const uint8_t* __restrict__ rows, const __grid_constant__ VarCombos V, uint64_t* __restrict__ cand_desc,
+                                 uint64_t* __restrict__ cand_mask, int64_t* __restrict__ cand_w, uint32_t* __restrict__ cand_pep) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries || !count[e]) return;
+  uint32_t lo = 0, hi = n_win;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
+  const uint32_t q = lo % V.n_combos;
+  const uint64_t fi = rbegin[lo] + (e - flat_off[lo]);
+  const uint32_t ent = fent[fi];
+  const uint64_t d = idx_desc[ent];
+  const uint8_t* r = rows + (d & 0xFFFFFFFFFFull) * 16;
+  const uint32_t L = (uint32_t)(d >> 40) & 0xFF;
+  const int64_t w = fkey[fi] + V.shift[q];
+  const uint32_t pep = idx_pep[ent];
+  uint64_t allpos[kMaxVarLetters], cm[kMaxVarLetters], first[kMaxVarLetters];
+  uint32_t dcount[kMaxVarLetters];
+  for (int a = 0; a < V.n_letters; a++) {
+    uint64_t m = 0;
+    for (uint32_t i = 0; i < L; i++) if (r[i] == V.code[a]) m |= 1ULL << i;
+    allpos[a] = m; dcount[a] = (uint32_t)__popcll(m);
+    const uint32_t k = V.k[q][a];
+    first[a] = k == 0 ? 0ULL : (((1ULL << dcount[a]) - 1) ^ ((1ULL << (dcount[a] - k)) - 1));   // 2^d - 2^(d-k)
+    cm[a] = first[a];
+  }
+  uint32_t o = pos[e];
+  for (uint32_t j = 0; j < count[e]; j++, o++) {
+    uint64_t mask = 0;
+    for (int a = 0; a < V.n_letters; a++) {
+      // compressed bit (d-1-b) <-> b-th position (ascending) of allpos
+      uint64_t rest = allpos[a];
+      for (uint32_t b = 0; b < dcount[a]; b++) {
+        const uint64_t bit = rest & (~rest + 1); rest &= rest - 1;
+        if ((cm[a] >> (dcount[a] - 1 - b)) & 1) mask |= bit;
+      }
+    }
+    cand_desc[o] = d; cand_mask[o] = mask; cand_w[o] = w; cand_pep[o] = pep;
+    // next placement
+    for (int a = V.n_letters - 1; a >= 0; a--) {
+      if (V.k[q][a] == 0) continue;
+      const uint64_t nx = md_prev_combination(cm[a]);
+      if (nx) { cm[a] = nx; break; }
+      cm[a] = first[a];
+    }
+  }
+}
+
+__global__ void k_cand_offsets_expanded(const uint64_t* __restrict__ flat_off, const uint32_t* __restrict__ pos, uint32_t n_spec, uint32_t n_combos,
+                                        uint64_t* __restrict__ cand_off) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_spec) return;
+  cand_off[s] = pos[flat_off[(uint64_t)s * n_combos]];
+}
+
 __global__ void k_cand_offsets(const uint64_t* __restrict__ flat_off, const uint32_t* __restrict__ pos, uint32_t n_spec, uint64_t* __restrict__ cand_off) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > n_spec) return;
@@ -232,6 +343,13 @@ static void index_build_for(md_ctx* ctx, PeptideStore& P, MassIndex& X) {
   MD_CUDA(cudaMemcpyAsync(&mm[1], X.key.p + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   X.min_key = mm[0]; X.max_key = mm[1];
+  if (ctx->var_mode == MD_VARMOD_EXPANDED && &X == &ctx->index) {   // second order of the same entries: by fixed-modification weight
+    DevBuf<uint32_t> d_iota; d_iota.need(n);
+    X.fkey.need(n); X.fent.need(n);
+    MD_LAUNCH(ctx, k_iota, blocks(n), 256, 0, d_iota.p, n);
+    cubx_sort_pairs(ctx, X.wfix.p, X.fkey.p, d_iota.p, X.fent.p, n);  // stable: ties keep index order
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   X.ready = true;
 }
 
@@ -286,10 +404,68 @@ static uint64_t filter_windows(md_ctx* ctx, const MassIndex& X, const int16_t* c
   return E;
 }
 
+// MD_VARMOD_EXPANDED: for every count vector (k_a) over the variable letters, the window [lo - sum k_a d_a, hi - sum k_a d_a]
+// on the fixed-modification weight; every entry with count_a >= k_a contributes prod_a C(count_a, k_a) placements.
+static uint64_t candidates_expanded_dev(md_ctx* ctx, uint32_t n) {
+  IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->index; const ModTables& M = ctx->mods;
+  VarCombos V;
+  memset(&V, 0, sizeof(V));
+  for (int ch = 'A'; ch <= 'Z'; ch++) {
+    const uint32_t code = md_code_of((uint8_t)ch);
+    if (!M.has_var[code] || M.has_fix[code]) continue;
+    MD_REQUIRE(V.n_letters < kMaxVarLetters, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: more than 6 variable letters");
+    V.code[V.n_letters] = (uint8_t)code; V.delta[V.n_letters] = M.var[code]; V.n_letters++;
+  }
+  {  // count vectors in ascending mixed-radix order, last letter fastest
+    std::vector<uint8_t> k(kMaxVarLetters, 0);
+    for (;;) {
+      uint32_t sum = 0; int64_t sh = 0;
+      for (int a = 0; a < V.n_letters; a++) { sum += k[a]; sh += (int64_t)k[a] * V.delta[a]; }
+      if (sum <= M.nvar) {
+        MD_REQUIRE(V.n_combos < kMaxVarCombos, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: more than 96 count vectors");
+        for (int a = 0; a < V.n_letters; a++) V.k[V.n_combos][a] = k[a];
+        V.shift[V.n_combos++] = sh;
+      }
+      int a = V.n_letters - 1;
+      while (a >= 0 && k[a] >= M.nvar) { k[a] = 0; a--; }
+      if (a < 0) break;
+      k[a]++;
+    }
+  }
+  const uint32_t Q = (uint32_t)V.n_combos, nw = n * Q;
+  MD_REQUIRE((uint64_t)n * Q < 0x7FFFFFFFull, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: too many windows in one batch");
+  W.rbegin.need(nw + 1); W.rend.need(nw + 1); W.flat_off.need(nw + 2); W.cand_off.need(n + 2);
+  DevBuf<md_precursor>& d_win = W.t_win; d_win.need(nw + 1);
+  MD_LAUNCH(ctx, k_shifted_windows, blocks(nw), 256, 0, W.prec.p, n, V, d_win.p);
+  MD_LAUNCH(ctx, k_window_search, blocks((uint64_t)nw * 32, 128), 128, 0, X.fkey.p, X.n, d_win.p, nw, W.rbegin.p, W.rend.p);
+  DevBuf<uint64_t>& d_size = W.t_size; d_size.need(nw + 1);
+  MD_LAUNCH(ctx, k_range_sizes, blocks(nw + 1), 256, 0, W.rbegin.p, W.rend.p, nw, d_size.p);
+  cubx_exclusive_sum(ctx, d_size.p, W.flat_off.p, nw + 1);
+  const uint64_t E = d2h_scalar(ctx, W.flat_off.p + nw);
+  MD_REQUIRE(E < 0x7FFFFF00ull, MD_ERR_UNSUPPORTED, "candidate windows of one batch exceed 2^31 index entries; use smaller batches");
+  DevBuf<uint32_t>& d_cnt = W.t_flag; DevBuf<uint32_t>& d_pos = W.t_pos; DevBuf<int>& d_ovf = W.t_ovf;
+  d_cnt.need(E + 1); d_pos.need(E + 1); d_ovf.need(1);
+  MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
+  MD_CUDA(cudaMemsetAsync(d_cnt.p + E, 0, sizeof(uint32_t), ctx->stream));
+  if (E) MD_LAUNCH(ctx, k_expand_count, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, nw, E, X.fent.p, X.desc.p, X.rows.p, V, d_cnt.p, d_ovf.p);
+  cubx_exclusive_sum(ctx, d_cnt.p, d_pos.p, E + 1);
+  const uint32_t total = d2h_scalar(ctx, d_pos.p + E);
+  const int ovf = d2h_scalar(ctx, d_ovf.p);
+  MD_REQUIRE(!ovf, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: more than 2^20 placements for one peptide");
+  MD_REQUIRE(total < 0x7FFFFF00u, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: more than 2^31 candidates in one batch");
+  W.cand_desc.need(total + 1); W.cand_mask.need(total + 1); W.cand_w.need(total + 1); W.cand_pep.need(total + 1);
+  if (E) MD_LAUNCH(ctx, k_expand_scatter, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, nw, E, d_cnt.p, d_pos.p, X.fent.p, X.fkey.p, X.pep.p, X.desc.p, X.rows.p, V,
+                   W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
+  MD_LAUNCH(ctx, k_cand_offsets_expanded, blocks(n + 1), 256, 0, W.flat_off.p, d_pos.p, n, Q, W.cand_off.p);
+  ctx->mark("  expanded");
+  return total;
+}
+
 uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->index;
   W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2); W.cand_off.need(n + 2);
   if (!n) return 0;
+  if (ctx->var_mode == MD_VARMOD_EXPANDED) return candidates_expanded_dev(ctx, n);
   uint32_t total = 0;
   const uint64_t E = filter_windows(ctx, X, ctx->peps.counts.p, n, &total);
   W.cand_desc.need(total + 1); W.cand_mask.need(total + 1); W.cand_w.need(total + 1); W.cand_pep.need(total + 1);

@@ -410,7 +410,7 @@ int cmd_identification(int argc, char** argv) {
                                  {"d", "number-of-decoys", "decoys"}, {"l", "lower-mass-tolerance", "lower"}, {"u", "upper-mass-tolerance", "upper"},
                                  {"", "fragmentation-tolerance", "fragtol"}, {"t", "thread-count", "threads"}, {"", "max-time-for-decoy-generation", "maxtime"},
                                  {"r", "comet-revision", "rev"}, {"", "fasta", "fasta"}, {"c", "number-of-missed-cleavages", "mc"}, {"o", "out", "out"},
-                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}, {"", "stored-decoys", "stored"}});
+                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}, {"", "stored-decoys", "stored"}, {"", "variable-mode", "varmode"}});
   if (!a.has("mods") || !a.has("spectra") || !a.has("fasta")) die("identification: -m, -s and --fasta are required");
   const std::vector<Mod> mods = read_mods(a.get("mods"));
   const Fasta f = read_fasta(a.get("fasta"));
@@ -420,6 +420,11 @@ int cmd_identification(int argc, char** argv) {
   digest_into(ctx, f, (uint32_t)a.num("mc", 2), 5, 50);
   auto am = to_abi(mods);
   check(ctx, md_set_modifications(ctx, am.data(), (uint32_t)am.size(), (uint32_t)nvar), "md_set_modifications");
+  {
+    const std::string vm = a.get("varmode", "reference");
+    if (vm != "reference" && vm != "expanded") die("identification: --variable-mode must be reference or expanded");
+    check(ctx, md_set_variable_mode(ctx, vm == "expanded" ? MD_VARMOD_EXPANDED : MD_VARMOD_REFERENCE), "md_set_variable_mode");
+  }
   if (a.has("stored")) {
     // the `decoys` table as CSV (id, aa_sequence, ...) or one sequence per line: reused before new decoys are generated
     // (tasks/identification.rs:259-283)

@@ -74,6 +74,7 @@ def cmd_identification(args):
     eng = _engine(args)
     eng.digest(seqs, args.missed, args.min_len, args.max_len)
     eng.set_modifications(mods, args.nvar)
+    eng.set_variable_mode(maxdecoy.VARMOD_EXPANDED if args.variable_mode == "expanded" else maxdecoy.VARMOD_REFERENCE)
     if args.stored_decoys:
         eng.set_decoy_store(_read_stored_decoys(args.stored_decoys))
     eng.index_build()
@@ -194,6 +195,8 @@ def main(argv=None):
     p.add_argument("--minimum-peptide_length", dest="min_len", type=int, default=5)
     p.add_argument("--maximum-peptide_length", dest="max_len", type=int, default=50)
     p.add_argument("--top-k", type=int, default=5)
+    p.add_argument("--variable-mode", choices=["reference", "expanded"], default="reference",
+                   help="reference: all-or-first-hit placement like the reference; expanded: every placement of <= n variable modifications")
     p.add_argument("--stored-decoys", default="", help="CSV of the `decoys` table (or one sequence per line): reused before new decoys are generated")
     p.add_argument("-o", "--out", default="identification_out")
     p.set_defaults(fn=cmd_identification)

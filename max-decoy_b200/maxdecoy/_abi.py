@@ -18,6 +18,8 @@ STATUS_NAMES = {0: "MD_OK", -1: "MD_ERR_INVALID", -2: "MD_ERR_STATE", -3: "MD_ER
 DECOY_REFERENCE_RANDOM = 0
 DECOY_EXHAUSTIVE = 1
 DECOY_PERMUTE_TARGET = 2
+VARMOD_REFERENCE = 0   # md_varmod_mode
+VARMOD_EXPANDED = 1
 DECOY_STORED = 0xFFFFFFFF   # `attempt` of a decoy taken from the store (md_decoy_store_set)
 
 u8p = C.POINTER(C.c_uint8)
@@ -119,6 +121,7 @@ SYMBOLS = {
     "md_sequence_weight": (C.c_int64, [C.c_char_p, C.c_uint32]),
     "md_precursor_window": (C.c_int, [C.c_double, C.c_uint32, C.c_int64, C.c_int64, i64p, i64p, i64p]),
     "md_set_modifications": (C.c_int, [ctx_p, C.POINTER(md_modification), C.c_uint32, C.c_uint32]),
+    "md_set_variable_mode": (C.c_int, [ctx_p, C.c_int]),
     "md_substitution_map": (C.c_int, [ctx_p, i64p]),
     "md_digest": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(md_digest_params), u64p]),
     "md_peptides_export": (C.c_int, [ctx_p, C.POINTER(md_peptide_table)]),

@@ -321,6 +321,11 @@ class Engine:
             self.lib.md_decoy_table_free(C.byref(t))
         return out
 
+    def set_variable_mode(self, mode):
+        """VARMOD_REFERENCE: the reference's all-or-first-hit placement (modified_peptide.rs:512-543);
+        VARMOD_EXPANDED: every placement of up to nvar variable modifications is a candidate.  `index_build` afterwards."""
+        self._ck(self.lib.md_set_variable_mode(self.h, int(mode)))
+
     def set_decoy_store(self, sequences):
         """The `decoys` table: decoys persisted by earlier runs, reused before new ones are generated
         (tasks/identification.rs:259-283; models/peptides/decoy.rs:118-153).  An empty list clears the store."""

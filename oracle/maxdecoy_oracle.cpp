@@ -180,6 +180,8 @@ struct md_ctx {
   Peptides peps;
   Index index;
   DecoyStore store;
+  int var_mode = 0;                                   // md_varmod_mode
+  std::vector<std::pair<int64_t, uint32_t>> fixed;    // MD_VARMOD_EXPANDED: (weight incl. fixed mods, index entry), ascending
   std::vector<std::vector<Decoy>> last_decoys;
   bool have_last_decoys = false;
 };
@@ -305,7 +307,71 @@ bool fanout_admits(const ModSet& M, const int16_t* counts, int64_t P, int64_t lo
   return true;
 }
 
+// MD_VARMOD_EXPANDED (builder-defined): every placement of up to nvar variable modifications whose
+// weight lies in the window is a candidate.  Count vectors over the variable letters (alphabetical, last letter
+// fastest), per vector the window on the fixed-modification weight, per peptide the placements (last letter fastest,
+// each letter's subsets in NChooseK order, n_choose_k.rs:12-49).
+void candidates_expanded(const md_ctx* ctx, const md_precursor& pr, std::vector<Candidate>* out) {
+  const ModSet& M = ctx->mods; const Index& X = ctx->index; const Peptides& Pp = ctx->peps;
+  std::vector<int> letters;                                // variable-modifiable letters by character
+  {
+    std::vector<uint8_t> chars;
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++) if (M.has_var[a] && !M.has_fix[a]) chars.push_back((uint8_t)kAlphabet[a]);
+    std::sort(chars.begin(), chars.end());
+    for (uint8_t c : chars) letters.push_back(alpha_index(c));
+  }
+  const size_t nl = letters.size();
+  std::vector<uint32_t> k(nl, 0);
+  for (;;) {
+    uint32_t sum = 0; int64_t shift = 0;
+    for (size_t a = 0; a < nl; a++) { sum += k[a]; shift += (int64_t)k[a] * M.var[letters[a]]; }
+    if (sum <= M.nvar) {
+      const int64_t lo = pr.lo - shift, hi = pr.hi - shift;
+      auto b = std::lower_bound(ctx->fixed.begin(), ctx->fixed.end(), std::make_pair(lo, (uint32_t)0));
+      for (auto it = b; it != ctx->fixed.end() && it->first <= hi; ++it) {
+        const uint32_t p = X.pep[it->second];
+        const std::string& q = Pp.seq[p];
+        std::vector<std::vector<uint32_t>> pos(nl);
+        bool ok = true;
+        for (size_t a = 0; a < nl; a++) {
+          for (uint32_t i = 0; i < q.size(); i++) if (q[i] == kAlphabet[letters[a]]) pos[a].push_back(i);
+          if (pos[a].size() < k[a]) ok = false;
+        }
+        if (!ok) continue;
+        // odometer over the letters' k-subsets: compressed masks, MSB <-> first position, descending
+        std::vector<uint64_t> cm(nl), first(nl);
+        for (size_t a = 0; a < nl; a++) {
+          const uint32_t d = (uint32_t)pos[a].size();
+          first[a] = k[a] == 0 ? 0 : (((1ULL << d) - 1) ^ ((1ULL << (d - k[a])) - 1));
+          cm[a] = first[a];
+        }
+        for (;;) {
+          uint64_t mask = 0;
+          for (size_t a = 0; a < nl; a++) {
+            const uint32_t d = (uint32_t)pos[a].size();
+            for (uint32_t bix = 0; bix < d; bix++) if ((cm[a] >> (d - 1 - bix)) & 1) mask |= 1ULL << pos[a][bix];
+          }
+          out->push_back({p, mask, it->first + shift});
+          int a = (int)nl - 1;
+          for (; a >= 0; a--) {
+            if (k[a] == 0) continue;
+            const uint64_t nx = prev_combination(cm[a]);
+            if (nx) { cm[a] = nx; break; }
+            cm[a] = first[a];
+          }
+          if (a < 0) break;
+        }
+      }
+    }
+    int a = (int)nl - 1;
+    while (a >= 0 && k[a] >= M.nvar) { k[a] = 0; a--; }
+    if (a < 0) break;
+    k[a]++;
+  }
+}
+
 void candidates_for(const md_ctx* ctx, const md_precursor& pr, std::vector<Candidate>* out) {
+  if (ctx->var_mode == MD_VARMOD_EXPANDED) { candidates_expanded(ctx, pr, out); return; }
   const ModSet& M = ctx->mods; const Index& X = ctx->index; const Peptides& Pp = ctx->peps;
   size_t b = std::lower_bound(X.key.begin(), X.key.end(), pr.lo) - X.key.begin();
   size_t e = std::upper_bound(X.key.begin(), X.key.end(), pr.hi) - X.key.begin();
@@ -850,8 +916,26 @@ int md_index_build(md_ctx* ctx) {
   std::sort(kv.begin(), kv.end());
   ctx->index.key.resize(n); ctx->index.pep.resize(n);
   for (size_t i = 0; i < n; i++) { ctx->index.key[i] = kv[i].first; ctx->index.pep[i] = kv[i].second; }
+  ctx->fixed.clear();
+  if (ctx->var_mode == MD_VARMOD_EXPANDED) {
+    ctx->fixed.resize(n);
+    for (size_t i = 0; i < n; i++) {
+      const uint32_t p = ctx->index.pep[i];
+      int64_t w = P.weight[p];
+      for (int a = 0; a < MD_ALPHABET_SIZE; a++) if (M.has_fix[a]) w += (int64_t)P.counts[(size_t)p * MD_ALPHABET_SIZE + a] * M.fix[a];
+      ctx->fixed[i] = {w, (uint32_t)i};
+    }
+    std::sort(ctx->fixed.begin(), ctx->fixed.end());
+  }
   ctx->index.ready = true;
   index_store(ctx);
+  return MD_OK;
+}
+
+int md_set_variable_mode(md_ctx* ctx, int mode) {
+  if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_set_variable_mode: null ctx");
+  if (mode != MD_VARMOD_REFERENCE && mode != MD_VARMOD_EXPANDED) return fail(ctx, MD_ERR_INVALID, "md_set_variable_mode: unknown mode");
+  if (mode != ctx->var_mode) { ctx->var_mode = mode; ctx->index.ready = false; ctx->store.indexed = false; }
   return MD_OK;
 }
 

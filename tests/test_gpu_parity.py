@@ -180,6 +180,63 @@ def test_stored_decoys_bit_exact(gpu, cpu, mods, nvar):
             e.set_decoy_store([])
 
 
+def test_expanded_variable_mode_bit_exact(gpu, cpu):
+    """MD_VARMOD_EXPANDED: the same candidates in the same order (count vectors, fixed-weight order, placements in NChooseK
+    order), the same scores and PSM rows -- with one and with two variable letters, narrow and wide windows."""
+    from maxdecoy import Modification
+    var_s = Modification("x:21", "Phospho", "A", False, "S", 79.966331)
+    try:
+        for mods, nvar in (((synth.CAM, synth.OXM), 3), ((synth.CAM, synth.OXM, var_s), 2)):
+            for e in (gpu, cpu):
+                e.digest(list(wl.proteins(300)), 2, 5, 50)
+                e.set_modifications(list(mods), nvar)
+                e.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
+                e.index_build()
+            sp, _ = wl.spectra(300, 32, 2, with_ox=True)
+            pre = wl.precursors_of(cpu, sp)
+            wide = [(p[0], p[0] - 30_000_000, p[0] + 30_000_000, p[3], p[4]) for p in pre[:12]]
+            for prs in (pre, wide):
+                cg, cc = gpu.candidates(prs), cpu.candidates(prs)
+                assert_tables_equal(cg, cc)
+            assert len(cg["peptide_id"]) > 1000
+            prm = SearchParams(10, 10, n_decoys=40, decoy_mode=0, seed=5, top_k=5)
+            pg, stg, scg, offg = gpu.identify(sp, prm, want_all_scores=True)
+            pc, stc, scc, offc = cpu.identify(sp, prm, want_all_scores=True)
+            assert np.array_equal(offg, offc) and np.array_equal(scg, scc)
+            for k in pg.dtype.names:
+                if k != "_pad":
+                    assert np.array_equal(pg[k], pc[k]), k
+    finally:
+        for e in (gpu, cpu):
+            e.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+
+
+def test_expanded_variable_mode_finds_partially_modified_peptides(gpu):
+    """What the mode is for: a peptide with two methionines of which ONE is oxidised is invisible
+    to the reference's lookup (only the fully modified weight is queried) and is identified, placement included, in
+    expanded mode."""
+    prots = list(wl.proteins(400))
+    sp, truth = synth.synthetic_spectra(prots, 400, 2, mods=(synth.CAM, synth.OXM), seed=11, frac_random=0.0, ox_prob=0.6, max_var=1)
+    partial = [i for i, (q, m) in enumerate(truth) if m and q.count("M") >= 2]
+    assert len(partial) >= 8
+    won = {}
+    try:
+        for mode in (maxdecoy.VARMOD_REFERENCE, maxdecoy.VARMOD_EXPANDED):
+            gpu.digest(prots, 2, 5, 50)
+            gpu.set_modifications([synth.CAM, synth.OXM], 3)
+            gpu.set_variable_mode(mode)
+            gpu.index_build()
+            seqs = gpu.sequences_of(gpu.peptides())
+            psms, _ = gpu.identify(sp, SearchParams(10, 10, n_decoys=50, seed=1, top_k=1))
+            top = psms[:, 0]
+            won[mode] = sum(1 for i in partial if top["rank"][i] and not top["is_decoy"][i] and seqs[int(top["candidate"][i]) - 1] == truth[i][0]
+                            and int(top["var_mask"][i]) == truth[i][1])
+    finally:
+        gpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+    assert won[maxdecoy.VARMOD_REFERENCE] == 0
+    assert won[maxdecoy.VARMOD_EXPANDED] >= 0.7 * len(partial)
+
+
 def test_decoys_permute_bit_exact(gpu, cpu):
     for e in (gpu, cpu):
         _setup(e, 300, 2, (synth.CAM,), 0)

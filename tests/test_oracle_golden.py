@@ -144,6 +144,63 @@ def test_candidates_equal_literal_sql_fanout(cpu, mods, nvar):
     assert n_found > 0
 
 
+def test_expanded_variable_mode_equals_bruteforce(cpu):
+    """MD_VARMOD_EXPANDED: every subset of up to nvar variable-modifiable residues whose weight lies in
+    the window is a candidate -- against a brute force over all peptides and all subsets; and the reference mode's
+    candidates are a subset of it wherever the reference finds anything (same peptide, same placement, same weight)."""
+    import itertools
+    from maxdecoy import Modification
+    var_s = Modification("x:21", "Phospho", "A", False, "S", 79.966331)
+    mods, nvar = (synth.CAM, synth.OXM, var_s), 2
+    prots = list(wl.proteins(120))
+    cpu.digest(prots, 2, 5, 50)
+    cpu.set_modifications(list(mods), nvar)
+    cpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+    cpu.index_build()
+    seqs = cpu.sequences_of(cpu.peptides())
+    pm = pyref.Mods(mods, nvar)
+    rng = np.random.default_rng(5)
+    pre = []
+    for i in range(14):                                     # precursors of partially modified peptides
+        q = seqs[int(rng.integers(len(seqs)))]
+        elig = [j for j, c in enumerate(q) if c in pm.var and c not in pm.fix]
+        pick = [j for j in elig if rng.random() < 0.5][:nvar]
+        m = pyref.sequence_weight(q) + sum(pm.fix.get(c, 0) for c in q) + sum(pm.var[q[j]] for j in pick)
+        tol = m // 100_000
+        pre.append((m, m - tol, m + tol, 2, i))
+    ref = cpu.candidates(pre)
+    cpu.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
+    with pytest.raises(maxdecoy.MaxDecoyError):
+        cpu.candidates(pre)                                 # the mode change invalidated the index
+    cpu.index_build()
+    exp = cpu.candidates(pre)
+    wfix = [pyref.sequence_weight(q) + sum(pm.fix.get(c, 0) for c in q) for q in seqs]
+    found_partial = 0
+    for s, (P, lo, hi, z, sid) in enumerate(pre):
+        a, b = int(exp["off"][s]), int(exp["off"][s + 1])
+        got = [(int(exp["peptide_id"][i]) - 1, int(exp["var_mask"][i]), int(exp["mod_weight"][i])) for i in range(a, b)]
+        assert len(set(got)) == len(got)
+        want = set()
+        for p, q in enumerate(seqs):
+            if wfix[p] > hi or wfix[p] + nvar * 80_000_000 < lo:
+                continue
+            elig = [j for j, c in enumerate(q) if c in pm.var and c not in pm.fix]
+            for n in range(0, nvar + 1):
+                for sub in itertools.combinations(elig, n):
+                    w = wfix[p] + sum(pm.var[q[j]] for j in sub)
+                    if lo <= w <= hi:
+                        want.add((p, sum(1 << j for j in sub), w))
+        assert set(got) == want
+        assert len(want) >= 1                               # the generating form itself
+        found_partial += any(0 < bin(m).count("1") < sum(1 for c in seqs[p] if c in pm.var and c not in pm.fix) for p, m, w in got)
+        ra, rb = int(ref["off"][s]), int(ref["off"][s + 1])
+        for i in range(ra, rb):
+            assert (int(ref["peptide_id"][i]) - 1, int(ref["var_mask"][i]), int(ref["mod_weight"][i])) in want
+    assert found_partial > 0                                # forms the reference mode cannot find
+    cpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+    cpu.index_build()
+
+
 def test_no_modifiable_letter_means_no_targets(cpu):
     """identification.rs:375-379: with an empty modification list the recursion emits no query."""
     cpu.digest(list(wl.proteins(40)), 2, 5, 50)
