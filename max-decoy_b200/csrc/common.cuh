@@ -181,3 +181,10 @@ __host__ __device__ inline uint32_t md_attempt_cap(uint32_t n) { return 16u * n 
 
 // score rows: residue codes, padded to 16 bytes; decoy rows are fixed 64-byte slots
 #define MD_DECOY_ROW 64
+// Accepted decoys live in TWO PLANES of 32-byte half rows (first halves of all slots, then second halves): the score
+// kernel reads a row in 16-byte chunks only as far as the candidate is long, most decoys end inside the first half, and
+// with this layout the DRAM bursts that bring one first half bring its neighbours' first halves, not unused padding.
+#define MD_DECOY_HALF 32
+__host__ __device__ inline size_t md_dec_byte(size_t n_slots, size_t slot, uint32_t i) {
+  return i < MD_DECOY_HALF ? slot * MD_DECOY_HALF + i : (n_slots + slot) * MD_DECOY_HALF + (i - MD_DECOY_HALF);
+}

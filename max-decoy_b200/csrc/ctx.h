@@ -61,7 +61,7 @@ struct IdentifyWorkspace {
   DevBuf<uint32_t> work_list; DevBuf<uint32_t> counters; DevBuf<unsigned long long> stat64;
   // binned spectra
   DevBuf<uint16_t> gmap; DevBuf<uint32_t> gbits;   // per-CTA block maps in HBM (tables beyond the shared-memory map)
-  DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_pre; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
+  DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
   DevBuf<uint8_t> cub_tmp;

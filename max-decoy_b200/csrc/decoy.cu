@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
 // read from HBM once (staged in shared memory); the kept rows are copied by the whole CTA, four lanes per 64-byte row.
 __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
                                                       const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, uint32_t max_na, AttemptOut A,
-                                                      uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
+                                                      uint64_t n_slots, uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
                                                       int64_t* __restrict__ dec_w, uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt,
                                                       uint32_t* __restrict__ dec_count) {
   extern __shared__ __align__(16) unsigned long long s_key[];     // slots (0 = empty)
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
   for (uint32_t t = tid; t < nk * 4u; t += 256) {
     const uint32_t r = t >> 2, q = t & 3u;
     const uint64_t src = a0 + s_list[r], dst = dbase + have + r;
-    reinterpret_cast<uint4*>(dec_rows + dst * MD_DECOY_ROW)[q] = __ldg(reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW) + q);
+    *reinterpret_cast<uint4*>(dec_rows + md_dec_byte(n_slots, dst, q * 16u)) = __ldg(reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW) + q);
   }
   for (uint32_t r = tid; r < nk; r += 256) {
     const uint32_t a = s_list[r];
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
 // One CTA per listed spectrum: keep the successes of this round that are new (not equal to an accepted decoy or to an
 // earlier success), in attempt order, until the spectrum has n_per decoys (HashSet<Decoy>, decoy_generator.rs:40,164).
 __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
-                                                      const uint32_t* __restrict__ att_base, uint32_t n_per, AttemptOut A, uint8_t* __restrict__ dec_rows,
+                                                      const uint32_t* __restrict__ att_base, uint32_t n_per, AttemptOut A, uint64_t n_slots, uint8_t* __restrict__ dec_rows,
                                                       uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask, int64_t* __restrict__ dec_w,
                                                       uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt, uint32_t* __restrict__ dec_count) {
   __shared__ uint64_t s_hash[kMaxRoundAttempts];
@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restr
       const uint8_t* mine = A.rows + (uint64_t)(a0 + a) * MD_DECOY_ROW;
       for (uint32_t j = 0; j < have && keep; j++) {
         if (dec_hash[dbase + j] == h && dec_len[dbase + j] == L) {
-          const uint8_t* o = dec_rows + (dbase + j) * MD_DECOY_ROW; bool eq = true;
-          for (uint32_t i = 0; i < L; i++) if (o[i] != mine[i]) { eq = false; break; }
+          bool eq = true;
+          for (uint32_t i = 0; i < L; i++) if (dec_rows[md_dec_byte(n_slots, dbase + j, i)] != mine[i]) { eq = false; break; }
           if (eq) keep = false;
         }
       }
@@ -562,8 +562,7 @@ __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restr
     if (o < n_per) {
       const uint64_t src = a0 + a, dst = dbase + o;
       const uint4* sr = reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW);
-      uint4* dr = reinterpret_cast<uint4*>(dec_rows + dst * MD_DECOY_ROW);
-      dr[0] = sr[0]; dr[1] = sr[1]; dr[2] = sr[2]; dr[3] = sr[3];
+      for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4*>(dec_rows + md_dec_byte(n_slots, dst, q * 16u)) = sr[q];
       dec_len[dst] = A.len[src]; dec_mask[dst] = A.mask[src]; dec_w[dst] = A.w[src]; dec_hash[dst] = s_hash[a];
       dec_attempt[dst] = att_base[li] + a;
     }
@@ -795,10 +794,10 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       const size_t smem = (size_t)slots * 12 + (size_t)max_na * 10;
       if (smem <= 220 * 1024) {
         MD_CUDA(cudaFuncSetAttribute(k_decoy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, max_na, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, max_na, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
                   W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       } else {
-        MD_LAUNCH(ctx, k_decoy_select_n2, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+        MD_LAUNCH(ctx, k_decoy_select_n2, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
                   W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       }
     }
@@ -843,7 +842,7 @@ void decoys_export(md_ctx* ctx, uint32_t n, uint32_t n_per, md_decoy_table* out)
       size_t slot = (size_t)s * n_per + j;
       uint32_t L = len[slot];
       int64_t wu = MD_WATER_UDA;
-      for (uint32_t i = 0; i < L; i++) { uint8_t code = rows[slot * MD_DECOY_ROW + i]; out->seq[b + i] = md_letter_of(code); wu += kResidueMassByCode[code]; }
+      for (uint32_t i = 0; i < L; i++) { uint8_t code = rows[md_dec_byte(slots, slot, i)]; out->seq[b + i] = md_letter_of(code); wu += kResidueMassByCode[code]; }
       b += L;
       out->seq_off[k + 1] = b; out->var_mask[k] = mask[slot]; out->weight[k] = wu; out->mod_weight[k] = w[slot]; out->attempt[k] = att[slot];
       k++;

@@ -23,6 +23,7 @@ struct ExTables {
 
 struct DecoyOut {
   uint8_t* rows; uint8_t* len; uint64_t* mask; int64_t* w; uint64_t* hash; uint32_t* attempt; uint32_t* count;
+  uint64_t n_slots;   // decoy slots of the batch (two-plane row layout, md_dec_byte)
 };
 
 __global__ void __launch_bounds__(64) k_decoy_exhaustive(const md_precursor* __restrict__ prec, uint32_t n_spec, uint32_t n_per,
@@ -75,9 +76,7 @@ __global__ void __launch_bounds__(64) k_decoy_exhaustive(const md_precursor* __r
           const uint32_t ord = ordinal++;
           if (!is_peptide(ascii, L, h, PV.ht_key, PV.ht_val, PV.ht_mask, PV.seq, PV.off, PV.len)) {
             const uint64_t slot = dbase + found;
-            uint8_t* row = O.rows + slot * MD_DECOY_ROW;
-            for (uint32_t i = 0; i < L; i++) row[i] = T.code_of_a[cur[i]];
-            for (uint32_t i = L; i < MD_DECOY_ROW; i++) row[i] = MD_CODE_OTHER;
+            for (uint32_t i = 0; i < MD_DECOY_ROW; i++) O.rows[md_dec_byte(O.n_slots, slot, i)] = i < L ? T.code_of_a[cur[i]] : (uint8_t)MD_CODE_OTHER;
             O.len[slot] = (uint8_t)L; O.mask[slot] = 0; O.w[slot] = w; O.hash[slot] = h; O.attempt[slot] = ord;
             if (++found >= n_per) { done = true; break; }
           }
@@ -113,7 +112,7 @@ void decoys_exhaustive_dev(md_ctx* ctx, uint32_t n, uint32_t n_per) {
     MD_REQUIRE(T.m[a] > 0, MD_ERR_INVALID, "exhaustive decoys need positive residue masses");
   }
   PeptideView PV{(const unsigned long long*)P.ht_key.p, P.ht_val.p, P.ht_mask, P.seq.p, P.seq_off.p, P.len.p};
-  DecoyOut O{W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p, W.dec_attempt.p, W.dec_count.p};
+  DecoyOut O{W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p, W.dec_attempt.p, W.dec_count.p, (uint64_t)n * n_per};
   DevBuf<int>& flag = W.t_ovf; flag.need(1);
   MD_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
   MD_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));

@@ -96,7 +96,7 @@ __device__ __forceinline__ PeakEval eval_peak(double mz, float I, int64_t P, int
 
 __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const double* __restrict__ peak_mz, const float* __restrict__ peak_int,
                               const md_precursor* __restrict__ prec, uint32_t n, int64_t w, uint32_t min_peaks, int32_t* __restrict__ pk_bin,
-                              int32_t* __restrict__ pk_yq, uint32_t* __restrict__ pk_pre, uint32_t* __restrict__ pk_count, int32_t* __restrict__ pk_hbin, int* __restrict__ unsorted) {
+                              int32_t* __restrict__ pk_yq, uint32_t* __restrict__ pk_count, int32_t* __restrict__ pk_hbin, int* __restrict__ unsorted) {
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= n) return;
   const uint64_t p0 = peak_off[s], p1 = peak_off[s + 1];
@@ -166,19 +166,6 @@ __global__ void k_bin_spectra(const uint64_t* __restrict__ peak_off, const doubl
     if (last > carry_bin) carry_bin = last;
   }
   if (lane == 0) { pk_count[s] = carry_cnt; pk_hbin[s] = hbin; }
-  // exclusive prefix sums of y (mod 2^32: window sums are < 2^31, differences stay exact); carry_cnt + 1 entries at p0 + s
-  __syncwarp();
-  uint32_t run = 0;
-  uint32_t* pre = pk_pre + p0 + s;
-  for (uint32_t base = 0; base < carry_cnt; base += 32) {
-    const uint32_t i = base + lane;
-    const uint32_t v = i < carry_cnt ? (uint32_t)__ldcg(&pk_yq[p0 + i]) : 0u;
-    uint32_t incl = v;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-    if (i < carry_cnt) pre[i] = run + incl - v;
-    run += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0) pre[carry_cnt] = run;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -197,9 +184,10 @@ struct ScoreConst {
 
 struct ScoreArgs {
   const md_precursor* prec; uint32_t n_spec;
-  const uint64_t* peak_off; const int32_t* pk_bin; const int32_t* pk_yq; const uint32_t* pk_pre; const uint32_t* pk_count; const int32_t* pk_hbin;
+  const uint64_t* peak_off; const int32_t* pk_bin; const int32_t* pk_yq; const uint32_t* pk_count; const int32_t* pk_hbin;
   const uint64_t* cand_off; const uint64_t* cand_desc; const uint64_t* cand_mask; const int64_t* cand_w; const uint32_t* cand_pep;
   const uint8_t* idx_rows;
+  uint64_t dec_slots;   // decoy slots of the batch: the second halves of the decoy rows start dec_slots * 32 bytes in (md_dec_byte)
   const uint8_t* dec_rows; const uint8_t* dec_len; const uint64_t* dec_mask; const int64_t* dec_w; const uint32_t* dec_count;
   int64_t* tscore; int64_t* dscore;   // raw score of every candidate, or NULL (PSM rows only)
   md_psm* psm;
@@ -241,7 +229,7 @@ __device__ __forceinline__ int32_t gather(uint32_t bin, const TableView& V) {
 struct LaneTab { uint32_t q, r, vq, vr; };      // lane = residue code
 constexpr uint32_t kStop = 1u << 30;            // added to the running bin at the last residue: every later bin misses
 
-struct CandRef { const uint4* row; uint32_t len; uint64_t mask; int64_t modw; };
+struct CandRef { const uint4* row; const uint4* row_hi; uint32_t len; uint64_t mask; int64_t modw; };   // row: bytes 0..31, row_hi: bytes 32..63
 
 // Raw score of one candidate against the (tile of the) block-compressed table.
 //   b ion of split k, charge c: floor((B_k + c*proton) / (c*w)) + 1;  y ion: floor((modw - B_k + c*proton) / (c*w)) + 1
@@ -273,7 +261,7 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   if (nsplit == 0) QB += kStop;
   int64_t acc = 0;
   for (uint32_t c = 0; c * 4 < nword; c++) {
-    const uint4 v = __ldg(cr.row + c);
+    const uint4 v = __ldg(c < 2 ? cr.row + c : cr.row_hi + (c - 2));
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -307,16 +295,18 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   return acc;
 }
 
+// (without variable modifications every mask is 0: not read)
+template <bool HASVAR>
 __device__ __forceinline__ CandRef cand_ref(const ScoreArgs& A, uint32_t s, uint32_t v, uint32_t nt, uint64_t t0c, uint32_t n_per) {
   CandRef r;
   if (v < nt) {
     const uint64_t c = t0c + v, d = A.cand_desc[c];
-    r.row = reinterpret_cast<const uint4*>(A.idx_rows + (d & 0xFFFFFFFFFFull) * 16);
-    r.len = (uint32_t)(d >> 40) & 0xFF; r.mask = A.cand_mask[c]; r.modw = A.cand_w[c];
+    r.row = reinterpret_cast<const uint4*>(A.idx_rows + (d & 0xFFFFFFFFFFull) * 16); r.row_hi = r.row + 2;
+    r.len = (uint32_t)(d >> 40) & 0xFF; r.mask = HASVAR ? A.cand_mask[c] : 0ull; r.modw = A.cand_w[c];
   } else {
     const uint64_t j = (uint64_t)s * n_per + (v - nt);
-    r.row = reinterpret_cast<const uint4*>(A.dec_rows + j * MD_DECOY_ROW);
-    r.len = A.dec_len[j]; r.mask = A.dec_mask[j]; r.modw = A.dec_w[j];
+    r.row = reinterpret_cast<const uint4*>(A.dec_rows + j * MD_DECOY_HALF); r.row_hi = reinterpret_cast<const uint4*>(A.dec_rows + (A.dec_slots + j) * MD_DECOY_HALF);
+    r.len = A.dec_len[j]; r.mask = HASVAR ? A.dec_mask[j] : 0ull; r.modw = A.dec_w[j];
   }
   return r;
 }
@@ -363,11 +353,11 @@ __device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst
     if (u >= units) break;
     const uint32_t slot = u * 32 + lane;
     CandRef cr;
-    cr.row = reinterpret_cast<const uint4*>(A.idx_rows); cr.len = 0; cr.mask = 0; cr.modw = 0;
+    cr.row = reinterpret_cast<const uint4*>(A.idx_rows); cr.row_hi = cr.row; cr.len = 0; cr.mask = 0; cr.modw = 0;
     uint32_t v = 0;
     if (slot < cn) {
       v = s_order[slot];
-      cr = cand_ref(A, s, c0 + v, nt, t0c, C.n_per);
+      cr = cand_ref<HASVAR>(A, s, c0 + v, nt, t0c, C.n_per);
     }
     const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
     const int64_t part = score_one<NCH, HASVAR, MAPG>(cr, maxlen, V, C, L);
@@ -794,12 +784,12 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_REQUIRE(mfc <= 3, MD_ERR_UNSUPPORTED, "max_fragment_charge > 3 (the reference fixes it to 3: comet_parameter.rs:55)");
   MD_REQUIRE(p.top_k <= kMaxTopK, MD_ERR_UNSUPPORTED, "top_k > 128");
   // ---- K4a
-  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_pre.need(n_peaks + n + 2); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
+  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
   DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
   MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 4 * sizeof(int), ctx->stream));
   MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), ctx->stream));
   MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
-            W.pk_pre.p, W.pk_count.p, W.pk_hbin.p, d_flag.p);
+            W.pk_count.p, W.pk_hbin.p, d_flag.p);
   // the largest table of the batch decides whether the block maps fit shared memory
   MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
   int h_pre[4] = {0, 0, 0, 0};
@@ -838,10 +828,10 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
   const bool timing = getenv("MD_SCORE_TIMING") != nullptr;
   ScoreArgs A;
-  A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_pre = W.pk_pre.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
+  A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
   A.cand_off = W.cand_off.p; A.cand_desc = W.cand_desc.p; A.cand_mask = W.cand_mask.p; A.cand_w = W.cand_w.p; A.cand_pep = W.cand_pep.p;
   A.idx_rows = ctx->index.rows.p;
-  A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
+  A.dec_slots = (uint64_t)n * n_per; A.dec_rows = W.dec_rows.p; A.dec_len = W.dec_len.p; A.dec_mask = W.dec_mask.p; A.dec_w = W.dec_w.p; A.dec_count = n_per ? W.dec_count.p : nullptr;
   A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
   A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
   A.gmap = gstride ? W.gmap.p : nullptr; A.gbits = gstride ? W.gbits.p : nullptr; A.gmap_stride = gstride;
