@@ -555,7 +555,80 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     const uint32_t nact = scored ? (mt.pre_blocks ? mt.nact : sh.nact) : 0;
     MD_TICK(0);
 
-    const bool fast = K <= kFastTopK && ncand <= kCandChunk;   // warp-local top-k, merged by warp 0 while the others move on
+    const bool fast = K <= kFastTopK;   // per-warp running top-k lists, merged by the finish warp while the CTA scores the next spectrum
+    // the table of one tile of occupied blocks [cb0, cb0 + cbn) (block-uniform: every thread calls it)
+    auto build_tile = [&](const uint32_t cb0, const uint32_t cbn) {
+      // (1) block map of the tile (0 = the all-zero block), zero the occupied blocks
+      for (uint32_t k = tid; k <= nblk; k += kScoreThreads) {
+        uint32_t m = 0;
+        if (k < nblk) {
+          const uint32_t wd = bits[k >> 5];
+          if ((wd >> (k & 31)) & 1u) {
+            const uint32_t c = bpre[k >> 5] + (uint32_t)__popc(wd & ((1u << (k & 31)) - 1u));
+            if (c >= cb0 && c < cb0 + cbn) m = c - cb0 + 1u;
+          }
+        }
+        map[k] = (uint16_t)(m ? (m << kBlkShift) | (kBlk - 1u) : 0u);
+        if (m == 1u) sh.x0 = k << kBlkShift;                              // first bin of the tile
+      }
+      {
+        uint4* z = reinterpret_cast<uint4*>(tab);
+        const uint32_t n4 = (cbn + 1u) * (kBlk / 4);
+        for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { sh.unit = 0; sh.cin = 0; }
+      }
+      __syncthreads();
+      MD_TICK(2);
+      // (2) T as a difference array: every peak adds +y at the first bin of its window (bin-75), -y behind its last
+      //     (bin+76), and its own 151*y spike as -151*y at bin / +151*y at bin+1, so that the running sum over the
+      //     bins is R[b] = S[b] - 151*y[b] = -T[b].  All four bins lie in occupied blocks (the marking covers
+      //     [bin-75, bin+76]), R is 0 at the end of every run of occupied blocks, and the compressed blocks are in
+      //     bin order: one inclusive scan straight over the compressed table yields -T.  Integer adds commute, so
+      //     the shared-memory atomics keep the table exact.  A later tile starts from the sum of the differences
+      //     at the bins in front of it (sh.cin).
+      {
+        const uint32_t X0 = sh.x0;
+        int32_t cin = 0;
+        for (uint32_t p = tid; p < npk; p += kScoreThreads) {
+          const int32_t bp = pbin[p], y = pyq[p];
+          const uint32_t xa = (uint32_t)max(bp - kXcorrOffset, 0), xe = (uint32_t)(bp + kXcorrOffset + 1), xs = (uint32_t)bp;
+          const int32_t spike = 151 * y;
+          uint32_t m;
+          m = (uint32_t)map[xa >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xa & (kBlk - 1u))], y);
+          // (xe == NB for the last peak: the bins of the last block behind the table's end must read 0 too)
+          if (xe < (nblk << kBlkShift)) { m = (uint32_t)map[xe >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xe & (kBlk - 1u))], -y); }
+          m = (uint32_t)map[xs >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xs & (kBlk - 1u))], -spike);
+          m = (uint32_t)map[(xs + 1u) >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + ((xs + 1u) & (kBlk - 1u))], spike);
+          if (cb0 > 0) cin += (xa < X0 ? y : 0) - (xe < X0 ? y : 0) - (xs < X0 ? spike : 0) + (xs + 1u < X0 ? spike : 0);
+        }
+        if (cb0 > 0 && cin != 0) atomicAdd(&sh.cin, cin);
+      }
+      __syncthreads();
+      MD_TICK(3);
+      // (3) the scan, in place, negated: every thread owns a contiguous range of 16-byte words (an odd number of them:
+      //     the 128-bit accesses of a quarter warp then fall into distinct banks); pass A adds up the ranges, a warp scan
+      //     and the per-warp sums give every thread its start value, pass B rescans the range
+      {
+        uint4* t4 = reinterpret_cast<uint4*>(tab) + kBlk / 4;            // entry 0 = first occupied block
+        const uint32_t N4 = cbn * (kBlk / 4);
+        const uint32_t c4 = ((N4 + kScoreThreads - 1) / kScoreThreads) | 1u;
+        const uint32_t s0 = min(tid * c4, N4), s1 = min(s0 + c4, N4);
+        uint32_t part = 0;
+        for (uint32_t i = s0; i < s1; i++) { const uint4 v = t4[i]; part += v.x + v.y + v.z + v.w; }
+        uint32_t incl = part;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) sh.wsum[warp] = incl;
+        __syncthreads();
+        uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? sh.wsum[lane] : 0u) + (uint32_t)sh.cin + incl - part;
+        for (uint32_t i = s0; i < s1; i++) {
+          uint4 v = t4[i];
+          v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w;
+          t4[i] = make_uint4(0u - v.x, 0u - v.y, 0u - v.z, 0u - v.w);
+        }
+      }
+      __syncthreads();
+    };
+    const bool one_tile = nact <= kTileBlocks;   // the usual case: the table is built once and serves every chunk of candidates
     for (uint32_t c0 = 0; c0 < ncand || c0 == 0; c0 += kCandChunk) {
       const uint32_t cn = min(kCandChunk, ncand - c0);
       for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
@@ -598,75 +671,8 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       if (scored && cn) {
         for (uint32_t cb0 = 0; cb0 < nact; cb0 += kTileBlocks) {       // tiles of occupied blocks (usually one)
           const uint32_t cbn = min(kTileBlocks, nact - cb0);
-          // (1) block map of the tile (0 = the all-zero block), zero the occupied blocks
-          for (uint32_t k = tid; k <= nblk; k += kScoreThreads) {
-            uint32_t m = 0;
-            if (k < nblk) {
-              const uint32_t wd = bits[k >> 5];
-              if ((wd >> (k & 31)) & 1u) {
-                const uint32_t c = bpre[k >> 5] + (uint32_t)__popc(wd & ((1u << (k & 31)) - 1u));
-                if (c >= cb0 && c < cb0 + cbn) m = c - cb0 + 1u;
-              }
-            }
-            map[k] = (uint16_t)(m ? (m << kBlkShift) | (kBlk - 1u) : 0u);
-            if (m == 1u) sh.x0 = k << kBlkShift;                              // first bin of the tile
-          }
-          {
-            uint4* z = reinterpret_cast<uint4*>(tab);
-            const uint32_t n4 = (cbn + 1u) * (kBlk / 4);
-            for (uint32_t i = tid; i < n4; i += kScoreThreads) z[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) { sh.unit = 0; sh.cin = 0; }
-          }
-          __syncthreads();
-          MD_TICK(2);
-          // (2) T as a difference array: every peak adds +y at the first bin of its window (bin-75), -y behind its last
-          //     (bin+76), and its own 151*y spike as -151*y at bin / +151*y at bin+1, so that the running sum over the
-          //     bins is R[b] = S[b] - 151*y[b] = -T[b].  All four bins lie in occupied blocks (the marking covers
-          //     [bin-75, bin+76]), R is 0 at the end of every run of occupied blocks, and the compressed blocks are in
-          //     bin order: one inclusive scan straight over the compressed table yields -T.  Integer adds commute, so
-          //     the shared-memory atomics keep the table exact.  A later tile starts from the sum of the differences
-          //     at the bins in front of it (sh.cin).
-          {
-            const uint32_t X0 = sh.x0;
-            int32_t cin = 0;
-            for (uint32_t p = tid; p < npk; p += kScoreThreads) {
-              const int32_t bp = pbin[p], y = pyq[p];
-              const uint32_t xa = (uint32_t)max(bp - kXcorrOffset, 0), xe = (uint32_t)(bp + kXcorrOffset + 1), xs = (uint32_t)bp;
-              const int32_t spike = 151 * y;
-              uint32_t m;
-              m = (uint32_t)map[xa >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xa & (kBlk - 1u))], y);
-              // (xe == NB for the last peak: the bins of the last block behind the table's end must read 0 too)
-              if (xe < (nblk << kBlkShift)) { m = (uint32_t)map[xe >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xe & (kBlk - 1u))], -y); }
-              m = (uint32_t)map[xs >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + (xs & (kBlk - 1u))], -spike);
-              m = (uint32_t)map[(xs + 1u) >> kBlkShift] >> kBlkShift; if (m) atomicAdd(&tab[(m << kBlkShift) + ((xs + 1u) & (kBlk - 1u))], spike);
-              if (cb0 > 0) cin += (xa < X0 ? y : 0) - (xe < X0 ? y : 0) - (xs < X0 ? spike : 0) + (xs + 1u < X0 ? spike : 0);
-            }
-            if (cb0 > 0 && cin != 0) atomicAdd(&sh.cin, cin);
-          }
-          __syncthreads();
-          MD_TICK(3);
-          // (3) the scan, in place, negated: every thread owns a contiguous range of 16-byte words (an odd number of them:
-          //     the 128-bit accesses of a quarter warp then fall into distinct banks); pass A adds up the ranges, a warp scan
-          //     and the per-warp sums give every thread its start value, pass B rescans the range
-          {
-            uint4* t4 = reinterpret_cast<uint4*>(tab) + kBlk / 4;            // entry 0 = first occupied block
-            const uint32_t N4 = cbn * (kBlk / 4);
-            const uint32_t c4 = ((N4 + kScoreThreads - 1) / kScoreThreads) | 1u;
-            const uint32_t s0 = min(tid * c4, N4), s1 = min(s0 + c4, N4);
-            uint32_t part = 0;
-            for (uint32_t i = s0; i < s1; i++) { const uint4 v = t4[i]; part += v.x + v.y + v.z + v.w; }
-            uint32_t incl = part;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-            if (lane == 31) sh.wsum[warp] = incl;
-            __syncthreads();
-            uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? sh.wsum[lane] : 0u) + (uint32_t)sh.cin + incl - part;
-            for (uint32_t i = s0; i < s1; i++) {
-              uint4 v = t4[i];
-              v.x += run; v.y += v.x; v.z += v.y; v.w += v.z; run = v.w;
-              t4[i] = make_uint4(0u - v.x, 0u - v.y, 0u - v.z, 0u - v.w);
-            }
-          }
-          __syncthreads();
+          if (!one_tile || c0 == 0) build_tile(cb0, cbn);
+          else { if (tid == 0) sh.unit = 0; __syncthreads(); }               // same table; the chunk's order and zeroed scores are visible
           // (4) score the chunk against the tile; one warp first fetches the CTA's next spectrum
           if (!side_done) {
             if (warp == kPrefetchWarp) prefetch_spectrum(A, sh, slot ^ 1u, s_bin, s_yq);
@@ -696,7 +702,29 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
           if (u < nt) A.tscore[t0c + u] = s_score[v]; else A.dscore[(uint64_t)s * C.n_per + (u - nt)] = s_score[v];
         }
       }
-      // ---- top-k of (this chunk's candidates) U (best of the earlier chunks): K rounds of block-wide max
+      // ---- top-k, K <= 8: every warp keeps the K best keys it has seen so far (lane r holds its r-th best across chunks)
+      if (fast && scored && K) {   // (also without a candidate: the lists must not keep an earlier spectrum's keys)
+        unsigned long long k0 = tid < cn ? psm_key(s_score[tid], c0 + tid) : 0ull;
+        unsigned long long k1 = tid + kScoreThreads < cn ? psm_key(s_score[tid + kScoreThreads], c0 + tid + kScoreThreads) : 0ull;
+        if (ncand <= kCandChunk) {            // one chunk (the usual case): nothing to carry over
+          for (uint32_t r = 0; r < K; r++) {
+            const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
+            if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
+            if (lane == 0) sh.wtop[slot][warp][r] = wm;
+          }
+        } else {
+          unsigned long long carry = (c0 > 0 && lane < K) ? sh.wtop[slot][warp][lane] : 0ull, mine = 0ull;
+          for (uint32_t r = 0; r < K; r++) {
+            const unsigned long long b01 = k0 > k1 ? k0 : k1;
+            const unsigned long long wm = warp_max_u64(b01 > carry ? b01 : carry);
+            if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; else if (carry == wm) carry = 0ull; }
+            if (lane == r) mine = wm;
+          }
+          __syncwarp();
+          if (lane < K) sh.wtop[slot][warp][lane] = mine;
+        }
+      }
+      // ---- top-k of (this chunk's candidates) U (best of the earlier chunks), K > 8: K rounds of block-wide max
       if (!fast && scored && cn && K) {
         // scores -> keys, in place; slots cn..cn+K-1 (conceptually) hold the running list, owned by threads < K
         for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = (int64_t)psm_key(s_score[v], c0 + v);
@@ -727,16 +755,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     }
     // ---- PSM rows
     if (fast) {
-      // per-warp top-k lists; the finish warp merges them and writes the rows during the next scoring phase
-      if (scored && K) {
-        unsigned long long k0 = tid < ncand ? psm_key(s_score[tid], tid) : 0ull;
-        unsigned long long k1 = tid + kScoreThreads < ncand ? psm_key(s_score[tid + kScoreThreads], tid + kScoreThreads) : 0ull;
-        for (uint32_t r = 0; r < K; r++) {
-          const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
-          if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
-          if (lane == 0) sh.wtop[slot][warp][r] = wm;
-        }
-      }
+      // the per-warp top-k lists are complete; the finish warp merges them and writes the rows during the next scoring phase
       if (tid == 0) {
         FinRecord f; f.pr = pr; f.t0c = t0c; f.s = s; f.nt = nt; f.nd = nd; f.pending = 1; f.ranked = (scored && K) ? 1u : 0u;
         sh.fin[slot] = f;
