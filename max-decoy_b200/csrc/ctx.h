@@ -64,6 +64,7 @@ struct IdentifyWorkspace {
   DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
+  DevBuf<unsigned long long> part_top; DevBuf<uint32_t> parts_done;   // spectra split into parts (open searches): per-part top-k keys, arrival counters
   DevBuf<uint8_t> cub_tmp;
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
   DevBuf<uint64_t> t_size; DevBuf<int16_t> t_K; DevBuf<uint32_t> t_flag, t_pos; DevBuf<int> t_ovf, t_unsorted;

@@ -195,6 +195,9 @@ struct ScoreArgs {
   unsigned long long* stat64;  // [0] pairs scored, [1] algorithmic bytes (14 + len per pair)
   int* error;                  // set when a spectrum needs more table bins than kMaxBins
   unsigned long long* timing;  // MD_SCORE_TIMING=1: per-phase SM cycles summed over CTAs (thread 0's clock), else NULL
+  // spectra with very many candidates (open searches) are split into `parts` work items, one contiguous range of candidate
+  // chunks each; a part leaves its K best keys in part_top and the last part to finish (parts_done) writes the PSM rows
+  uint32_t parts; unsigned long long* part_top; uint32_t* parts_done;
   uint16_t* gmap; uint32_t* gbits; uint32_t gmap_stride;   // per-CTA block map / block bitmap in HBM for tables beyond kMapCap blocks
 };
 
@@ -371,11 +374,12 @@ struct SpecMeta {
   md_precursor pr;
   uint64_t t0c, pk0;
   uint32_t s, nt, nd, npk, nact;
+  uint32_t part, c_lo, c_hi;         // this work item's part of the spectrum: candidates [c_lo, c_hi)
   int32_t hbin;
   uint32_t pre_blocks;               // peaks, bitmap and block numbering are already in shared memory
 };
 
-struct FinRecord { md_precursor pr; uint64_t t0c; uint32_t s, nt, nd, pending, ranked; };
+struct FinRecord { md_precursor pr; uint64_t t0c; uint32_t s, nt, nd, pending, ranked, part; };
 
 struct SpecShared {
   SpecMeta meta[2];
@@ -406,10 +410,12 @@ __device__ __forceinline__ uint32_t cand_len(const ScoreArgs& A, uint32_t s, uin
 // occupied-block bitmap with its numbering.
 __device__ __noinline__ void prefetch_spectrum(const ScoreArgs& A, SpecShared& sh, uint32_t slot, int32_t* s_bin, int32_t* s_yq) {
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t sn = 0;
-  if (lane == 0) sn = atomicAdd(A.work, 1u);
-  sn = __shfl_sync(0xffffffffu, sn, 0);
+  uint32_t vn = 0;
+  if (lane == 0) vn = atomicAdd(A.work, 1u);
+  vn = __shfl_sync(0xffffffffu, vn, 0);
+  const uint32_t sn = vn / A.parts;          // work item -> (spectrum, part); sn >= n_spec ends the CTA
   SpecMeta m;
+  m.part = vn % A.parts; m.c_lo = 0; m.c_hi = 0;
   m.s = sn; m.pre_blocks = 0; m.nact = 0; m.nt = 0; m.nd = 0; m.npk = 0; m.hbin = -1; m.t0c = 0; m.pk0 = 0;
   m.pr.mass = 0; m.pr.lo = 0; m.pr.hi = 0; m.pr.charge = 0; m.pr.spectrum_id = 0;
   if (sn < A.n_spec) {
@@ -421,6 +427,10 @@ __device__ __noinline__ void prefetch_spectrum(const ScoreArgs& A, SpecShared& s
     const uint32_t NB = m.hbin >= 0 ? (uint32_t)m.hbin + kXcorrOffset + 1 : 0;
     const uint32_t nblk = (NB + kBlk - 1) >> kBlkShift, nwords = (nblk + 31) >> 5;
     const uint32_t ncand = m.nt + m.nd;
+    {   // this part's contiguous range of candidate chunks
+      const uint32_t nchunks = (ncand + kCandChunk - 1) / kCandChunk, per = (nchunks + A.parts - 1) / A.parts;
+      m.c_lo = min(m.part * per * kCandChunk, ncand); m.c_hi = min((m.part + 1) * per * kCandChunk, ncand);
+    }
     const bool scored = m.hbin >= 0 && NB <= kMaxBins && ncand <= 0xFFFFFFu;
     if (scored && m.npk <= kPeakCap && nblk <= kMapCap) {
       const int32_t* gb = A.pk_bin + m.pk0; const int32_t* gy = A.pk_yq + m.pk0;
@@ -469,10 +479,32 @@ __device__ __noinline__ void finish_spectrum(const ScoreArgs& A, const ScoreCons
       if (lane == r) mine = wm;
     }
   }
+  if (A.parts > 1) {
+    // leave this part's keys; the last part of the spectrum to arrive merges all of them
+    unsigned long long* pt = A.part_top + (size_t)f.s * A.parts * kFastTopK;
+    if (lane < kFastTopK) pt[f.part * kFastTopK + lane] = lane < K ? mine : 0ull;
+    __threadfence();
+    uint32_t arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&A.parts_done[f.s], 1u);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived + 1 != A.parts) return;
+    __threadfence();
+    static_assert(8 * kFastTopK <= 64, "a lane merges at most two keys of the parts' lists");
+    unsigned long long k0 = lane < A.parts * kFastTopK ? __ldcg(pt + lane) : 0ull;
+    unsigned long long k1 = lane + 32 < A.parts * kFastTopK ? __ldcg(pt + lane + 32) : 0ull;
+    mine = 0ull;
+    for (uint32_t r = 0; r < K; r++) {
+      const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
+      if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
+      if (lane == r) mine = wm;
+    }
+  }
   if (lane < K) write_psm_row(A, C, f.pr, f.s, lane, mine, f.nt, f.nd, f.t0c);
 }
 
-template <bool HASVAR>
+// MODE 0: no spectrum of the batch has more candidates than one chunk (the usual 10-ppm search: the chunk loop runs once,
+// known at compile time); 1: general; 2: general, and spectra are divided into parts (ScoreArgs::parts > 1)
+template <bool HASVAR, int MODE>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C) {
   extern __shared__ __align__(16) int32_t tab[];                     // kTileBins
   int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins);    // kCandChunk
@@ -629,8 +661,9 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       __syncthreads();
     };
     const bool one_tile = nact <= kTileBlocks;   // the usual case: the table is built once and serves every chunk of candidates
-    for (uint32_t c0 = 0; c0 < ncand || c0 == 0; c0 += kCandChunk) {
-      const uint32_t cn = min(kCandChunk, ncand - c0);
+    const uint32_t c_lo = MODE == 2 ? mt.c_lo : 0u, c_hi = MODE == 2 ? mt.c_hi : ncand;     // this work item's candidates (the whole spectrum unless it was split)
+    for (uint32_t c0 = c_lo; MODE == 0 ? c0 == 0 : (c0 < c_hi || c0 == c_lo); c0 += kCandChunk) {
+      const uint32_t cn = c0 < c_hi ? min(kCandChunk, c_hi - c0) : 0u;
       for (uint32_t v = tid; v < cn; v += kScoreThreads) s_score[v] = 0;
       // counting sort of the chunk by peptide length, longest first
       {
@@ -671,7 +704,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       if (scored && cn) {
         for (uint32_t cb0 = 0; cb0 < nact; cb0 += kTileBlocks) {       // tiles of occupied blocks (usually one)
           const uint32_t cbn = min(kTileBlocks, nact - cb0);
-          if (!one_tile || c0 == 0) build_tile(cb0, cbn);
+          if (!one_tile || c0 == c_lo) build_tile(cb0, cbn);
           else { if (tid == 0) sh.unit = 0; __syncthreads(); }               // same table; the chunk's order and zeroed scores are visible
           // (4) score the chunk against the tile; one warp first fetches the CTA's next spectrum
           if (!side_done) {
@@ -706,14 +739,14 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
       if (fast && scored && K) {   // (also without a candidate: the lists must not keep an earlier spectrum's keys)
         unsigned long long k0 = tid < cn ? psm_key(s_score[tid], c0 + tid) : 0ull;
         unsigned long long k1 = tid + kScoreThreads < cn ? psm_key(s_score[tid + kScoreThreads], c0 + tid + kScoreThreads) : 0ull;
-        if (ncand <= kCandChunk) {            // one chunk (the usual case): nothing to carry over
+        if (MODE == 0 || c_hi - c_lo <= kCandChunk) {      // one chunk (the usual case): nothing to carry over
           for (uint32_t r = 0; r < K; r++) {
             const unsigned long long wm = warp_max_u64(k0 > k1 ? k0 : k1);
             if (wm != 0ull) { if (k0 == wm) k0 = 0ull; else if (k1 == wm) k1 = 0ull; }
             if (lane == 0) sh.wtop[slot][warp][r] = wm;
           }
         } else {
-          unsigned long long carry = (c0 > 0 && lane < K) ? sh.wtop[slot][warp][lane] : 0ull, mine = 0ull;
+          unsigned long long carry = (c0 > c_lo && lane < K) ? sh.wtop[slot][warp][lane] : 0ull, mine = 0ull;
           for (uint32_t r = 0; r < K; r++) {
             const unsigned long long b01 = k0 > k1 ? k0 : k1;
             const unsigned long long wm = warp_max_u64(b01 > carry ? b01 : carry);
@@ -757,7 +790,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     if (fast) {
       // the per-warp top-k lists are complete; the finish warp merges them and writes the rows during the next scoring phase
       if (tid == 0) {
-        FinRecord f; f.pr = pr; f.t0c = t0c; f.s = s; f.nt = nt; f.nd = nd; f.pending = 1; f.ranked = (scored && K) ? 1u : 0u;
+        FinRecord f; f.pr = pr; f.t0c = t0c; f.s = s; f.nt = nt; f.nd = nd; f.pending = 1; f.ranked = (scored && K) ? 1u : 0u; f.part = mt.part;
         sh.fin[slot] = f;
       }
       MD_TICK(5);
@@ -777,6 +810,17 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 __global__ void k_max_i32(const int32_t* __restrict__ v, uint32_t n, int32_t* __restrict__ out) {
   int32_t m = INT32_MIN;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// most candidates (targets + decoys) of one spectrum of the batch
+__global__ void k_max_candidates(const uint64_t* __restrict__ cand_off, const uint32_t* __restrict__ dec_count, uint32_t n, int32_t* __restrict__ out) {
+  int32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t c = cand_off[i + 1] - cand_off[i] + (dec_count ? dec_count[i] : 0u);
+    m = max(m, (int32_t)min(c, (uint64_t)0x7FFFFFFF));
+  }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
@@ -811,6 +855,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
             W.pk_count.p, W.pk_hbin.p, d_flag.p);
   // the largest table of the batch decides whether the block maps fit shared memory
   MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
+  MD_LAUNCH(ctx, k_max_candidates, std::min<uint32_t>(blocks(n), 64), 256, 0, W.cand_off.p, n_per ? W.dec_count.p : nullptr, n, d_flag.p + 3);
   int h_pre[4] = {0, 0, 0, 0};
   MD_CUDA(cudaMemcpyAsync(h_pre, d_flag.p, sizeof(h_pre), cudaMemcpyDeviceToHost, ctx->stream));
   // ---- K4
@@ -834,7 +879,20 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   MD_REQUIRE(!h_pre[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
   if (want_all) { W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1); }
-  const uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->n_sm);
+  // Few spectra with very many candidates each (open searches) would leave SMs idle and make one CTA walk hundreds of
+  // chunks: split every spectrum into `parts` work items (contiguous ranges of candidate chunks; each builds the table
+  // itself, which is cheap beside the chunks), about two items per SM.  MD_SCORE_SPLIT_MIN = candidates per spectrum
+  // (batch average) from which that is done (tests lower it).
+  uint32_t parts = 1;
+  {
+    uint64_t n_cand = (uint64_t)n * n_per, split_min = 16ull * kCandChunk;
+    { uint64_t nt = 0; MD_CUDA(cudaMemcpyAsync(&nt, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream)); MD_CUDA(cudaStreamSynchronize(ctx->stream)); n_cand += nt; }
+    if (const char* env = getenv("MD_SCORE_SPLIT_MIN")) split_min = std::max<long long>(1, atoll(env));
+    if (n < (uint32_t)ctx->n_sm && p.top_k <= kFastTopK && n_cand / n >= split_min)
+      parts = std::min<uint32_t>(std::min<uint32_t>(8u, (2u * (uint32_t)ctx->n_sm + n - 1) / n), (uint32_t)((n_cand / n + kCandChunk - 1) / kCandChunk));
+    parts = std::max(parts, 1u);
+  }
+  const uint32_t grid = std::min<uint32_t>(n * parts, (uint32_t)ctx->n_sm);
   const uint32_t max_nblk = h_pre[2] >= 0 ? ((uint32_t)h_pre[2] + kXcorrOffset + 1 + kBlk - 1) / kBlk : 0;
   uint32_t gstride = 0;
   if (max_nblk > kMapCap && max_nblk <= (kMaxBins >> kBlkShift)) {   // block maps of this batch do not fit shared memory
@@ -854,16 +912,22 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   A.tscore = want_all ? W.tscore.p : nullptr; A.dscore = want_all ? W.dscore.p : nullptr; A.psm = psm_dev; A.work = work.p; A.stat64 = W.stat64.p;
   A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
   A.gmap = gstride ? W.gmap.p : nullptr; A.gbits = gstride ? W.gbits.p : nullptr; A.gmap_stride = gstride;
+  A.parts = parts; A.part_top = nullptr; A.parts_done = nullptr;
+  if (parts > 1) {
+    W.part_top.need((size_t)n * parts * kFastTopK); W.parts_done.need(n);
+    MD_CUDA(cudaMemsetAsync(W.parts_done.p, 0, n * sizeof(uint32_t), ctx->stream));
+    A.part_top = W.part_top.p; A.parts_done = W.parts_done.p;
+  }
   const size_t smem = (size_t)kTileBins * sizeof(int32_t) + (size_t)kCandChunk * sizeof(int64_t) + 2 * (size_t)kPeakCap * 8 + (size_t)kCandChunk * 2 +
                       ((size_t)kMapCap + 2) * 2;
   MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
-  if (has_var) {
-    MD_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MD_LAUNCH(ctx, k_score<true>, grid, kScoreThreads, smem, A, C);
-  } else {
-    MD_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MD_LAUNCH(ctx, k_score<false>, grid, kScoreThreads, smem, A, C);
-  }
+  auto launch = [&](auto kernel) {
+    MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MD_LAUNCH(ctx, kernel, grid, kScoreThreads, smem, A, C);
+  };
+  const bool single = parts == 1 && h_pre[3] <= (int)kCandChunk;     // every spectrum fits one chunk of candidates
+  if (has_var) { if (parts > 1) launch(k_score<true, 2>); else if (single) launch(k_score<true, 0>); else launch(k_score<true, 1>); }
+  else { if (parts > 1) launch(k_score<false, 2>); else if (single) launch(k_score<false, 0>); else launch(k_score<false, 1>); }
   MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
   unsigned long long h_stat[2] = {0, 0};
   int h_flag[2] = {0, 0};

@@ -296,10 +296,12 @@ def _dense_spectra(n, n_peaks, seed=1):
     return maxdecoy.Spectra(sp.precursor_mz, sp.charge, np.array(off, dtype=np.uint64), np.concatenate(mzs), np.concatenate(ints))
 
 
-@pytest.mark.parametrize("case", ["wide_window_chunked", "top_k_generic", "dense_peaks", "low_res_bins", "high_charge", "few_peaks_and_empty"])
-def test_identify_kernel_paths(gpu, cpu, case):
+@pytest.mark.parametrize("case", ["wide_window_chunked", "wide_window_running_lists", "wide_window_split", "top_k_generic", "dense_peaks", "low_res_bins", "high_charge",
+                                  "few_peaks_and_empty"])
+def test_identify_kernel_paths(gpu, cpu, case, monkeypatch):
     """The branches of k_score the 10-ppm / top-5 cases never reach: candidate chunks beyond shared memory with the
-    generic top-k merge, top_k > 8, spectra whose binned peaks do not fit shared memory, 1.0005-Da bins (one tile),
+    generic top-k merge, the same with per-warp running top-k lists (top_k <= 8), spectra split into parts over several CTAs
+    (what an open search over few spectra does), top_k > 8, spectra whose binned peaks do not fit shared memory, 1.0005-Da bins (one tile),
     fragment charges up to 3, and spectra that are not scored at all."""
     for e in (gpu, cpu):
         _setup(e, 600, 2, (synth.CAM, synth.OXM), 2)
@@ -307,6 +309,11 @@ def test_identify_kernel_paths(gpu, cpu, case):
     kw = dict(n_decoys=30, seed=9, top_k=5)
     if case == "wide_window_chunked":
         kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=12)     # thousands of targets per spectrum
+    elif case == "wide_window_running_lists":
+        kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=5)
+    elif case == "wide_window_split":
+        kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=8)
+        monkeypatch.setenv("MD_SCORE_SPLIT_MIN", "1")
     elif case == "top_k_generic":
         kw.update(top_k=40)
     elif case == "dense_peaks":
@@ -330,8 +337,8 @@ def test_identify_kernel_paths(gpu, cpu, case):
     assert np.array_equal(offg, offc) and np.array_equal(scg, scc)
     for f in ("spectrum_id", "rank", "is_decoy", "charge", "candidate", "var_mask", "mod_weight", "raw_score", "score", "n_targets", "n_decoys"):
         assert np.array_equal(pg[f], pc[f]), f
-    if case == "wide_window_chunked":
-        assert int(np.diff(offg).max()) > 1536              # more candidates than one shared-memory chunk
+    if case.startswith("wide_window"):
+        assert int(np.diff(offg).max()) > 2 * 1536          # more candidates than two shared-memory chunks
     if case == "few_peaks_and_empty":
         assert np.all(pg["rank"][[0, 5, 6]] == 0) and np.any(pg["rank"][1] > 0)
     # without the per-candidate score output the PSM rows must be the same
