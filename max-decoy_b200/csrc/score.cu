@@ -659,6 +659,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         }
       }
       __syncthreads();
+      MD_TICK(6);
     };
     const bool one_tile = nact <= kTileBlocks;   // the usual case: the table is built once and serves every chunk of candidates
     const uint32_t c_lo = MODE == 2 ? mt.c_lo : 0u, c_hi = MODE == 2 ? mt.c_hi : ncand;     // this work item's candidates (the whole spectrum unless it was split)
@@ -938,10 +939,10 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   if (timing) {
     unsigned long long t[8];
     MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
-    double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
-    static const char* names[6] = {"stage+blocks", "sort", "map+zero", "differences", "scan+score", "topk"};
+    double tot = 0; for (int k = 0; k < 7; k++) tot += (double)t[k];
+    static const char* names[7] = {"stage+blocks", "sort", "map+zero", "differences", "score", "topk", "scan"};
     fprintf(stderr, "[md_score_timing] grid=%u", grid);
-    for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.1f%%", names[k], 100.0 * (double)t[k] / tot);
+    for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%.1f%%", names[k], 100.0 * (double)t[k] / tot);
     fprintf(stderr, " cycles/CTA=%.0f\n", tot / grid);
   }
   MD_REQUIRE(!h_flag[1], MD_ERR_UNSUPPORTED, "a spectrum needs more than 2^26 fragment bins or has more than 2^24 candidates");
