@@ -580,11 +580,14 @@ void launch_random(md_ctx* ctx, int vmode, uint32_t grid, const RandomArgs& RA, 
 }
 template <class MaskT>
 int random_occupancy(int vmode) {
+  static int cached[3] = {0, 0, 0};     // (a property of the kernel image: queried once per process)
+  if (cached[vmode]) return cached[vmode];
   int occ = 0;
   if (vmode == 0) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<0, MaskT>, kThreads, 0));
   else if (vmode == 1) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<1, MaskT>, kThreads, 0));
   else MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<2, MaskT>, kThreads, 0));
-  return occ > 0 ? occ : 1;
+  cached[vmode] = occ > 0 ? occ : 1;
+  return cached[vmode];
 }
 
 DecoyTables make_tables(const ModTables& M) {
@@ -698,14 +701,22 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaMemcpyAsync(count.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  // spectra in ascending precursor mass: neighbouring attempts grow sequences of similar length (lockstep passes)
+  // spectra in (roughly) ascending precursor mass: neighbouring attempts grow sequences of similar length (lockstep passes)
   std::vector<uint32_t> by_mass(n);
   {
     std::vector<md_precursor> hp(n);
     MD_CUDA(cudaMemcpyAsync(hp.data(), W.prec.p, n * sizeof(md_precursor), cudaMemcpyDeviceToHost, ctx->stream));
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t s = 0; s < n; s++) by_mass[s] = s;
-    std::stable_sort(by_mass.begin(), by_mass.end(), [&](uint32_t a, uint32_t b) { return hp[a].mass < hp[b].mass; });
+    // (the order only steers which attempts run side by side, not the results: a counting sort into 4096 mass buckets is
+    // as good as an exact sort and costs microseconds instead of half a millisecond of host time per call)
+    int64_t mlo = INT64_MAX, mhi = INT64_MIN;
+    for (uint32_t s = 0; s < n; s++) { mlo = std::min(mlo, hp[s].mass); mhi = std::max(mhi, hp[s].mass); }
+    constexpr uint32_t kBuckets = 4096;
+    const double scale = mhi > mlo ? (double)(kBuckets - 1) / (double)(mhi - mlo) : 0.0;
+    std::vector<uint32_t> head(kBuckets + 1, 0), bucket(n);
+    for (uint32_t s = 0; s < n; s++) { bucket[s] = (uint32_t)((double)(hp[s].mass - mlo) * scale); head[bucket[s] + 1]++; }
+    for (uint32_t b = 0; b < kBuckets; b++) head[b + 1] += head[b];
+    for (uint32_t s = 0; s < n; s++) by_mass[head[bucket[s]]++] = s;
   }
   for (uint32_t s = 0; s < n; s++) {
     uint64_t c = md_attempt_cap(n_per);
