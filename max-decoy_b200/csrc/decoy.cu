@@ -487,17 +487,38 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
     for (uint32_t m = keepbits; m; m &= m - 1) { if (o < nk) s_list[o] = (uint16_t)(cb + (uint32_t)__ffs(m) - 1u); o++; }
   }
   __syncthreads();
-  // copy the kept rows (four lanes per row) and their scalars
-  for (uint32_t t = tid; t < nk * 4u; t += 256) {
-    const uint32_t r = t >> 2, q = t & 3u;
-    const uint64_t src = a0 + s_list[r], dst = dbase + have + r;
-    *reinterpret_cast<uint4*>(dec_rows + md_dec_byte(n_slots, dst, q * 16u)) = __ldg(reinterpret_cast<const uint4*>(A.rows + src * MD_DECOY_ROW) + q);
+  // copy the kept rows (four lanes per row) and their scalars; loads are issued four at a time before their stores (the
+  // compiler may not move a load above a store through these pointers, and one row per round trip to HBM is what made
+  // this phase two thirds of the kernel)
+  for (uint32_t t0 = tid; t0 < nk * 4u; t0 += 4u * 256u) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t t = t0 + (uint32_t)j * 256u;
+      if (t < nk * 4u) v[j] = __ldg(reinterpret_cast<const uint4*>(A.rows + (uint64_t)(a0 + s_list[t >> 2]) * MD_DECOY_ROW) + (t & 3u));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t t = t0 + (uint32_t)j * 256u;
+      if (t < nk * 4u) *reinterpret_cast<uint4*>(dec_rows + md_dec_byte(n_slots, dbase + have + (t >> 2), (t & 3u) * 16u)) = v[j];
+    }
   }
-  for (uint32_t r = tid; r < nk; r += 256) {
-    const uint32_t a = s_list[r];
-    const uint64_t src = a0 + a, dst = dbase + have + r;
-    dec_len[dst] = A.len[src]; dec_mask[dst] = A.mask[src]; dec_w[dst] = A.w[src]; dec_hash[dst] = A.hash[src];
-    dec_attempt[dst] = att_base[li] + a;
+  for (uint32_t r0 = tid; r0 < nk; r0 += 2u * 256u) {
+    uint8_t ln[2]; uint64_t mk[2], hs[2]; int64_t wt[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t r = r0 + (uint32_t)j * 256u;
+      if (r < nk) { const uint64_t src = a0 + s_list[r]; ln[j] = A.len[src]; mk[j] = A.mask[src]; wt[j] = A.w[src]; hs[j] = A.hash[src]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t r = r0 + (uint32_t)j * 256u;
+      if (r < nk) {
+        const uint64_t dst = dbase + have + r;
+        dec_len[dst] = ln[j]; dec_mask[dst] = mk[j]; dec_w[dst] = wt[j]; dec_hash[dst] = hs[j];
+        dec_attempt[dst] = att_base[li] + s_list[r];
+      }
+    }
   }
   if (tid == 0) dec_count[s] = have + nk;
 }

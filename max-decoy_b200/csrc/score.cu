@@ -876,7 +876,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     if (c < MD_NCODES && ctx->mods.has_var[c]) has_var = true;
   }
   uint64_t n_targets = 0;
-  if (want_all) MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MD_CUDA(cudaMemcpyAsync(&n_targets, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   MD_REQUIRE(!h_pre[0], MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
   if (want_all) { W.tscore.need(n_targets + 1); W.dscore.need((size_t)n * n_per + 1); }
@@ -887,7 +887,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   uint32_t parts = 1;
   {
     uint64_t n_cand = (uint64_t)n * n_per, split_min = 16ull * kCandChunk;
-    { uint64_t nt = 0; MD_CUDA(cudaMemcpyAsync(&nt, W.cand_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream)); MD_CUDA(cudaStreamSynchronize(ctx->stream)); n_cand += nt; }
+    n_cand += n_targets;
     if (const char* env = getenv("MD_SCORE_SPLIT_MIN")) split_min = std::max<long long>(1, atoll(env));
     if (n < (uint32_t)ctx->n_sm && p.top_k <= kFastTopK && n_cand / n >= split_min)
       parts = std::min<uint32_t>(std::min<uint32_t>(8u, (2u * (uint32_t)ctx->n_sm + n - 1) / n), (uint32_t)((n_cand / n + kCandChunk - 1) / kCandChunk));
