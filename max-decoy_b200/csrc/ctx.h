@@ -68,7 +68,7 @@ struct IdentifyWorkspace {
   DevBuf<uint8_t> cub_tmp;
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
   DevBuf<uint64_t> t_size; DevBuf<int16_t> t_K; DevBuf<uint32_t> t_flag, t_pos; DevBuf<int> t_ovf, t_unsorted;
-  DevBuf<uint32_t> t_list, t_off, t_base, t_queue, t_spill;
+  DevBuf<uint32_t> t_list, t_off, t_base, t_queue, t_spill, t_blk;
   DevBuf<md_precursor> t_win;        // MD_VARMOD_EXPANDED: shifted windows, one per (spectrum, count vector)
   // exhaustive mode
   DevBuf<int32_t> ex_comp; DevBuf<uint64_t> ex_cum; DevBuf<uint32_t> ex_ncomp;

@@ -86,6 +86,13 @@ __device__ void store_attempt(const AttemptOut& O, uint64_t slot, const TSeq& se
 }
 
 // work item -> (list entry, attempt ordinal) by binary search on the round's prefix of attempt counts
+// the same with a coarse table: blk[b] = entry of work item b << kBlkLog (the search runs between two neighbouring table values)
+constexpr uint32_t kBlkLog = 10;
+__device__ __forceinline__ uint32_t find_entry_coarse(const uint32_t* __restrict__ att_off, const uint32_t* __restrict__ blk, uint32_t w) {
+  uint32_t lo = blk[w >> kBlkLog], hi = blk[(w >> kBlkLog) + 1] + 1u;   // att_off[lo] <= w < att_off[hi]
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (att_off[mid] <= w) lo = mid; else hi = mid; }
+  return lo;
+}
 __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ att_off, uint32_t n_list, uint32_t w) {
   uint32_t lo = 0, hi = n_list;
   while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (att_off[mid] <= w) lo = mid; else hi = mid; }
@@ -173,6 +180,7 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
 
 struct RandomArgs {
   const md_precursor* prec; const uint32_t* list; const uint32_t* att_off; const uint32_t* att_base;
+  const uint32_t* att_blk;              // coarse index into att_off (find_entry_coarse)
   uint32_t n_list, total;
   uint32_t* queue;                       // work counter of this launch
   const uint32_t* remap; const uint32_t* remap_n;   // wide pass: work item -> attempt (the narrow pass's spill list), or NULL
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
         if (q >= total) drained = true;
         else {
           wi = A.remap ? A.remap[q] : q;
-          const uint32_t li = find_entry(A.att_off, A.n_list, wi);
+          const uint32_t li = find_entry_coarse(A.att_off, A.att_blk, wi);
           const md_precursor pr = A.prec[A.list[li]];
           P = pr.mass;
           rng.start(A.seed, pr.spectrum_id, A.att_base[li] + (wi - A.att_off[li]));
@@ -758,7 +766,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   DevBuf<int>& d_ovf = W.t_ovf;
   d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(4); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
-  std::vector<uint32_t> list, off, base;
+  std::vector<uint32_t> list, off, base, blk;
   for (int round = 0; round < 64; round++) {
     list.clear(); off.assign(1, 0); base.clear();
     // How many attempts each unfinished spectrum gets this round.  A spectrum's decoys are its first n distinct successes
@@ -801,7 +809,19 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       MD_CUDA(cudaMemsetAsync(d_queue.p, 0, 4 * sizeof(uint32_t), ctx->stream));
       W.t_spill.need((size_t)total + 1);
       RandomArgs RA;
-      RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total;
+      {   // coarse index: entry of every 1024th work item (+ one past the end)
+        const uint32_t nb = (total >> kBlkLog) + 2;
+        blk.resize(nb);
+        uint32_t e = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+          const uint64_t w0 = std::min<uint64_t>((uint64_t)b << kBlkLog, total - 1);
+          while (e + 1 < n_list && off[e + 1] <= w0) e++;
+          blk[b] = e;
+        }
+        W.t_blk.need(nb);
+        MD_CUDA(cudaMemcpyAsync(W.t_blk.p, blk.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total; RA.att_blk = W.t_blk.p;
       RA.seed = seed; RA.overflow = d_ovf.p;
       if (!wide_only) {
         RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = W.t_spill.p; RA.spill_n = d_queue.p + 1;
