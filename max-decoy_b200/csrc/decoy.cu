@@ -407,11 +407,17 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
   const uint64_t t0 = cand_off[s], nt = cand_off[s + 1] - t0;
   if (nt == 0) { O.len[wi] = 0; return; }
   const uint64_t c = t0 + attempt % nt;
-  // the reference tests the shuffled sequence with fixed modifications only (:278-279)
-  if (cand_mask[c] != 0 || !md_in_window(cand_w[c], pr.lo, pr.hi)) { O.len[wi] = 0; return; }
   const uint64_t d = cand_desc[c];
   const uint8_t* row = idx_rows + (d & 0xFFFFFFFFFFull) * 16;
   const uint32_t L = (uint32_t)(d >> 40) & 0xFF;
+  // the reference tests the shuffled sequence with fixed modifications only (:278-279): the candidate's weight without
+  // the variable modifications it was found with (a permutation keeps the weight)
+  int64_t wfix = cand_w[c];
+  for (uint64_t m = cand_mask[c]; m; m &= m - 1) {
+    const int a = md_alpha_of_code(row[__ffsll((long long)m) - 1]);
+    if (a >= 0) wfix -= T.var_a[a];
+  }
+  if (!md_in_window(wfix, pr.lo, pr.hi)) { O.len[wi] = 0; return; }
   bool ok = true;
   for (uint32_t i = 0; i < L; i++) {
     int a = md_alpha_of_code(row[i]);
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
     uint32_t j = rng.below(i);
     uint8_t a = seq.at(i - 1); seq.at(i - 1) = seq.at(j); seq.at(j) = a;
   }
-  store_attempt(O, wi, seq, L, 0, cand_w[c], T, PV);
+  store_attempt(O, wi, seq, L, 0, wfix, T, PV);
 }
 
 // One CTA per listed spectrum: keep the successes of this round that are new (not equal to an accepted decoy or to an
