@@ -1,5 +1,5 @@
 """Randomized parity stress (GPU vs oracle; test infrastructure, run by tests/test_gpu_stress.py): decoys, candidates and identify over random seeds, modification
-sets, decoy counts, windows and batch sizes.  python tools/gpu_stress.py [rounds]"""
+sets, decoy counts, windows and batch sizes.  python tools/gpu_stress.py [rounds [seed]]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "max-decoy_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,7 @@ from maxdecoy import SearchParams, synth, Modification
 from oracle_lib import oracle_engine
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-rng = np.random.default_rng(2026)
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 gpu, cpu = maxdecoy.Engine(), oracle_engine(8)
 extra = [Modification("x:21", "Phospho", "A", False, "S", 79.966331), Modification("x:7", "Deamid", "A", False, "N", 0.984016),
          Modification("x:9", "FixK", "A", True, "K", 8.014199)]
