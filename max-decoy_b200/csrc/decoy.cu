@@ -773,13 +773,14 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(4); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   std::vector<uint32_t> list, off, base, blk;
+  const double later_factor = getenv("MD_DECOY_LATER_PCT") ? std::max(100, atoi(getenv("MD_DECOY_LATER_PCT"))) / 100.0 : 1.05;   // head room of the later rounds (swept on C2: 100..180 %)
   const uint32_t want0_pct = getenv("MD_DECOY_WANT0_PCT") ? (uint32_t)std::max(100, atoi(getenv("MD_DECOY_WANT0_PCT"))) : 110u;   // round 0 asks for n * 1.10 + 32 attempts (swept on C2: 100..160 %)
   for (int round = 0; round < 64; round++) {
     list.clear(); off.assign(1, 0); base.clear();
     // How many attempts each unfinished spectrum gets this round.  A spectrum's decoys are its first n distinct successes
     // in attempt order, so asking for too many only wastes work; asking for too few costs another round, and a round
     // never takes less than one 100-try attempt (~0.3 ms) however small it is.  Round 0 asks for 1.1 n + 32; later rounds use
-    // the spectrum's own yield with 30 % head room, and rounds too small to fill the GPU ask for up to 4x that.
+    // the spectrum's own yield with 5 % head room (their attempts are the expensive ones: hard spectra), and rounds too small to fill the GPU ask for up to 4x that.
     std::vector<uint32_t> wants;
     uint64_t sum = 0;
     for (uint32_t si = 0; si < n; si++) {
@@ -789,7 +790,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       if (used[s] == 0) { const uint32_t rem = n_per - count[s]; want = (uint32_t)((uint64_t)rem * want0_pct / 100u) + 32; }
       else {
         double yield = std::max(0.02, (double)count[s] / (double)used[s]);
-        want = (uint32_t)((double)(n_per - count[s]) / yield * 1.3) + 48;
+        want = (uint32_t)((double)(n_per - count[s]) / yield * later_factor) + 48;
       }
       want = std::min<uint32_t>({want, (uint32_t)kMaxRoundAttempts, cap[s] - used[s]});
       list.push_back(s); wants.push_back(want); sum += want;
