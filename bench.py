@@ -2,7 +2,7 @@
 """bench.py -- spectra/s and candidates scored/s of the MaxDecoy identification hot path on B200.
 
 A step = one pass of the hot path (precursor windows -> index window search -> ModifiedPeptide filter ->
-decoy generation -> fragment scoring -> top-k PSM rows [-> NCCL gather of the PSM tables]) over one batch of
+decoy generation -> fragment scoring -> top-k PSM rows [-> gather of the PSM tables over NCCL]) over one batch of
 synthetic spectra, against the peptide index that `digest` + `index_build` left resident in HBM (the
 reference keeps that state in PostgreSQL between its `digest` and `identification` subcommands).
 
@@ -10,8 +10,11 @@ reference keeps that state in PostgreSQL between its `digest` and `identificatio
   python bench.py --impl reference [...]                     the CPU arm: the oracle port of the reference's
                                                              algorithm on the host cores (the Rust reference cannot be
                                                              built here: no cargo/PostgreSQL/Comet)
-N > 1 is launched by torchrun (one rank per GPU); spectra are sharded (weak scaling: every rank gets its own
-batch), the index is replicated, and the only collective is the all_gather of the PSM tables.
+N > 1 is launched by torchrun (one rank per GPU).  The headline value is weak scaling (every rank searches its own
+10k-spectrum batch of the C2 workload, index replicated); the PSM tables are gathered by the library itself
+(md_comm_init / md_gather_psms: NCCL on the library's comm stream).  The same run also measures C4 -- ONE fixed set of
+100k spectra dealt over the ranks by parallel.partition_spectra (strong scaling) -- and checks the gathered table against
+the table one GPU computes alone (`c4_strong` in the JSON line).
 """
 import argparse
 import json
@@ -20,6 +23,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "max-decoy_b200"))
@@ -37,8 +41,12 @@ CONFIGS = {
     "c5": dict(n_proteins=20000, mc=2, n_spectra=64, ppm=10, var=False, n_decoys=0, abs_da=500,
                text="C5 (one GPU's share): +-500 Da open search over the 20k-protein index, ~1M candidates per spectrum, targets only"),
 }
+# BASELINE.json configs[3]: the C2 index, ONE set of 100k spectra sharded over the ranks
+C4_SPECTRA = 100000
+C4_CHUNK = 10000
 TOP_K = 5
 FRAG_TOL = 0.02
+SEED0 = 7
 
 
 def load_peaks():
@@ -113,7 +121,7 @@ def make_workload(cfg, rank, n_spectra):
     from maxdecoy import synth
     prots = synth.synthetic_proteins(cfg["n_proteins"])
     mods = [synth.CAM, synth.OXM] if cfg["var"] else [synth.CAM]
-    sp, _ = synth.synthetic_spectra(prots, n_spectra, cfg["mc"], mods=tuple(mods), seed=7 + 1000 * rank)
+    sp, _ = synth.synthetic_spectra(prots, n_spectra, cfg["mc"], mods=tuple(mods), seed=SEED0 + 1000 * rank)
     return prots, mods, sp
 
 
@@ -124,36 +132,48 @@ def search_params(cfg):
                         top_k=TOP_K, min_peaks=10, max_fragment_charge=3, abs_lower_uda=a, abs_upper_uda=a)
 
 
-def cpu_identify(cfg, prots, mods, sp, sample, threads, repeats=1):
-    """The oracle (CPU port of the reference's algorithm) on the first `sample` spectra; returns (spectra/s, pairs/s, stats)."""
+def config_of(cfg, n_spec, world):
+    """The `config` object of the JSON line -- the same for both arms (the CPU arm times a bounded sample of it)."""
+    return {"workload": cfg["text"], "spectra_per_gpu": n_spec, "proteins": cfg["n_proteins"], "fragment_tolerance_da": FRAG_TOL, "top_k": TOP_K,
+            "l2": "flushed (256 MiB write) before every timed step; flush not timed",
+            "parallelism": "spectra sharded x%d (one batch per rank), index replicated, PSM all-gather per batch by md_gather_psms "
+                           "(NCCL on the library's comm stream: overlaps the next batch)" % world}
+
+
+def psm_crc(table):
+    """CRC-32 of the PSM rows in spectrum order -- every field except `score`'s padding is integer and reproducible."""
+    import numpy as np
+    return zlib.crc32(np.ascontiguousarray(table).tobytes()) & 0xFFFFFFFF
+
+
+def cpu_identify(cfg, prots, mods, sp, sample, threads):
+    """The oracle (CPU port of the reference's algorithm) on the first `sample` spectra; returns (spectra/s, pairs/s, psms, n)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import oracle_engine
     import numpy as np
     e = oracle_engine(threads)
-    t0 = time.time()
     e.digest(prots, cfg["mc"], 5, 50)
     e.set_modifications(mods, 3 if cfg["var"] else 0)
     e.index_build()
-    t_index = time.time() - t0
     sub = sp.subset(np.arange(min(sample, len(sp))))
-    best = None
-    for _ in range(repeats):
-        t0 = time.time()
-        _, st = e.identify(sub, search_params(cfg))
-        dt = time.time() - t0
-        if best is None or dt < best[0]:
-            best = (dt, st)
-    dt, st = best
+    t0 = time.time()
+    psms, st = e.identify(sub, search_params(cfg))
+    dt = time.time() - t0
     e.close()
-    return len(sub) / dt, (st["n_targets"] + st["n_decoys"]) / dt, st, t_index, len(sub)
+    return len(sub) / dt, (st["n_targets"] + st["n_decoys"]) / dt, psms, len(sub)
 
 
 def run_reference(args, cfg, rank, world):
+    """--impl reference: the CPU port on all host threads, each step = the first `--ref-sample` spectra of rank 0's batch
+    of the same workload (the same spectra our arm searches first)."""
     if rank != 0:
         return
+    import numpy as np
     threads = os.cpu_count() or 1
-    sample = args.ref_sample
-    prots, mods, sp = make_workload(cfg, 0, sample)
+    n_spec = args.spectra or cfg["n_spectra"]
+    sample = min(args.ref_sample, n_spec)
+    prots, mods, sp = make_workload(cfg, 0, n_spec)
+    sp = sp.subset(np.arange(sample))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import oracle_engine
     e = oracle_engine(threads)
@@ -165,18 +185,21 @@ def run_reference(args, cfg, rank, world):
         e.identify(sp, prm)
     t0 = time.time()
     pairs = 0
+    psms = None
     for _ in range(args.steps):
-        _, st = e.identify(sp, prm)
+        psms, st = e.identify(sp, prm)
         pairs += st["n_targets"] + st["n_decoys"]
     dt = time.time() - t0
+    e.close()
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": "spectra_per_sec", "value": v, "unit": "spectra/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "candidates_per_sec": pairs / dt,
-            "config": {"workload": cfg["text"], "fragment_tolerance_da": FRAG_TOL, "top_k": TOP_K},
+            "config": config_of(cfg, n_spec, world),
+            "psm_crc_sample": psm_crc(psms) if psms is not None else None,
             "cpu_baseline": {"value": v, "unit": "spectra/s", "cores": threads, "kind": "port",
-                             "sample": "%d spectra of the workload per step, %d host threads; CPU oracle port of the reference's algorithm with an in-memory "
-                                       "mass-sorted index (the Rust reference needs cargo + PostgreSQL + Comet, none present)" % (sample, threads)},
+                             "sample": "the first %d spectra of rank 0's batch of the workload per step, %d host threads over spectra; CPU oracle port of the "
+                                       "reference's algorithm with an in-memory mass-sorted index (the Rust reference needs cargo + PostgreSQL + Comet, none present)" % (sample, threads)},
             "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -202,6 +225,48 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+# ------------------------------------------------------------------------------------------------ C4 data
+def _c4_chunk(job):
+    cfg, c, n = job
+    _, _, sp = make_workload(cfg, c, n)
+    return sp.precursor_mz, sp.charge, sp.peak_off, sp.peak_mz, sp.peak_intensity
+
+
+def c4_path(n_total):
+    return "/dev/shm/md_bench_c4_%s_%d.npz" % (os.environ.get("MASTER_PORT", "solo%d" % os.getpid()), n_total)
+
+
+def c4_generate(cfg, n_total, path):
+    """Rank 0, before CUDA is touched (the generator forks workers): the C4 set = chunks of 10k spectra, chunk c drawn with
+    the seed rank c uses in the weak-scaling run, concatenated; written to /dev/shm for the other ranks."""
+    import multiprocessing as mp
+    import numpy as np
+    jobs = [(cfg, c, min(C4_CHUNK, n_total - c * C4_CHUNK)) for c in range((n_total + C4_CHUNK - 1) // C4_CHUNK)]
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        parts = pool.map(_c4_chunk, jobs)
+    off = [np.zeros(1, dtype=np.uint64)]
+    base = 0
+    for p in parts:
+        off.append(p[2][1:] + np.uint64(base))
+        base += int(p[2][-1])
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, precursor_mz=np.concatenate([p[0] for p in parts]), charge=np.concatenate([p[1] for p in parts]), peak_off=np.concatenate(off),
+             peak_mz=np.concatenate([p[3] for p in parts]), peak_intensity=np.concatenate([p[4] for p in parts]))
+    os.replace(tmp, path)
+
+
+def c4_load(path, timeout=600):
+    import numpy as np
+    from maxdecoy import Spectra
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > timeout:
+            raise RuntimeError("C4 spectra never appeared at " + path)
+        time.sleep(0.2)
+    d = np.load(path)
+    return Spectra(d["precursor_mz"], d["charge"], d["peak_off"], d["peak_mz"], d["peak_intensity"])
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -215,6 +280,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512, help="spectra of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=128, help="spectra per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-spectra", type=int, default=-1, help="size of the strong-scaling set (default 100000 with --config c2, else 0 = skip)")
+    ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = dict(CONFIGS[args.config])
@@ -229,10 +296,17 @@ def main():
         return
 
     import numpy as np
+    n_c4 = 0 if args.no_c4 else (args.c4_spectra if args.c4_spectra >= 0 else (C4_SPECTRA if args.config == "c2" and not args.spectra else 0))
+    t0 = time.time()
+    if n_c4 and rank == 0:
+        c4_generate(cfg, n_c4, c4_path(n_c4))          # forks: before torch / CUDA
+    t_c4gen = time.time() - t0
+
     import torch
     import torch.distributed as dist
     import maxdecoy
-    from maxdecoy import _abi
+    from maxdecoy import _abi, parallel
+    import ctypes as C
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -250,77 +324,66 @@ def main():
     t0 = time.time(); eng.index_build(); t_index = time.time() - t0
     istats = eng.index_stats()
     prm = search_params(cfg)
+    # the library's own communicator (md_comm_init): rank 0 draws the id, torch.distributed only carries its 128 bytes
+    if world > 1:
+        box = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(rank, world, box[0])
 
     ext = torch.cuda.ExternalStream(eng.lib.md_stream_handle(eng.h), device=torch.device("cuda", local_rank))
-    # ---- device-resident inputs (value) and pinned host inputs (e2e)
+
     def as_torch(a):  # unsigned 32/64-bit arrays travel as their signed views (same bytes)
         if a.dtype == np.uint64:
             a = a.view(np.int64)
         elif a.dtype == np.uint32:
             a = a.view(np.int32)
         return torch.from_numpy(a).pin_memory()
-    host = {k: as_torch(getattr(sp, k)) for k in ("precursor_mz", "charge", "spectrum_id", "peak_off", "peak_mz", "peak_intensity")}
-    dev = {k: v.cuda(non_blocking=False) for k, v in host.items()}
-    sd = _abi.md_spectra()
-    sd.n = n_spec
-    for k in host:
-        setattr(sd, k, dev[k].data_ptr())
-    sh = _abi.md_spectra()
-    sh.n = n_spec
-    for k in host:
-        setattr(sh, k, host[k].data_ptr())
+
+    FIELDS = ("precursor_mz", "charge", "spectrum_id", "peak_off", "peak_mz", "peak_intensity")
+
+    def stage(spx):
+        """pinned host copies + device copies of a Spectra, and the md_spectra views of both"""
+        host = {k: as_torch(getattr(spx, k)) for k in FIELDS}
+        dev = {k: v.cuda(non_blocking=False) for k, v in host.items()}
+        sd, sh = _abi.md_spectra(), _abi.md_spectra()
+        sd.n = sh.n = len(spx)
+        for k in FIELDS:
+            setattr(sd, k, dev[k].data_ptr())
+            setattr(sh, k, host[k].data_ptr())
+        return host, dev, sd, sh
+
+    host, dev, sd, sh = stage(sp)
     psm_bytes = n_spec * TOP_K * 56
-    # PSM tables, double-buffered: the gather of one batch runs (NCCL's stream) while the next batch is searched
+    # PSM tables, double-buffered: the gather of one batch runs (comm stream) while the next batch is searched
     psm_devs = [torch.empty(psm_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
-    psm_alls = [torch.empty(psm_bytes * world, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    psm_dev = psm_devs[0]
-    gathers = [None, None]
+    psm_alls = [torch.empty(psm_bytes * world, dtype=torch.uint8, device="cuda") for _ in range(2)]
     tick = [0]
     psm_host = torch.empty(psm_bytes, dtype=torch.uint8).pin_memory()
+    psm_host_all = torch.empty(psm_bytes * world, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    import ctypes as C
     pc = prm.to_c()
-
-    def gather_async(k):
-        """all_gather of PSM buffer k, asynchronous: the library's stream goes on with the next batch; the buffer is
-        waited for before it is written again (two batches later) and at the end of the timed region."""
-        gathers[k] = dist.all_gather_into_tensor(psm_alls[k], psm_devs[k], async_op=True)
-
-    def drain_gathers():
-        for k in (0, 1):
-            if gathers[k] is not None:
-                gathers[k].wait()
-                gathers[k] = None
 
     def step_device():
         k = tick[0] & 1
         tick[0] += 1
-        if gathers[k] is not None:
-            gathers[k].wait()
-            gathers[k] = None
         st = eng.identify_device(sd, prm, psm_devs[k].data_ptr())
         if world > 1:
-            gather_async(k)
+            eng.gather_psms_device(psm_devs[k].data_ptr(), n_spec * TOP_K, psm_alls[k].data_ptr())
         return st
 
     def step_host():
-        k = tick[0] & 1
-        tick[0] += 1
         st = _abi.md_identify_stats()
         rc = eng.lib.md_identify(eng.h, C.byref(sh), C.byref(pc), C.c_void_p(psm_host.data_ptr()), C.byref(st), None, None)
         if rc != 0:
             raise RuntimeError(eng.lib.md_last_error(eng.h).decode())
         if world > 1:
-            if gathers[k] is not None:
-                gathers[k].wait()
-                gathers[k] = None
-            psm_devs[k].copy_(psm_host, non_blocking=True)
-            gather_async(k)
+            eng._ck(eng.lib.md_gather_psms(eng.h, C.c_void_p(psm_host.data_ptr()), n_spec * TOP_K, C.c_void_p(psm_host_all.data_ptr())))
         return eng._stats(st)
 
     def timed(fn, steps):
-        """K steps, each bracketed by CUDA events on the library's stream; L2 flushed (untimed) before each."""
+        """K steps, each bracketed by CUDA events on the library's stream; L2 flushed (untimed) before each.  The gathers
+        still in flight on the comm stream when the last step returns belong to the timed steps (md_sync)."""
         total_ms, last = 0.0, None
         with torch.cuda.stream(ext):
             for _ in range(steps):
@@ -331,13 +394,10 @@ def main():
                 b.record(ext)
                 b.synchronize()
                 total_ms += a.elapsed_time(b)
-            if world > 1:   # the gathers still in flight belong to the timed steps
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(ext)
-                drain_gathers()
-                b.record(ext)
-                b.synchronize()
-                total_ms += a.elapsed_time(b)
+            if world > 1:
+                t0 = time.perf_counter()
+                eng.sync()
+                total_ms += (time.perf_counter() - t0) * 1e3
         return total_ms, last
 
     def barrier():
@@ -352,12 +412,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
     clocks = ClockSampler(local_rank)
     clocks.start()
     with torch.cuda.stream(ext):
         for _ in range(args.warmup):
             step_device()
-        drain_gathers()
+        eng.sync()
     barrier()
     clocks.mark()
     wall0 = time.time()
@@ -366,36 +433,90 @@ def main():
     wall = time.time() - wall0
     clk = clocks.stop()
     ms_dev = max_over_ranks(ms_dev)
+    # the PSM table of the last timed step (gathered over all ranks), as the checksum of the run
+    last = (tick[0] - 1) & 1
+    table_all = (psm_alls[last] if world > 1 else psm_devs[last]).cpu().numpy().view(_abi.PSM_DTYPE).reshape(-1, TOP_K)
+    crc_all = psm_crc(table_all)
+    table_own = psm_devs[last].cpu().numpy().view(_abi.PSM_DTYPE).reshape(-1, TOP_K).copy()
 
     with torch.cuda.stream(ext):
         step_host()
-        drain_gathers()
     barrier()
     ms_e2e, st_h = timed(step_host, args.steps)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    e2e_same = bool(np.array_equal(psm_host.numpy().view(_abi.PSM_DTYPE).reshape(-1, TOP_K), table_own))
+    pairs_all = sum_over_ranks(st["n_pairs"])
 
-    pairs = st["n_pairs"]
-    if world > 1:
-        t = torch.tensor([pairs], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        pairs_all = float(t.item())
-    else:
-        pairs_all = float(pairs)
+    # ------------------------------------------------------------------------------------------ C4: strong scaling
+    c4 = None
+    if n_c4:
+        full = c4_load(c4_path(n_c4))
+        full.spectrum_id = np.arange(len(full), dtype=np.uint32)
+        sub, _ = parallel.shard(full, rank, world)
+        rows = parallel.padded_rows(len(full), world)
+        _, c4dev, c4sd, _ = stage(sub)
+        mine = torch.full((rows * TOP_K * 56,), 255, dtype=torch.uint8, device="cuda")   # padding rows: spectrum_id 0xFFFFFFFF
+        allr = torch.empty(rows * TOP_K * 56 * world, dtype=torch.uint8, device="cuda")
+
+        def c4_pass():
+            s = eng.identify_device(c4sd, prm, mine.data_ptr())
+            if world > 1:
+                eng.gather_psms_device(mine.data_ptr(), rows * TOP_K, allr.data_ptr())
+            eng.sync()
+            return s
+
+        with torch.cuda.stream(ext):
+            c4_pass()
+            barrier()
+            ms_c4, c4_steps, c4_st = 0.0, 2, None
+            for _ in range(c4_steps):
+                flush.fill_(1)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(ext)
+                c4_st = c4_pass()
+                b.record(ext)
+                b.synchronize()
+                ms_c4 += a.elapsed_time(b)
+        ms_c4 = max_over_ranks(ms_c4)
+        c4_pairs = sum_over_ranks(c4_st["n_pairs"])
+        gathered = (allr if world > 1 else mine).cpu().numpy().view(_abi.PSM_DTYPE)
+        c4 = {"workload": "C4: the C2 index, ONE set of %d spectra dealt over %d rank(s) by parallel.partition_spectra (mass-sorted blocks of 32), "
+                          "PSM tables gathered by md_gather_psms" % (len(full), world),
+              "scaling": "strong", "spectra": len(full), "value": len(full) * c4_steps / (ms_c4 / 1e3), "unit": "spectra/s", "ms_per_pass": ms_c4 / c4_steps,
+              "candidates_per_sec": c4_pairs * c4_steps / (ms_c4 / 1e3), "spectra_on_rank0": len(sub)}
+        if rank == 0:
+            table = parallel.drop_padding(gathered, TOP_K, len(full))
+            c4["psm_crc"] = psm_crc(table)
+            if world > 1:   # the same 100k spectra on this GPU alone must give the same table
+                _, _, fsd, _ = stage(full)
+                alone = torch.empty(len(full) * TOP_K * 56, dtype=torch.uint8, device="cuda")
+                with torch.cuda.stream(ext):
+                    eng.identify_device(fsd, prm, alone.data_ptr())
+                    eng.sync()
+                c4["psm_crc_single_gpu"] = psm_crc(alone.cpu().numpy().view(_abi.PSM_DTYPE).reshape(-1, TOP_K))
+                c4["crc_matches_single_gpu"] = c4["psm_crc_single_gpu"] == c4["psm_crc"]
+            try:
+                os.remove(c4_path(n_c4))
+            except OSError:
+                pass
+        barrier()
+
     def shutdown():
-        """Ordered teardown, then a hard exit: the library and torch/NCCL each own CUDA state whose static destructors
-        must not race at interpreter exit (seen as SIGSEGV after the result line with N > 1)."""
+        """Ordered teardown, then a normal return: the library's communicator and context go first, then torch's."""
+        eng.sync()
+        if world > 1:
+            eng.comm_destroy()
         eng.close()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
 
     if rank != 0:
         shutdown()
+        return
 
     peaks, peak_kind = load_peaks()
     total_spectra = n_spec * world
@@ -410,28 +531,32 @@ def main():
         "metric": "spectra_per_sec", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": cfg["text"], "spectra_per_gpu": n_spec, "proteins": cfg["n_proteins"], "unique_peptides": n_pep,
-                   "index_device_mb": round(istats["device_bytes"] / 1e6, 1), "fragment_tolerance_da": FRAG_TOL, "top_k": TOP_K,
-                   "l2": "flushed (256 MiB write) before every timed step; flush not timed", "parallelism": "spectra sharded x%d, index replicated, PSM all_gather per batch (asynchronous, double-buffered: overlaps the next batch)" % world},
+        "config": config_of(cfg, n_spec, world),
+        "index": {"unique_peptides": n_pep, "device_mb": round(istats["device_bytes"] / 1e6, 1)},
         "candidates_per_sec": pairs_all * args.steps / (ms_dev / 1e3),
         "pairs_per_step": pairs_all,
         "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
+        "psm_crc": crc_all, "psm_rows": int(table_all.shape[0] * table_all.shape[1]),
         "e2e": {"value": total_spectra * args.steps / (ms_e2e / 1e3), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(psm_bytes),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "psm_rows_equal_device_path": e2e_same},
         "roofline": {"kernel": "k_score (fused fragment-and-score + top-k)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": int(st["score_bytes"]), "launch_ms": st["ms_kernel_score"], "pairs_per_launch": int(st["n_pairs"]),
                      "note": "algorithmic bytes = sum over scored pairs of (14 + peptide length); the kernel is integer-issue / shared-memory-gather bound, see DESIGN.md section 5"},
         "stage_ms_per_step": {"lookup": st["ms_lookup"], "decoys": st["ms_decoys"], "score": st["ms_score"], "kernel_decoy_attempts": st["ms_kernel_decoy"],
                               "kernel_score": st["ms_kernel_score"], "decoy_attempts": int(st["n_attempts"])},
-        "one_time": {"digest_s": t_digest, "index_build_s": t_index, "synthetic_generation_s": t_gen},
+        "one_time": {"digest_s": t_digest, "index_build_s": t_index, "synthetic_generation_s": t_gen, "c4_generation_s": t_c4gen},
         "clocks": clk, "wall_s_timed_region": wall,
     }
+    if c4 is not None:
+        line["c4_strong"] = c4
     if world == 1 and not args.no_cpu_baseline:
-        v, pv, cst, _, ns = cpu_identify(cfg, prots, mods, sp, args.cpu_sample, os.cpu_count() or 1)
-        line["cpu_baseline"] = {"value": v, "unit": "spectra/s", "cores": os.cpu_count() or 1, "kind": "port", "candidates_per_sec": pv,
+        ncores = os.cpu_count() or 1
+        v, pv, cpsm, ns = cpu_identify(cfg, prots, mods, sp, args.cpu_sample, ncores)
+        line["cpu_baseline"] = {"value": v, "unit": "spectra/s", "cores": ncores, "kind": "port", "candidates_per_sec": pv,
+                                "psm_rows_equal_gpu": bool(all(np.array_equal(cpsm[f], table_own[:ns][f]) for f in ("rank", "is_decoy", "candidate", "raw_score", "var_mask", "mod_weight"))),
                                 "sample": "first %d spectra of the same workload, one pass, %d host threads over spectra; CPU oracle port with an in-memory "
-                                          "mass-sorted index (favourable to the CPU: the real reference adds PostgreSQL round trips and an external Comet run)" % (ns, os.cpu_count() or 1)}
+                                          "mass-sorted index (favourable to the CPU: the real reference adds PostgreSQL round trips and an external Comet run)" % (ns, ncores)}
     emit(line)
     shutdown()
 

@@ -17,6 +17,7 @@ pub enum md_ctx {}
     pub seq: *mut u8, pub seq_off: *mut u64, pub missed_cleavages: *mut u8, pub weight: *mut i64,
     pub counts: *mut i16, pub assoc_off: *mut u64, pub assoc_protein: *mut u32,
 }
+#[repr(C)] pub struct md_index_stats { pub n_peptides: u64, pub seq_bytes: u64, pub device_bytes: u64, pub min_key: i64, pub max_key: i64 }
 #[repr(C)] pub struct md_precursor { pub mass: i64, pub lo: i64, pub hi: i64, pub charge: u32, pub spectrum_id: u32 }
 #[repr(C)] pub struct md_candidate_table {
     pub n_spectra: u32, pub n: u64, pub off: *mut u64, pub peptide_id: *mut u64, pub var_mask: *mut u64, pub mod_weight: *mut i64,
@@ -48,6 +49,7 @@ extern "C" {
     pub fn md_create(cfg: *const md_config, out: *mut *mut md_ctx) -> c_int;
     pub fn md_destroy(ctx: *mut md_ctx);
     pub fn md_last_error(ctx: *const md_ctx) -> *const c_char;
+    pub fn md_backend_name() -> *const c_char;
     pub fn md_residue_mass(one_letter_code: u8) -> i64;
     pub fn md_sequence_weight(seq: *const u8, len: u32) -> i64;
     pub fn md_precursor_window(mz: f64, charge: u32, lower_ppm: i64, upper_ppm: i64, p: *mut i64, lo: *mut i64, hi: *mut i64) -> c_int;
@@ -58,6 +60,8 @@ extern "C" {
     pub fn md_peptides_export(ctx: *mut md_ctx, out: *mut md_peptide_table) -> c_int;
     pub fn md_peptide_table_free(t: *mut md_peptide_table);
     pub fn md_index_build(ctx: *mut md_ctx) -> c_int;
+    pub fn md_index_stats_get(ctx: *mut md_ctx, out: *mut md_index_stats) -> c_int;
+    pub fn md_index_export(ctx: *mut md_ctx, begin: u64, count: u64, peptide_id: *mut u64, key: *mut i64) -> c_int;
     pub fn md_window_search(ctx: *mut md_ctx, lo: *const i64, hi: *const i64, n: u32, begin: *mut u64, end: *mut u64) -> c_int;
     pub fn md_candidates(ctx: *mut md_ctx, p: *const md_precursor, n: u32, out: *mut md_candidate_table) -> c_int;
     pub fn md_candidate_table_free(t: *mut md_candidate_table);
@@ -68,6 +72,14 @@ extern "C" {
     pub fn md_decoy_table_free(t: *mut md_decoy_table);
     pub fn md_identify(ctx: *mut md_ctx, spectra: *const md_spectra, params: *const md_search_params, psms: *mut md_psm,
                        stats: *mut md_identify_stats, all_scores: *mut *mut i64, all_off: *mut *mut u64) -> c_int;
+    pub fn md_identify_device(ctx: *mut md_ctx, spectra_dev: *const md_spectra, params: *const md_search_params, psms_dev: *mut md_psm,
+                              stats: *mut md_identify_stats) -> c_int;
+    pub fn md_comm_unique_id(id: *mut u8) -> c_int;                       // MD_COMM_ID_BYTES = 128
+    pub fn md_comm_init(ctx: *mut md_ctx, rank: i32, nranks: i32, id: *const u8) -> c_int;
+    pub fn md_gather_psms(ctx: *mut md_ctx, local: *const md_psm, rows_per_rank: u64, all: *mut md_psm) -> c_int;
+    pub fn md_comm_destroy(ctx: *mut md_ctx) -> c_int;
+    pub fn md_sync(ctx: *mut md_ctx) -> c_int;
+    pub fn md_stream_handle(ctx: *mut md_ctx) -> *mut c_void;
     pub fn md_last_decoys_export(ctx: *mut md_ctx, out: *mut md_decoy_table) -> c_int;
     pub fn md_free(p: *mut c_void);
 }

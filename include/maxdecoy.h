@@ -316,6 +316,30 @@ MD_API int md_identify(md_ctx* ctx, const md_spectra* spectra, const md_search_p
 MD_API int md_identify_device(md_ctx* ctx, const md_spectra* spectra_dev,
                               const md_search_params* params, md_psm* psms_dev,
                               md_identify_stats* stats);
+/* ------------------------------------------------------------------ multi-GPU: spectra sharded, index replicated */
+
+/* The reference walks the spectra one after the other (the `for spectrum in spectra` loop of identification_task,
+ * tasks/identification.rs:201) and no iteration reads what another one wrote, so the loop is the unit of parallelism:
+ * one process and one md_ctx per GPU, every rank digests the same FASTA (the index is replicated), identifies its own
+ * share of the spectra (global spectrum ids key the decoy RNG, so the result does not depend on the number of ranks)
+ * and the only exchange is the gather of the fixed-width PSM tables -- NCCL over NVLink.
+ *
+ * md_comm_unique_id: rank 0 draws the communicator id (ncclGetUniqueId) and hands the bytes to the other ranks by
+ *   whatever channel the host has (a file, an environment variable, MPI, a torch.distributed store).
+ * md_comm_init: collective over all ranks (ncclCommInitRank on the ctx's device).  nranks == 1 needs no NCCL at all.
+ * md_gather_psms: all-gather of `rows_per_rank` PSM rows from every rank into `all` (nranks * rows_per_rank rows, rank
+ *   major) on the ctx stream.  `local` and `all` may each be a device pointer (used in place: `local` can be the
+ *   buffer md_identify_device wrote) or a host pointer (staged through the ctx); every rank passes the same
+ *   rows_per_rank (pad short shards with rows whose rank field is 0).  Returns after the rows are in `all` unless both
+ *   pointers are device pointers, in which case the gather is asynchronous on the ctx stream until md_sync.
+ *   Without md_comm_init (or with nranks == 1) it is a copy.
+ * md_comm_destroy: releases the communicator (md_destroy does it too). */
+#define MD_COMM_ID_BYTES 128
+MD_API int md_comm_unique_id(uint8_t id[MD_COMM_ID_BYTES]);
+MD_API int md_comm_init(md_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t id[MD_COMM_ID_BYTES]);
+MD_API int md_gather_psms(md_ctx* ctx, const md_psm* local, uint64_t rows_per_rank, md_psm* all);
+MD_API int md_comm_destroy(md_ctx* ctx);
+
 MD_API int md_sync(md_ctx* ctx);
 /* The cudaStream_t the ctx launches on (NULL in the oracle), for callers that bracket calls
  * with their own CUDA events. */

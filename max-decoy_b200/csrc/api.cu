@@ -35,6 +35,14 @@ int guarded(md_ctx* ctx, F body) {
   }
 }
 
+// Rust's `as i64` (mass/mod.rs:6-8): saturating, NaN -> 0 (a plain C++ cast would be undefined there)
+int64_t sat_i64(double x) {
+  if (std::isnan(x)) return 0;
+  if (x >= 9223372036854775807.0) return INT64_MAX;
+  if (x <= -9223372036854775808.0) return INT64_MIN;
+  return (int64_t)x;
+}
+
 void host_precursor_window(double mz, uint32_t z, int64_t lppm, int64_t uppm, int64_t* P, int64_t* lo, int64_t* hi) {
   // tasks/identification.rs:203-211; every product/sum rounded on its own (volatile blocks contraction)
   const double H = 1.007276;
@@ -45,11 +53,11 @@ void host_precursor_window(double mz, uint32_t z, int64_t lppm, int64_t uppm, in
   volatile double b = H * zc;
   volatile double a = mz * zc;
   volatile double d0 = a - b;
-  *P = (int64_t)(d0 * 1000000.0);
+  *P = sat_i64(d0 * 1000000.0);
   volatile double ml = mz - tl; volatile double al = ml * zc; volatile double dl = al - b;
-  *lo = (int64_t)(dl * 1000000.0);
+  *lo = sat_i64(dl * 1000000.0);
   volatile double mu = mz + tu; volatile double au = mu * zc; volatile double du = au - b;
-  *hi = (int64_t)(du * 1000000.0);
+  *hi = sat_i64(du * 1000000.0);
 }
 
 template <class T>
@@ -192,6 +200,7 @@ void md_destroy(md_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  comm_release(ctx);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStream_t s = ctx->stream;
   delete ctx;  // frees the device buffers
@@ -202,7 +211,7 @@ const char* md_last_error(const md_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 void md_free(void* p) { free(p); }
 int md_sync(md_ctx* ctx) {
   if (!ctx) return fail(ctx, MD_ERR_INVALID, "md_sync: null ctx");
-  return guarded(ctx, [&] { MD_CUDA(cudaStreamSynchronize(ctx->stream)); });
+  return guarded(ctx, [&] { MD_CUDA(cudaStreamSynchronize(ctx->stream)); comm_sync(ctx); });
 }
 
 int64_t md_residue_mass(uint8_t c) { return kResidueMassByCode[md_code_of(c)]; }
@@ -441,13 +450,18 @@ void md_decoy_table_free(md_decoy_table* t) {
 int md_identify_device(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_psm* psms_dev, md_identify_stats* stats) {
   if (!ctx || !S || !p || (S->n && p->top_k && !psms_dev)) return fail(ctx, MD_ERR_INVALID, "md_identify_device: null argument");
   if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_identify_device: md_index_build first");
+  if (S->n && (!S->precursor_mz || !S->charge || !S->peak_off)) return fail(ctx, MD_ERR_INVALID, "spectra: null array");
   return guarded(ctx, [&] {
     validate_params(p);
     if (stats) memset(stats, 0, sizeof(*stats));
     ctx->reset_counters(); ctx->last.have = false;
     if (!S->n) return;
+    comm_wait_for_buffer(ctx, psms_dev);
+    // (the caller's buffers must be complete when the call is made: work on other streams is the caller's to wait for)
     uint64_t n_peaks = 0;
-    MD_CUDA(cudaMemcpy(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    MD_CUDA(cudaMemcpyAsync(&n_peaks, (const uint64_t*)S->peak_off + S->n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MD_CUDA(cudaStreamSynchronize(ctx->stream));
+    MD_REQUIRE(S->n == 0 || n_peaks < (1ull << 40), MD_ERR_INVALID, "spectra: peak_off[n] is not a plausible peak count");
     SpectraDev D{S->n, S->precursor_mz, S->charge, S->spectrum_id, S->peak_off, S->peak_mz, S->peak_intensity};
     const std::vector<uint32_t> cut = plan_passes(ctx, D, *p);
     MD_REQUIRE(cut.size() == 2 || !p->keep_decoys, MD_ERR_UNSUPPORTED, "keep_decoys needs a batch that fits one pass");
@@ -471,6 +485,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
     for (uint32_t s = 0; s < n; s++) {
       MD_REQUIRE(S->peak_off[s + 1] >= S->peak_off[s], MD_ERR_INVALID, "spectra: peak_off not monotone");
       MD_REQUIRE(S->charge[s] != 0, MD_ERR_INVALID, "spectra: charge 0");
+      MD_REQUIRE(std::isfinite(S->precursor_mz[s]) && S->precursor_mz[s] > 0.0 && S->precursor_mz[s] < 1.0e7, MD_ERR_INVALID, "spectra: precursor m/z must be finite and in (0, 1e7)");
     }
     if (!n) { if (all_scores && all_off) { *all_scores = (int64_t*)calloc(1, 8); *all_off = (uint64_t*)calloc(1, 8); } return; }
     IdentifyWorkspace& W = ctx->ws;

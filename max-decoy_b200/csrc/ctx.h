@@ -101,6 +101,17 @@ struct md_ctx {
   MassIndex dindex;
   IdentifyWorkspace ws;
   LastDecoys last;
+  // multi-GPU (comm.cu): NCCL communicator of this rank, staging buffers of md_gather_psms for host pointers
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  DevBuf<md_psm> gat_send, gat_recv;
+  // device-to-device gathers run on their own stream behind the rows they send, so that the next batch is searched
+  // meanwhile; the last two are remembered: md_identify_device waits (on the device) before it overwrites a buffer
+  // whose gather may still be in flight
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_rows = nullptr;
+  struct PendingGather { const void* local = nullptr; cudaEvent_t done = nullptr; } pending[2];
+  uint32_t n_gathers = 0;
   uint64_t launches = 0;   // hand-written kernels launched by the current call
   uint64_t cub_calls = 0;  // CUB primitive invocations (scan/select/sort), counted separately
   // per-call accumulators reported through md_identify_stats
@@ -143,3 +154,6 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
 void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p, uint32_t id_base);
 
 size_t cub_temp_bytes_max(size_t n);
+void comm_release(md_ctx* ctx);   // comm.cu: ncclCommDestroy if a communicator exists
+void comm_wait_for_buffer(md_ctx* ctx, const void* buf);   // comm.cu: the ctx stream waits for a gather still reading `buf`
+void comm_sync(md_ctx* ctx);

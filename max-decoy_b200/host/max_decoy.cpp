@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <array>
@@ -410,7 +411,8 @@ int cmd_identification(int argc, char** argv) {
                                  {"d", "number-of-decoys", "decoys"}, {"l", "lower-mass-tolerance", "lower"}, {"u", "upper-mass-tolerance", "upper"},
                                  {"", "fragmentation-tolerance", "fragtol"}, {"t", "thread-count", "threads"}, {"", "max-time-for-decoy-generation", "maxtime"},
                                  {"r", "comet-revision", "rev"}, {"", "fasta", "fasta"}, {"c", "number-of-missed-cleavages", "mc"}, {"o", "out", "out"},
-                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}, {"", "stored-decoys", "stored"}, {"", "variable-mode", "varmode"}});
+                                 {"", "seed", "seed"}, {"", "decoy-mode", "mode"}, {"", "top-k", "topk"}, {"", "device", "device"}, {"", "stored-decoys", "stored"}, {"", "variable-mode", "varmode"},
+                                 {"", "rank", "rank"}, {"", "nranks", "nranks"}, {"", "comm-file", "commfile"}});
   if (!a.has("mods") || !a.has("spectra") || !a.has("fasta")) die("identification: -m, -s and --fasta are required");
   const std::vector<Mod> mods = read_mods(a.get("mods"));
   const Fasta f = read_fasta(a.get("fasta"));
@@ -450,59 +452,155 @@ int cmd_identification(int argc, char** argv) {
   p.lower_ppm = a.num("lower", 5); p.upper_ppm = a.num("upper", 5); p.fragment_tolerance = std::strtod(a.get("fragtol", "0.02").c_str(), nullptr);
   p.n_decoys = (uint32_t)a.num("decoys", 1000); p.decoy_mode = (int32_t)a.num("mode", 0); p.seed = (uint64_t)a.num("seed", 0);
   p.top_k = (uint32_t)a.num("topk", 5); p.min_peaks = 10; p.max_fragment_charge = 3; p.keep_decoys = 1;
-  const md_spectra sp = S.abi();
-  std::vector<md_psm> psms((size_t)sp.n * p.top_k);
-  md_identify_stats st;
-  check(ctx, md_identify(ctx, &sp, &p, psms.data(), &st, nullptr, nullptr), "md_identify");
-  // the candidate sets that were scored -> the reference's per-spectrum files (tasks/identification.rs:323-368)
-  std::vector<md_precursor> pre(sp.n);
-  for (uint32_t i = 0; i < sp.n; i++) {
-    md_precursor_window(S.pmz[i], S.charge[i], p.lower_ppm, p.upper_ppm, &pre[i].mass, &pre[i].lo, &pre[i].hi);
-    pre[i].charge = S.charge[i]; pre[i].spectrum_id = i;
+  // ---- multi-GPU: one process per GPU (--rank R --nranks N --comm-file PATH, --device = the rank's GPU); the spectra are
+  //      sorted by neutral precursor mass and dealt in blocks of 32 over the ranks (every rank sees the same mass mix), the
+  //      index is replicated (every rank digested the same FASTA), the PSM tables are gathered with md_gather_psms
+  const int rank = (int)a.num("rank", 0), nranks = (int)a.num("nranks", 1);
+  if (nranks < 1 || rank < 0 || rank >= nranks) die("identification: --rank / --nranks out of range");
+  if (nranks > 1) {
+    if (!a.has("commfile")) die("identification: --nranks > 1 needs --comm-file (rank 0 leaves the communicator id there)");
+    const std::string cf = a.get("commfile");
+    uint8_t id[MD_COMM_ID_BYTES];
+    if (rank == 0) {
+      check(nullptr, md_comm_unique_id(id), "md_comm_unique_id");
+      write_file(cf + ".tmp", std::string((const char*)id, sizeof id));
+      if (std::rename((cf + ".tmp").c_str(), cf.c_str()) != 0) die("cannot write " + cf);
+    } else {
+      std::string got;
+      for (int tries = 0; tries < 1200 && got.size() != sizeof id; tries++) {
+        std::ifstream in(cf, std::ios::binary);
+        if (in) { std::ostringstream ss; ss << in.rdbuf(); got = ss.str(); }
+        if (got.size() != sizeof id) usleep(100000);
+      }
+      if (got.size() != sizeof id) die("identification: no communicator id at " + cf);
+      std::memcpy(id, got.data(), sizeof id);
+    }
+    check(ctx, md_comm_init(ctx, rank, nranks, id), "md_comm_init");
+    if (rank == 0) std::remove(cf.c_str());
   }
-  md_candidate_table cand; md_decoy_table dec; md_peptide_table pt;
-  check(ctx, md_candidates(ctx, pre.data(), sp.n, &cand), "md_candidates");
-  check(ctx, md_last_decoys_export(ctx, &dec), "md_last_decoys_export");
+  const uint32_t n_all = (uint32_t)S.pmz.size();
+  constexpr uint32_t kDeal = 32;
+  std::vector<uint32_t> mine;    // this rank's spectra (global ordinals), ascending in neutral mass
+  {
+    std::vector<uint32_t> order(n_all);
+    for (uint32_t i = 0; i < n_all; i++) order[i] = i;
+    if (nranks > 1)
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return S.pmz[x] * S.charge[x] - 1.007276 * S.charge[x] < S.pmz[y] * S.charge[y] - 1.007276 * S.charge[y]; });
+    for (uint32_t b = 0; b * kDeal < n_all; b++)
+      if ((int)(b % (uint32_t)nranks) == rank) for (uint32_t i = b * kDeal; i < std::min(n_all, (b + 1) * kDeal); i++) mine.push_back(order[i]);
+  }
+  const uint32_t n_blocks = (n_all + kDeal - 1) / kDeal, rows_per_rank = ((n_blocks + nranks - 1) / nranks) * kDeal;
+  std::vector<md_psm> my_psms((size_t)rows_per_rank * p.top_k);
+  for (auto& r : my_psms) { std::memset(&r, 0, sizeof r); r.spectrum_id = 0xFFFFFFFFu; }   // padding rows
+  md_peptide_table pt;
   check(ctx, md_peptides_export(ctx, &pt), "md_peptides_export");
   auto pep_seq = [&](uint64_t id) { return std::string((const char*)pt.seq + pt.seq_off[id - 1], pt.seq_off[id] - pt.seq_off[id - 1]); };
-  auto dec_seq = [&](uint64_t i) { return std::string((const char*)dec.seq + dec.seq_off[i], dec.seq_off[i + 1] - dec.seq_off[i]); };
   const std::string dir = a.get("out", "identification_out");
   mkdir(dir.c_str(), 0777);
   const std::string rev = a.get("rev", "# comet_version 2019.01 rev. 4");
-  std::string csv;
-  for (uint32_t s = 0; s < sp.n; s++) {
-    const std::string name = S.scan_id[s].empty() ? S.spectrum_id[s] : S.scan_id[s];
-    std::string fasta; std::set<std::string> seen_t, seen_d;
-    for (uint64_t i = cand.off[s]; i < cand.off[s + 1]; i++) {
-      const std::string q = pep_seq(cand.peptide_id[i]);
-      if (!seen_t.insert(q).second) continue;
-      const std::string sum = mod_summary(q, mods, cand.var_mask[i]);
-      fasta += ">PEPTIDE_" + q + " MaxDecoyId=" + std::to_string(cand.peptide_id[i]) + (sum.empty() ? "" : " ModRes=" + sum) + "\n" + q + "\n";
+  // ---- the spectrum file goes through the library in batches: the decoys of a batch are kept for the per-spectrum FASTA
+  //      files, and a batch is sized so that they fit one pass of the workspaces (2^25 decoy slots, 32k spectra); global
+  //      spectrum ids keep the decoy RNG streams independent of the batching and of the number of ranks
+  const uint32_t batch_max = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(32768, (1ull << 25) / std::max<uint32_t>(1, p.n_decoys)));
+  std::map<uint32_t, std::string> csv_rows;     // global spectrum ordinal -> its psms.csv lines
+  md_identify_stats total;
+  std::memset(&total, 0, sizeof total);
+  for (size_t b0 = 0; b0 < mine.size(); b0 += batch_max) {
+    const uint32_t bn = (uint32_t)std::min<size_t>(batch_max, mine.size() - b0);
+    SpectraSoA B;
+    std::vector<uint32_t> gid(bn);
+    for (uint32_t k = 0; k < bn; k++) {
+      const uint32_t g = mine[b0 + k];
+      gid[k] = g;
+      B.pmz.push_back(S.pmz[g]); B.charge.push_back(S.charge[g]);
+      B.mz.insert(B.mz.end(), S.mz.begin() + S.off[g], S.mz.begin() + S.off[g + 1]);
+      B.inten.insert(B.inten.end(), S.inten.begin() + S.off[g], S.inten.begin() + S.off[g + 1]);
+      B.off.push_back(B.mz.size());
     }
-    for (uint64_t i = dec.off[s]; i < dec.off[s + 1]; i++) {
-      const std::string q = dec_seq(i);
-      if (!seen_d.insert(q).second) continue;
-      const std::string sum = mod_summary(q, mods, dec.var_mask[i]);
-      fasta += ">DECOY_" + q + (sum.empty() ? "" : " ModRes=" + sum) + "\n" + q + "\n";
+    md_spectra sp = B.abi();
+    sp.spectrum_id = gid.data();
+    md_psm* psms = my_psms.data() + b0 * p.top_k;
+    md_identify_stats st;
+    check(ctx, md_identify(ctx, &sp, &p, psms, &st, nullptr, nullptr), "md_identify");
+    total.n_spectra += st.n_spectra; total.n_targets += st.n_targets; total.n_decoys += st.n_decoys; total.n_less_decoys += st.n_less_decoys;
+    // the candidate sets that were scored -> the reference's per-spectrum files (tasks/identification.rs:323-368)
+    std::vector<md_precursor> pre(bn);
+    for (uint32_t i = 0; i < bn; i++) {
+      md_precursor_window(B.pmz[i], B.charge[i], p.lower_ppm, p.upper_ppm, &pre[i].mass, &pre[i].lo, &pre[i].hi);
+      pre[i].charge = B.charge[i]; pre[i].spectrum_id = gid[i];
     }
-    const std::string fpath = dir + "/" + name + ".fasta";
-    write_file(fpath, fasta);
-    if (seen_d.size() < p.n_decoys) write_file(dir + "/" + name + ".less_decoys", std::to_string(seen_d.size()));
-    write_file(dir + "/" + name + ".comet.params", comet_params(rev, mods, fpath, seen_t.size() + seen_d.size(), nvar, p.fragment_tolerance, p.lower_ppm, p.upper_ppm));
-    for (uint32_t r = 0; r < p.top_k; r++) {
-      const md_psm& row = psms[(size_t)s * p.top_k + r];
-      if (!row.rank) continue;
-      const std::string q = row.is_decoy ? dec_seq(dec.off[s] + row.candidate) : pep_seq(row.candidate);
-      char sc[48]; std::snprintf(sc, sizeof sc, "%.9g", (double)row.score);
-      csv += S.spectrum_id[s] + "," + S.scan_id[s] + "," + std::to_string(row.rank) + "," + (row.is_decoy ? "t," : "f,") +
-             (row.is_decoy ? "" : std::to_string(row.candidate)) + "," + q + "," + mod_summary(q, mods, row.var_mask) + "," + std::to_string(row.mod_weight) + "," +
-             std::to_string(pre[s].mass) + "," + std::to_string(row.charge) + "," + sc + "," + std::to_string(row.n_targets + row.n_decoys) + "\n";
+    md_candidate_table cand; md_decoy_table dec;
+    check(ctx, md_last_decoys_export(ctx, &dec), "md_last_decoys_export");
+    check(ctx, md_candidates(ctx, pre.data(), bn, &cand), "md_candidates");
+    auto dec_seq = [&](uint64_t i) { return std::string((const char*)dec.seq + dec.seq_off[i], dec.seq_off[i + 1] - dec.seq_off[i]); };
+    for (uint32_t s = 0; s < bn; s++) {
+      const uint32_t g = gid[s];
+      const std::string name = S.scan_id[g].empty() ? S.spectrum_id[g] : S.scan_id[g];
+      std::string fasta; std::set<std::string> seen_t, seen_d;
+      for (uint64_t i = cand.off[s]; i < cand.off[s + 1]; i++) {
+        const std::string q = pep_seq(cand.peptide_id[i]);
+        if (!seen_t.insert(q).second) continue;
+        const std::string sum = mod_summary(q, mods, cand.var_mask[i]);
+        fasta += ">PEPTIDE_" + q + " MaxDecoyId=" + std::to_string(cand.peptide_id[i]) + (sum.empty() ? "" : " ModRes=" + sum) + "\n" + q + "\n";
+      }
+      for (uint64_t i = dec.off[s]; i < dec.off[s + 1]; i++) {
+        const std::string q = dec_seq(i);
+        if (!seen_d.insert(q).second) continue;
+        const std::string sum = mod_summary(q, mods, dec.var_mask[i]);
+        fasta += ">DECOY_" + q + (sum.empty() ? "" : " ModRes=" + sum) + "\n" + q + "\n";
+      }
+      const std::string fpath = dir + "/" + name + ".fasta";
+      write_file(fpath, fasta);
+      if (seen_d.size() < p.n_decoys) write_file(dir + "/" + name + ".less_decoys", std::to_string(seen_d.size()));
+      write_file(dir + "/" + name + ".comet.params", comet_params(rev, mods, fpath, seen_t.size() + seen_d.size(), nvar, p.fragment_tolerance, p.lower_ppm, p.upper_ppm));
+      std::string& csv = csv_rows[g];
+      for (uint32_t r = 0; r < p.top_k; r++) {
+        const md_psm& row = psms[(size_t)s * p.top_k + r];
+        if (!row.rank) continue;
+        const std::string q = row.is_decoy ? dec_seq(dec.off[s] + row.candidate) : pep_seq(row.candidate);
+        char sc[48]; std::snprintf(sc, sizeof sc, "%.9g", (double)row.score);
+        csv += S.spectrum_id[g] + "," + S.scan_id[g] + "," + std::to_string(row.rank) + "," + (row.is_decoy ? "t," : "f,") +
+               (row.is_decoy ? "" : std::to_string(row.candidate)) + "," + q + "," + mod_summary(q, mods, row.var_mask) + "," + std::to_string(row.mod_weight) + "," +
+               std::to_string(pre[s].mass) + "," + std::to_string(row.charge) + "," + sc + "," + std::to_string(row.n_targets + row.n_decoys) + "\n";
+      }
     }
+    md_candidate_table_free(&cand); md_decoy_table_free(&dec);
   }
-  write_file(dir + "/psms.csv", csv);
-  std::printf("%llu spectra, %llu targets, %llu decoys scored, %llu spectra with fewer decoys than requested -> %s\n", (unsigned long long)st.n_spectra,
-              (unsigned long long)st.n_targets, (unsigned long long)st.n_decoys, (unsigned long long)st.n_less_decoys, dir.c_str());
-  md_candidate_table_free(&cand); md_decoy_table_free(&dec); md_peptide_table_free(&pt);
+  // ---- PSM rows of this rank (spectrum order); with several ranks every rank leaves its part and rank 0, once the gather
+  //      of the PSM tables has brought everybody's rows, checks the parts against the gathered table and joins them
+  auto part_path = [&](int r) { return dir + "/psms.rank" + std::to_string(r) + ".csv"; };
+  std::string csv;
+  for (auto& kv : csv_rows) csv += kv.second;
+  if (nranks == 1) write_file(dir + "/psms.csv", csv);
+  else {
+    write_file(part_path(rank) + ".tmp", csv);
+    std::rename((part_path(rank) + ".tmp").c_str(), part_path(rank).c_str());
+    std::vector<md_psm> all((size_t)rows_per_rank * p.top_k * nranks);
+    check(ctx, md_gather_psms(ctx, my_psms.data(), (uint64_t)rows_per_rank * p.top_k, all.data()), "md_gather_psms");
+    if (rank == 0) {
+      uint64_t rows_ranked = 0; std::set<uint32_t> seen;
+      for (auto& r : all) if (r.spectrum_id != 0xFFFFFFFFu) { seen.insert(r.spectrum_id); if (r.rank) rows_ranked++; }
+      if (seen.size() != n_all) die("md_gather_psms: gathered " + std::to_string(seen.size()) + " spectra, expected " + std::to_string(n_all));
+      std::map<std::string, std::vector<std::string>> by_spectrum;   // spectrum id -> lines, parts in any order
+      uint64_t lines = 0;
+      for (int r = 0; r < nranks; r++) {
+        std::string text;
+        for (int tries = 0; tries < 600; tries++) { std::ifstream in(part_path(r)); if (in) { std::ostringstream ss; ss << in.rdbuf(); text = ss.str(); break; } usleep(100000); }
+        for (auto& ln : lines_of(text)) { if (ln.empty()) continue; by_spectrum[ln.substr(0, ln.find(','))].push_back(ln); lines++; }
+        std::remove(part_path(r).c_str());
+      }
+      if (lines != rows_ranked) die("psms.csv: " + std::to_string(lines) + " lines in the ranks' parts, " + std::to_string(rows_ranked) + " ranked rows gathered");
+      std::string joined;
+      for (uint32_t g = 0; g < n_all; g++) { auto it = by_spectrum.find(S.spectrum_id[g]); if (it != by_spectrum.end()) { for (auto& ln : it->second) joined += ln + "\n"; by_spectrum.erase(it); } }
+      write_file(dir + "/psms.csv", joined);
+    }
+    check(ctx, md_comm_destroy(ctx), "md_comm_destroy");
+  }
+  std::printf("%s%llu spectra, %llu targets, %llu decoys scored, %llu spectra with fewer decoys than requested -> %s\n",
+              nranks > 1 ? ("rank " + std::to_string(rank) + "/" + std::to_string(nranks) + ": ").c_str() : "", (unsigned long long)total.n_spectra,
+              (unsigned long long)total.n_targets, (unsigned long long)total.n_decoys, (unsigned long long)total.n_less_decoys, dir.c_str());
+  md_peptide_table_free(&pt);
   md_destroy(ctx);
   return 0;
 }

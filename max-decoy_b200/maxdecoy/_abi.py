@@ -20,6 +20,7 @@ DECOY_EXHAUSTIVE = 1
 DECOY_PERMUTE_TARGET = 2
 VARMOD_REFERENCE = 0   # md_varmod_mode
 VARMOD_EXPANDED = 1
+COMM_ID_BYTES = 128
 DECOY_STORED = 0xFFFFFFFF   # `attempt` of a decoy taken from the store (md_decoy_store_set)
 
 u8p = C.POINTER(C.c_uint8)
@@ -140,6 +141,10 @@ SYMBOLS = {
                               C.POINTER(md_identify_stats), C.POINTER(i64p), C.POINTER(u64p)]),
     "md_identify_device": (C.c_int, [ctx_p, C.POINTER(md_spectra), C.POINTER(md_search_params), C.c_void_p,
                                      C.POINTER(md_identify_stats)]),
+    "md_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "md_comm_init": (C.c_int, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "md_gather_psms": (C.c_int, [ctx_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "md_comm_destroy": (C.c_int, [ctx_p]),
     "md_sync": (C.c_int, [ctx_p]),
     "md_stream_handle": (C.c_void_p, [ctx_p]),
     "md_last_decoys_export": (C.c_int, [ctx_p, C.POINTER(md_decoy_table)]),

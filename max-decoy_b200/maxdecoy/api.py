@@ -376,6 +376,36 @@ class Engine:
     def sync(self):
         self._ck(self.lib.md_sync(self.h))
 
+    # ---- multi-GPU (one Engine per rank; spectra sharded, index replicated) ---------------
+    def comm_unique_id(self):
+        """Rank 0: the communicator id (128 bytes) to hand to the other ranks."""
+        buf = (C.c_uint8 * _abi.COMM_ID_BYTES)()
+        rc = self.lib.md_comm_unique_id(buf)
+        if rc != 0:
+            raise MaxDecoyError(rc, (self.lib.md_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id=None):
+        buf = (C.c_uint8 * _abi.COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._ck(self.lib.md_comm_init(self.h, int(rank), int(nranks), buf))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def gather_psms(self, psms):
+        """All-gather of this rank's [rows, top_k] PSM table (host array) -> [nranks * rows, top_k], rank major."""
+        nranks = getattr(self, "nranks", 1)
+        psms = np.ascontiguousarray(psms)
+        out = np.zeros((nranks * psms.shape[0],) + psms.shape[1:], dtype=psms.dtype)
+        rows = psms.size
+        self._ck(self.lib.md_gather_psms(self.h, _ptr(psms), rows, _ptr(out)))
+        return out
+
+    def gather_psms_device(self, local_dev_ptr, rows, all_dev_ptr):
+        """Device-pointer variant: asynchronous on the ctx stream until `sync()`."""
+        self._ck(self.lib.md_gather_psms(self.h, C.c_void_p(local_dev_ptr), int(rows), C.c_void_p(all_dev_ptr)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.md_comm_destroy(self.h))
+
     @staticmethod
     def _stats(st):
         return {k: getattr(st, k) for k, _ in st._fields_}

@@ -158,39 +158,52 @@ def spectrum_fasta(target_rows, decoy_rows, mods):
 
 
 def write_identification_outputs(directory, names, engine, spectra, params, mods, max_variable_mods, comet_revision):
-    """identification_task's file outputs for every spectrum of a batch (tasks/identification.rs:323-368), from ONE
-    GPU call: the candidate sets are exactly those that were scored.  names[i] = basename of spectrum i (the reference
-    derives it from the one-spectrum mzML file name).  Returns the PSM table."""
+    """identification_task's file outputs for every spectrum of a file (tasks/identification.rs:323-368): the candidate
+    sets are exactly those that were scored.  names[i] = basename of spectrum i (the reference derives it from the
+    one-spectrum mzML file name).  The file goes through the library in batches whose decoys fit one pass of the
+    workspaces (2^25 decoy slots, 32k spectra); spectrum ids stay global, so the decoy RNG streams -- and with them the
+    result -- do not depend on the batching.  Returns the PSM table."""
     import numpy as np
     from .api import SearchParams
     p = SearchParams(**{k: getattr(params, k) for k in ("lower_ppm", "upper_ppm", "fragment_tolerance", "n_decoys", "decoy_mode", "seed",
                                                          "top_k", "min_peaks", "max_fragment_charge", "abs_lower_uda", "abs_upper_uda")},
                      keep_decoys=True)
-    psms, stats = engine.identify(spectra, p)
-    decoys = engine.last_decoys()
-    pre = []
-    for i in range(len(spectra)):
-        P, lo, hi = engine.precursor_window(float(spectra.precursor_mz[i]), int(spectra.charge[i]), p.lower_ppm, p.upper_ppm)
-        if p.abs_lower_uda or p.abs_upper_uda:
-            lo, hi = P - p.abs_lower_uda, P + p.abs_upper_uda
-        pre.append((P, lo, hi, int(spectra.charge[i]), i))
-    cand = engine.candidates(pre)
     table = engine.peptides()
     seqs = engine.sequences_of(table)
-    raw, so = decoys["seq"].tobytes(), decoys["seq_off"]
     os.makedirs(directory, exist_ok=True)
-    for s, name in enumerate(names):
-        t = [(seqs[int(cand["peptide_id"][i]) - 1], int(cand["peptide_id"][i]), int(cand["var_mask"][i]))
-             for i in range(int(cand["off"][s]), int(cand["off"][s + 1]))]
-        d = [(raw[int(so[i]):int(so[i + 1])].decode(), int(decoys["var_mask"][i]))
-             for i in range(int(decoys["off"][s]), int(decoys["off"][s + 1]))]
-        text, nt, nd = spectrum_fasta(t, d, mods)
-        fasta_path = os.path.join(directory, name + ".fasta")
-        with open(fasta_path, "w") as fh:
-            fh.write(text)
-        if nd < p.n_decoys:                                   # GenerationResult::Timeout in the reference
-            with open(os.path.join(directory, name + ".less_decoys"), "w") as fh:
-                fh.write("%d" % nd)
-        with open(os.path.join(directory, name + ".comet.params"), "w") as fh:
-            fh.write(comet_params(comet_revision, mods, fasta_path, nt + nd, max_variable_mods, p.fragment_tolerance, p.lower_ppm, p.upper_ppm))
-    return psms, stats
+    n = len(spectra)
+    batch = max(1, min(32768, (1 << 25) // max(1, p.n_decoys)))
+    ids = spectra.spectrum_id if spectra.spectrum_id is not None else np.arange(n, dtype=np.uint32)
+    all_psms, total = [], None
+    for b0 in range(0, max(n, 1), batch):
+        idx = np.arange(b0, min(n, b0 + batch))
+        sub = spectra.subset(idx)
+        sub.spectrum_id = np.ascontiguousarray(ids[idx], dtype=np.uint32)
+        psms, stats = engine.identify(sub, p)
+        all_psms.append(psms)
+        total = stats if total is None else {k: total[k] + v for k, v in stats.items()}
+        decoys = engine.last_decoys() if len(sub) else None
+        pre = []
+        for i in range(len(sub)):
+            P, lo, hi = engine.precursor_window(float(sub.precursor_mz[i]), int(sub.charge[i]), p.lower_ppm, p.upper_ppm)
+            if p.abs_lower_uda or p.abs_upper_uda:
+                lo, hi = P - p.abs_lower_uda, P + p.abs_upper_uda
+            pre.append((P, lo, hi, int(sub.charge[i]), int(sub.spectrum_id[i])))
+        cand = engine.candidates(pre)
+        raw, so = (decoys["seq"].tobytes(), decoys["seq_off"]) if decoys is not None else (b"", [0])
+        for s in range(len(sub)):
+            name = names[b0 + s]
+            t = [(seqs[int(cand["peptide_id"][i]) - 1], int(cand["peptide_id"][i]), int(cand["var_mask"][i]))
+                 for i in range(int(cand["off"][s]), int(cand["off"][s + 1]))]
+            d = [(raw[int(so[i]):int(so[i + 1])].decode(), int(decoys["var_mask"][i]))
+                 for i in range(int(decoys["off"][s]), int(decoys["off"][s + 1]))]
+            text, nt, nd = spectrum_fasta(t, d, mods)
+            fasta_path = os.path.join(directory, name + ".fasta")
+            with open(fasta_path, "w") as fh:
+                fh.write(text)
+            if nd < p.n_decoys:                                   # GenerationResult::Timeout in the reference
+                with open(os.path.join(directory, name + ".less_decoys"), "w") as fh:
+                    fh.write("%d" % nd)
+            with open(os.path.join(directory, name + ".comet.params"), "w") as fh:
+                fh.write(comet_params(comet_revision, mods, fasta_path, nt + nd, max_variable_mods, p.fragment_tolerance, p.lower_ppm, p.upper_ppm))
+    return np.concatenate(all_psms) if all_psms else np.zeros((0, p.top_k)), total

@@ -72,6 +72,30 @@ def gather_psms(psms, top_k, n_total, group=None, device=None, block=32):
     return order_by_spectrum(allrows[keep], n_total)
 
 
+def pad_rows(psms, top_k, rows):
+    """[n_local, top_k] table -> [rows, top_k] with padding rows (spectrum_id 0xFFFFFFFF, rank 0) behind it."""
+    buf = np.zeros((rows, top_k), dtype=PSM_DTYPE)
+    buf["spectrum_id"] = 0xFFFFFFFF
+    buf[:len(psms)] = psms.reshape(-1, top_k)
+    return buf
+
+
+def drop_padding(allrows, top_k, n_total):
+    allrows = allrows.reshape(-1, top_k)
+    keep = allrows["spectrum_id"][:, 0] != 0xFFFFFFFF
+    return order_by_spectrum(allrows[keep], n_total)
+
+
+def identify_sharded_comm(engine, spectra, params, rank, world, block=32):
+    """The same over the library's own collective (md_comm_init / md_gather_psms of include/maxdecoy.h: NCCL inside the
+    CUDA library, a copy in a single-rank run): what a host without torch.distributed (the Rust / C++ host) calls."""
+    sub, _ = shard(spectra, rank, world, block)
+    psms, stats = engine.identify(sub, params)
+    rows = padded_rows(len(spectra), world, block)
+    allrows = engine.gather_psms(pad_rows(psms, params.top_k, rows))
+    return drop_padding(allrows, params.top_k, len(spectra)), stats
+
+
 def order_by_spectrum(rows, n_total):
     """Sort gathered [n, top_k] rows by global spectrum id (stable)."""
     order = np.argsort(rows["spectrum_id"][:, 0], kind="stable")

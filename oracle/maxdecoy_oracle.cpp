@@ -679,6 +679,7 @@ int validate_spectra(md_ctx* ctx, const md_spectra* S) {
     for (uint64_t i = S->peak_off[s] + 1; i < S->peak_off[s + 1]; i++)
       if (S->peak_mz[i] < S->peak_mz[i - 1]) return fail(ctx, MD_ERR_INVALID, "spectra: peaks of a spectrum must be sorted by m/z");
     if (S->charge[s] == 0) return fail(ctx, MD_ERR_INVALID, "spectra: charge 0");
+    if (!(std::isfinite(S->precursor_mz[s]) && S->precursor_mz[s] > 0.0 && S->precursor_mz[s] < 1.0e7)) return fail(ctx, MD_ERR_INVALID, "spectra: precursor m/z must be finite and in (0, 1e7)");
   }
   return MD_OK;
 }
@@ -757,6 +758,18 @@ void md_destroy(md_ctx* ctx) { delete ctx; }
 const char* md_last_error(const md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 void md_free(void* p) { std::free(p); }
 int md_sync(md_ctx*) { return MD_OK; }
+// multi-GPU entry points: the checker is one process on the host; a single rank gathers by copying
+int md_comm_unique_id(uint8_t* id) { if (!id) return MD_ERR_INVALID; memset(id, 0, MD_COMM_ID_BYTES); return MD_OK; }
+int md_comm_init(md_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t*) {
+  if (!ctx || rank != 0) return MD_ERR_INVALID;
+  return nranks == 1 ? MD_OK : MD_ERR_UNSUPPORTED;
+}
+int md_gather_psms(md_ctx* ctx, const md_psm* local, uint64_t rows, md_psm* all) {
+  if (!ctx || (rows && (!local || !all))) return MD_ERR_INVALID;
+  if (rows && local != all) memmove(all, local, rows * sizeof(md_psm));
+  return MD_OK;
+}
+int md_comm_destroy(md_ctx* ctx) { return ctx ? MD_OK : MD_ERR_INVALID; }
 void* md_stream_handle(md_ctx*) { return nullptr; }
 
 int64_t md_residue_mass(uint8_t c) { return residue_mass(c); }

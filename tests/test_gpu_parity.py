@@ -389,3 +389,34 @@ def test_passes_do_not_change_results(gpu, cpu, monkeypatch):
     assert (stm["n_targets"], stm["n_decoys"], stm["n_pairs"]) == (st1["n_targets"], st1["n_decoys"], st1["n_pairs"])
     pc, _, scc, offc = cpu.identify(sp, prm, want_all_scores=True)
     assert np.array_equal(scm, scc) and np.array_equal(many["raw_score"], pc["raw_score"]) and np.array_equal(many["candidate"], pc["candidate"])
+
+
+def test_gather_psms_single_rank_and_device_pointers(gpu):
+    """md_gather_psms without a communicator is a copy -- host to host, and in place on device pointers (the buffer
+    md_identify_device wrote is the send buffer)."""
+    import ctypes as C
+    import torch
+    from maxdecoy import _abi, parallel
+    prots = list(wl.proteins(150))
+    gpu.digest(prots, 2, 5, 50)
+    gpu.set_modifications([synth.CAM], 0)
+    gpu.index_build()
+    sp, _ = wl.spectra(150, 40, 2)
+    prm = SearchParams(10, 10, n_decoys=30, seed=9, top_k=3)
+    gpu.comm_init(0, 1, None)
+    want, _ = gpu.identify(sp, prm)
+    got, _ = parallel.identify_sharded_comm(gpu, sp, prm, 0, 1, block=8)
+    assert got.tobytes() == want.tobytes()
+    dev = {k: torch.from_numpy(getattr(sp, k).view(np.int64) if getattr(sp, k).dtype == np.uint64 else getattr(sp, k)).cuda()
+           for k in ("precursor_mz", "charge", "peak_off", "peak_mz", "peak_intensity")}
+    sd = _abi.md_spectra()
+    sd.n = len(sp)
+    for k, v in dev.items():
+        setattr(sd, k, v.data_ptr())
+    rows = torch.zeros(len(sp) * 3 * 56, dtype=torch.uint8, device="cuda")
+    allr = torch.zeros_like(rows)
+    gpu.identify_device(sd, prm, rows.data_ptr())
+    gpu.gather_psms_device(rows.data_ptr(), len(sp) * 3, allr.data_ptr())
+    gpu.sync()
+    assert allr.cpu().numpy().tobytes() == want.tobytes()
+    gpu.comm_destroy()

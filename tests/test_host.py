@@ -37,6 +37,17 @@ def test_header_and_ctypes_view_agree():
     assert set(syms) == set(_abi.SYMBOLS), set(syms) ^ set(_abi.SYMBOLS)
 
 
+def test_rust_binding_declares_every_symbol():
+    """ffi/maxdecoy_sys.rs (the uncompiled Rust view a maintainer of the reference would add) and the code block of
+    INTEGRATION.md name exactly the header's entry points."""
+    rs = open(os.path.join(ROOT, "ffi", "maxdecoy_sys.rs")).read()
+    rs_syms = set(re.findall(r"pub fn (md_\w+)\s*\(", rs))
+    assert rs_syms == set(header_symbols()), rs_syms ^ set(header_symbols())
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for s in header_symbols():
+        assert s in doc, "INTEGRATION.md does not mention %s" % s
+
+
 def test_cuda_library_exports_every_declared_symbol():
     lib = _abi.bind(_ensure_cuda_lib())            # AttributeError on a missing symbol
     out = subprocess.check_output(["nm", "-D", "--defined-only", CUDA_SO], text=True)
@@ -150,6 +161,26 @@ def test_partition_is_a_balanced_permutation(n, world, block):
     for p in parts:                                     # every shard ascends in neutral mass
         m = mz[p] * z[p] - 1.007276 * z[p]
         assert np.all(np.diff(m) >= 0)
+
+
+def test_comm_entry_points_single_rank():
+    """md_comm_init / md_gather_psms with one rank: no collective library needed, the gather is a copy, and the sharded
+    driver over the library's own collective returns what a plain identify returns."""
+    from oracle_lib import oracle_engine
+    e = oracle_engine(2)
+    e.digest(list(wl.proteins(60)), 2, 5, 50)
+    e.set_modifications([synth.CAM], 0)
+    e.index_build()
+    sp, _ = wl.spectra(60, 20, 2)
+    prm = maxdecoy.SearchParams(10, 10, n_decoys=10, seed=3, top_k=2)
+    e.comm_init(0, 1, None)
+    want, _ = e.identify(sp, prm)
+    got, _ = parallel.identify_sharded_comm(e, sp, prm, 0, 1, block=8)
+    assert got.tobytes() == want.tobytes()
+    with pytest.raises(maxdecoy.MaxDecoyError):
+        e.comm_init(1, 1, None)
+    e.comm_destroy()
+    e.close()
 
 
 # ------------------------------------------------------------------------------------------ N > 1 (gloo, CPU)
