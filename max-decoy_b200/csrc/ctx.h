@@ -55,7 +55,6 @@ struct IdentifyWorkspace {
   // accepted targets
   DevBuf<uint64_t> cand_desc; DevBuf<uint64_t> cand_mask; DevBuf<int64_t> cand_w; DevBuf<uint32_t> cand_pep;
   // decoy attempts (one slot per attempt of the current round) and accepted decoys (n_per slots per spectrum)
-  DevBuf<uint8_t> rec_seq;           // attempt records: sequences as alphabet indices (decoy.cu)
   DevBuf<uint8_t> att_rows; DevBuf<uint8_t> att_len; DevBuf<uint64_t> att_mask; DevBuf<int64_t> att_w; DevBuf<uint64_t> att_hash;
   DevBuf<uint8_t> dec_rows; DevBuf<uint8_t> dec_len; DevBuf<uint64_t> dec_mask; DevBuf<int64_t> dec_w; DevBuf<uint64_t> dec_hash;
   DevBuf<uint32_t> dec_attempt; DevBuf<uint32_t> dec_count; DevBuf<uint32_t> att_base; DevBuf<uint32_t> att_limit;

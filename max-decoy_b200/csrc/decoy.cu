@@ -23,7 +23,7 @@ constexpr int kThreads = 128;          // lanes per CTA of the attempt kernels
 constexpr int kMaxRoundAttempts = 4096;  // per spectrum per round (bounds the selection kernel's shared memory)
 
 // letter tables in alphabet-index space, built once per call on the host
-constexpr uint32_t kGapTab = 2048, kNnTab = 1024;
+constexpr uint32_t kGapTab = 512, kNnTab = 1024;
 struct DecoyTables {
   int64_t mprime[32];      // residue mass + fixed delta, by alphabet index (0..20)
   int64_t sorted_m[32];    // mprime sorted ascending (ties by alphabet index), padded with INT64_MAX
@@ -49,8 +49,6 @@ struct DecoyTables {
   uint8_t nn_letter[32];
   int32_t nn_lo, nn_hi;
   uint32_t nn_shift;
-  // most sorted gaps / thresholds inside one bucket: the residual steps the kernel takes behind each table
-  uint32_t gap_depth, nn_depth;
 };
 
 struct TSeq {  // a lane's working sequence in shared memory (alphabet indices), transposed for conflict-free access
@@ -102,10 +100,10 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ att_
 }
 
 // Philox4x32-10 output stream of one attempt, buffered in a per-lane shared-memory ring so that the block function runs
-// for the whole warp at once (at the ticks of the kernel loop) instead of as a divergent tail behind whichever lane happens
-// to run dry.  The stream is exactly Philox4::next()'s: blocks c0 = 0, 1, 2, ... in order, four words each.
+// for the whole warp at once (every kRngPeriod steps of the kernel loop) instead of as a divergent tail behind whichever
+// lane happens to run dry.  The stream is exactly Philox4::next()'s: blocks c0 = 0, 1, 2, ... in order, four words each.
 #ifndef MD_RNG_RING
-#define MD_RNG_RING 16
+#define MD_RNG_RING 8
 #endif
 constexpr uint32_t kRing = MD_RNG_RING;   // words per lane (power of two)
 struct RngRing {
@@ -135,11 +133,16 @@ struct RngRing {
     head++; count--;
     return v;
   }
+  __device__ __forceinline__ uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
 };
-#ifndef MD_DECOY_TICK
-#define MD_DECOY_TICK 16
+#ifndef MD_RNG_PERIOD
+#define MD_RNG_PERIOD 8
 #endif
-constexpr uint32_t kTick = MD_DECOY_TICK;   // kernel-loop passes between two ticks (power of two)
+constexpr uint32_t kRngPeriod = MD_RNG_PERIOD;
+#ifndef MD_REFILL_MIN
+#define MD_REFILL_MIN 8
+#endif
+constexpr int kRefillMin = MD_REFILL_MIN;   // free lanes of a warp that trigger a refill
 
 // position masks are 32 bits wide in the narrow pass (sequences of <= 32 residues: nearly all of them) and 64 in the wide one
 template <class MaskT> struct MaskOps;
@@ -180,313 +183,212 @@ struct RandomArgs {
   const uint32_t* att_blk;              // coarse index into att_off (find_entry_coarse)
   uint32_t n_list, total;
   uint32_t* queue;                       // work counter of this launch
-  const uint2* remap; const uint32_t* remap_n;   // wide pass: work item -> (attempt record, list entry) left over by the narrow pass, or NULL
-  uint2* spill; uint32_t* spill_n;       // narrow pass: attempts that grew past 32 residues, left to the wide pass
+  const uint32_t* remap; const uint32_t* remap_n;   // wide pass: work item -> attempt (the narrow pass's spill list), or NULL
+  uint32_t* spill; uint32_t* spill_n;    // narrow pass: attempts that grew past 32 residues, left to the wide pass
   uint64_t seed; int* overflow;
-  uint32_t gap_depth, nn_depth;          // residual steps behind the two bucket tables (DecoyTables)
 };
-
-// What an attempt leaves behind: the sequence as alphabet indices (one byte per residue, 64-byte slots), its length (0 =
-// no decoy), the modified weight and the variable-modification mask.  k_attempt_finish turns the records into score rows.
-struct RecordOut { uint8_t* seq; uint8_t* len; uint64_t* mask; int64_t* w; };
 
 // One lane = one attempt at a time, run as a flat state machine: every pass of the kernel loop does ONE step for every
-// lane that has an attempt, and every kind of step ends in the same "put letter c at position p" code --
-//   GROW    append a uniform letter (decoy_generator.rs:142-159) until the weight exceeds the upper limit;
-//   SUBST   the first improving substitution at or behind the pass position (modified_peptide.rs:454-487);
-//   KICK    when the pass is over: a uniform letter at a uniform position (:489-505), next try --
-// so the lanes of a warp stay together although their attempts are in different phases / tries / positions / lengths
-// (nested loops would make 31 finished lanes wait for the one that runs all 100 tries).  Every kTick passes the warp
-// stops at a TICK: lanes whose attempt ended (hit, 100 tries without one, too long) write their record and take the next
-// attempt from the warp's pool -- 32 work items fetched and resolved (work item -> spectrum, precursor, attempt ordinal) by
-// the 32 lanes together, so no lane ever walks that chain of dependent loads alone -- and all lanes top up their
-// random-number rings together.  Inside the loop an attempt is its residual d = weight - precursor: 64 bits while it
-// grows, 32 bits afterwards (|d| stays far below 2^30 uDa; checked, reported via `overflow`), and the window is
-// [dlo, dlo + span] in the same space.
-// Random numbers: one Philox word per kick (position = high half of r*L, letter = high half of low32(r*L)*21) and one
-// word per FOUR grown letters (letter = high half of g*21, g <- low half; the word's remainder is dropped when the
-// growth ends).
+// lane that has an attempt -- the first improving substitution at or behind the pass position, or, when the pass is
+// over, the random kick -- and both kinds of step end in the same "put letter c at position p" code, so the lanes of a
+// warp stay together although their attempts are at different tries / positions / lengths (nested try/position loops
+// would make 31 finished lanes wait for the one that runs all 100 tries).  Lanes whose attempt ends (hit, or 100 tries
+// without one) park until a quarter of the warp is free, then fetch and grow new attempts together.  Inside the loop an
+// attempt is its residual d = weight - precursor in 32 bits (|d| stays far below 2^30 uDa after the grow phase; checked,
+// reported via `overflow`) and the window is [dlo, dlo + span] in the same space.
 // VMODE: 0 = no variable modification can apply, 1 = one variable letter without a fixed modification (its positions are
 // tracked, try_variable_modifications needs no walk over the sequence), 2 = anything else (generic enumeration).
-template <class MaskT> struct LaneSeq {   // a lane's working sequence in shared memory: alphabet indices, 4 per word, words strided by kThreads
-  uint8_t* base;   // + 4 * tid
-  __device__ __forceinline__ uint8_t& at(uint32_t i) const { return base[(i >> 2) * (4 * kThreads) + (i & 3u)]; }
-};
-template <class MaskT> struct LaneSeqCode {  // view as residue codes for md_try_variable
-  LaneSeq<MaskT> s; const uint8_t* code_of_a;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return code_of_a[s.at(i)]; }
-};
-
 template <int VMODE, class MaskT>
 __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, const __grid_constant__ ModTables M, const __grid_constant__ DecoyTables T,
-                                                           RecordOut O) {
+                                                           AttemptOut O, PeptideView PV) {
   using MO = MaskOps<MaskT>;
   constexpr uint32_t kBits = MO::bits;
   constexpr bool kNarrow = kBits < MD_MAX_PEPTIDE_LEN;
-  constexpr uint32_t kRows = kNarrow ? kBits : MD_MAX_PEPTIDE_LEN;     // longest sequence this pass holds
-  constexpr uint32_t kWords = (kRows + 3) / 4;
+  constexpr uint32_t kRows = kNarrow ? kBits : MD_MAX_PEPTIDE_LEN;
   constexpr uint32_t kAbove = 40;       // offset of the d < 0 tables
-  // shared memory (dynamic: the wide pass needs more than the 48 KB a kernel gets statically), see random_smem_bytes()
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  uint32_t* s_seq = reinterpret_cast<uint32_t*>(s_raw);                       // kWords x kThreads
-  uint32_t* s_rng = s_seq + kWords * kThreads;                                // kRing x kThreads
-  uint32_t* s_pool = s_rng + kRing * kThreads;                                // per warp: 32 resolved work items x 8 words, [word][item]
-  uint32_t* s_keep = s_pool + 8 * kThreads;                                   // per lane, used at the ticks only: precursor (lo, hi), record, list entry
-  MaskT* s_pm = reinterpret_cast<MaskT*>(s_keep + 4 * kThreads);              // per lane and letter: the positions holding that letter
-  int32_t* s_mprime = reinterpret_cast<int32_t*>(s_pm + MD_ALPHABET_SIZE * kThreads);   // by alphabet index; [31] = 0 (the "letter" a grown position replaces)
-  int32_t* s_var = s_mprime + 32;
-  uint32_t* s_gap = reinterpret_cast<uint32_t*>(s_var + 32);                  // d > 0 tables at [0..], d < 0 tables at [kAbove..]
-  uint32_t* s_gmask = s_gap + kAbove + 40;
-  int32_t* s_thr2 = reinterpret_cast<int32_t*>(s_gmask + kAbove + 40);          // 32 + one padding entry behind
-  uint8_t* s_gtab = reinterpret_cast<uint8_t*>(s_thr2 + 40);
-  uint8_t* s_nntab = s_gtab + 2 * kGapTab;
-  uint8_t* s_nnletter = s_nntab + kNnTab;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  for (uint32_t i = tid; i < 2 * kGapTab; i += kThreads) s_gtab[i] = T.gap_tab[i / kGapTab][i % kGapTab];
-  for (uint32_t i = tid; i < kNnTab; i += kThreads) s_nntab[i] = T.nn_tab[i];
-  if (tid < 33) { s_gmask[tid] = T.maskb_prefix[tid]; s_gmask[kAbove + tid] = T.maska_prefix[tid]; }
-  if (tid < 32) {
-    s_gap[tid] = T.gapb_sorted[tid]; s_gap[kAbove + tid] = T.gapa_sorted[tid];
-    s_mprime[tid] = tid < MD_ALPHABET_SIZE ? (int32_t)T.mprime[tid] : 0; s_var[tid] = tid < MD_ALPHABET_SIZE ? (int32_t)T.var_a[tid] : 0;
-    s_thr2[tid] = T.nn_thr2[tid]; s_nnletter[tid] = T.nn_letter[tid];
-    if (tid < 8) { s_thr2[32 + tid] = INT32_MAX; s_gap[32 + tid] = 0xFFFFFFFFu; s_gap[kAbove + 32 + tid] = 0xFFFFFFFFu; }
+  __shared__ uint8_t sseq[kRows * kThreads];
+  __shared__ uint32_t s_rng[kRing * kThreads];
+  __shared__ MaskT s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
+  __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
+  __shared__ int32_t s_mprime[32];      // by alphabet index
+  __shared__ int32_t s_var[32];
+  __shared__ uint8_t s_runmin[32];
+  __shared__ uint32_t s_gap[kAbove + 32], s_gmask[kAbove + 33];   // d > 0 tables at [0..], d < 0 tables at [kAbove..]
+  __shared__ uint8_t s_gtab[2 * kGapTab], s_nntab[kNnTab], s_nnletter[32];
+  __shared__ int32_t s_thr2[32];
+  for (uint32_t i = threadIdx.x; i < 2 * kGapTab; i += kThreads) s_gtab[i] = T.gap_tab[i / kGapTab][i % kGapTab];
+  for (uint32_t i = threadIdx.x; i < kNnTab; i += kThreads) s_nntab[i] = T.nn_tab[i];
+  if (threadIdx.x < 33) { s_gmask[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_gmask[kAbove + threadIdx.x] = T.maska_prefix[threadIdx.x]; }
+  if (threadIdx.x < 32) {
+    s_gap[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gap[kAbove + threadIdx.x] = T.gapa_sorted[threadIdx.x];
+    const int64_t sm = T.sorted_m[threadIdx.x];
+    s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
+    s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
+    s_runmin[threadIdx.x] = T.run_min_a[threadIdx.x];
+    s_thr2[threadIdx.x] = T.nn_thr2[threadIdx.x]; s_nnletter[threadIdx.x] = T.nn_letter[threadIdx.x];
   }
   __syncthreads();
-  LaneSeq<MaskT> seq{reinterpret_cast<uint8_t*>(s_seq) + 4 * tid};
-  const uint32_t gap_shift = T.gap_shift, nn_shift = T.nn_shift, gap_depth = A.gap_depth, nn_depth = A.nn_depth;
+  TSeq seq{sseq + threadIdx.x};
+  const uint32_t gap_shift = T.gap_shift, nn_shift = T.nn_shift;
   const int32_t nn_lo = T.nn_lo, nn_hi = T.nn_hi;
   const int va = VMODE == 1 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
   const int32_t vdelta = VMODE == 1 ? (int32_t)M.var[M.var_simple_code] : 0;
   const uint32_t total = A.remap ? *A.remap_n : A.total;
-  uint32_t* pool = s_pool + warp * 256u;
 
-  bool busy = false, grow = false, drained = false;
-  uint32_t pending = 0;           // how the lane's attempt ended, until the next tick: 1 = hit, 2 = no decoy, 3 = too long for this pass
-  uint32_t pool_i = 0, pool_n = 0;   // (warp-uniform) unread items of the pool
+  bool busy = false, drained = false;
+  uint32_t pending = 0;           // 1 = hit, 2 = gave up: the result is written when the free lanes refill together
   uint32_t present = 0;           // letters in the sequence
-  MaskT* pm = s_pm + tid;
-  uint32_t L = 0, pos = 0, tries = 0, span = 0, flags = 0, gw = 0, gleft = 0;
-  int64_t d64 = 0, dhi = 0;
-  int32_t dlo = 0;
+  MaskT* pm = s_pm + threadIdx.x;
+  auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= (MaskT)1 << i; present |= 1u << a; };
+  auto del_letter = [&](uint32_t a, uint32_t i) { const MaskT v = pm[a * kThreads] & ~((MaskT)1 << i); pm[a * kThreads] = v; if (v == 0) present &= ~(1u << a); };
+  uint32_t wi = 0, L = 0, pos = 0, tries = 0, span = 0, flags = 0;
+  int64_t P = 0;
+  int32_t d = 0, dlo = 0;
   MaskT mask = 0, vpos = 0, lmask = 0;
-  RngRing rng; rng.buf = s_rng + tid; rng.start(A.seed, 0, 0);
+  RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(A.seed, 0, 0);
 
-  for (uint32_t it = 0;; it++) {
-    if ((it & (kTick - 1u)) == 0u) {
-      // ---- TICK (1): what ended since the last tick
-      if (pending) {
-        const uint32_t rec = s_keep[2 * kThreads + tid];
-        if (pending == 1) {
-          const int64_t P = (int64_t)(((uint64_t)s_keep[kThreads + tid] << 32) | s_keep[tid]);
-          O.len[rec] = (uint8_t)L; O.w[rec] = P + d64; O.mask[rec] = (uint64_t)mask;
-          uint4* dst = reinterpret_cast<uint4*>(O.seq + (size_t)rec * MD_DECOY_ROW);
-#pragma unroll
-          for (uint32_t q = 0; q < (kWords + 3) / 4; q++) {
-            uint4 v;
-            v.x = s_seq[(4 * q + 0) * kThreads + tid];
-            v.y = 4 * q + 1 < kWords ? s_seq[(4 * q + 1) * kThreads + tid] : 0u;
-            v.z = 4 * q + 2 < kWords ? s_seq[(4 * q + 2) * kThreads + tid] : 0u;
-            v.w = 4 * q + 3 < kWords ? s_seq[(4 * q + 3) * kThreads + tid] : 0u;
-            dst[q] = v;
+  uint32_t rng_timer = 1;
+  for (;;) {
+    // ---- refill: when at least 8 lanes are free (or nobody works), they fetch and grow new attempts together
+    uint32_t busy_m = __ballot_sync(0xffffffffu, busy);
+    uint32_t free_m = 0;
+    if (__popc(busy_m) <= 32 - kRefillMin) free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
+    if (free_m && (__popc(free_m) >= kRefillMin || busy_m == 0)) {
+      if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, (uint64_t)mask, P + d, T, PV); pending = 0; }
+      if (!busy && !drained) {
+        const uint32_t q = atomicAdd(A.queue, 1u);
+        if (q >= total) drained = true;
+        else {
+          wi = A.remap ? A.remap[q] : q;
+          const uint32_t li = find_entry_coarse(A.att_off, A.att_blk, wi);
+          const md_precursor pr = A.prec[A.list[li]];
+          P = pr.mass;
+          rng.start(A.seed, pr.spectrum_id, A.att_base[li] + (wi - A.att_off[li]));
+          // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
+          int64_t w = MD_WATER_UDA;
+          L = 0; mask = 0; vpos = 0; present = 0; bool dead = false;
+          for (int a = 0; a < MD_ALPHABET_SIZE; a++) pm[a * kThreads] = 0;
+          for (;;) {
+            const uint32_t a = rng.below(MD_ALPHABET_SIZE);
+            if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
+            if (!kNarrow || L < kBits) {
+              if (VMODE == 1 && (int)a == va) vpos |= (MaskT)1 << L;
+              add_letter(a, L); seq.at(L) = (uint8_t)a;
+            }
+            L++;
+            w += s_mprime[a];
+            if (w > pr.hi) break;
           }
-        } else if (pending == 2 || !kNarrow) {
-          O.len[rec] = 0;
-        } else {
-          A.spill[atomicAdd(A.spill_n, 1u)] = make_uint2(rec, s_keep[3 * kThreads + tid]);   // the wide pass runs this attempt (same RNG stream, same record)
+          if (kNarrow && !dead && L > kBits) {
+            A.spill[atomicAdd(A.spill_n, 1u)] = wi;       // the wide pass runs this attempt (same RNG stream, same slot)
+          } else {
+            const int64_t dd = w - P, dl = pr.lo - P, sp = pr.hi - pr.lo;
+            if (!dead && (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF || dl > 0x3FFFFFFF || dl < -0x3FFFFFFF || sp < 0 || sp > 0x7FFFFFFF)) { flags |= 2u; dead = true; }
+            if (dead) store_attempt(O, wi, seq, 0, 0, 0, T, PV);
+            else {
+              busy = true; tries = 0; pos = 0; d = (int32_t)dd; dlo = (int32_t)dl; span = (uint32_t)sp;
+              lmask = L >= kBits ? ~(MaskT)0 : (((MaskT)1 << L) - 1);
+            }
+          }
         }
-        pending = 0;
       }
-      // ---- TICK (2): free lanes take the next attempts of the warp's pool
-      uint32_t wants = __ballot_sync(0xffffffffu, !busy);
-      while (wants != 0u && !drained) {
-        if (pool_n == 0u) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(A.queue, 32u);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (base >= total) { drained = true; break; }
-          const uint32_t wi = base + lane;
-          if (wi < total) {
-            uint32_t rec, li;
-            if (A.remap) { const uint2 r = A.remap[wi]; rec = r.x; li = r.y; }
-            else { rec = wi; li = find_entry_coarse(A.att_off, A.att_blk, wi); }
-            const md_precursor pr = A.prec[A.list[li]];
-            const int64_t dl = pr.lo - pr.mass, sp = pr.hi - pr.lo;
-            const bool bad = dl > 0x3FFFFFFF || dl < -0x3FFFFFFF || sp < 0 || sp > 0x3FFFFFFF;
-            pool[0 * 32 + lane] = (uint32_t)(uint64_t)pr.mass; pool[1 * 32 + lane] = (uint32_t)((uint64_t)pr.mass >> 32);
-            pool[2 * 32 + lane] = (uint32_t)(int32_t)dl; pool[3 * 32 + lane] = bad ? 0xFFFFFFFFu : (uint32_t)sp;
-            pool[4 * 32 + lane] = pr.spectrum_id; pool[5 * 32 + lane] = A.att_base[li] + (rec - A.att_off[li]);
-            pool[6 * 32 + lane] = rec; pool[7 * 32 + lane] = li;
-          }
-          __syncwarp();
-          pool_i = 0; pool_n = min(32u, total - base);
-        }
-        const uint32_t rank = (uint32_t)__popc(wants & ((1u << lane) - 1u));
-        if (!busy && rank < pool_n) {
-          const uint32_t e = pool_i + rank;
-          const uint32_t sp = pool[3 * 32 + e], rec = pool[6 * 32 + e];
-          if (sp == 0xFFFFFFFFu) { flags |= 2u; O.len[rec] = 0; }            // window outside the 32-bit residual range
-          else {
-            const int64_t P = (int64_t)(((uint64_t)pool[1 * 32 + e] << 32) | pool[0 * 32 + e]);
-            s_keep[tid] = pool[0 * 32 + e]; s_keep[kThreads + tid] = pool[1 * 32 + e]; s_keep[2 * kThreads + tid] = rec; s_keep[3 * kThreads + tid] = pool[7 * 32 + e];
-            dlo = (int32_t)pool[2 * 32 + e]; span = sp; dhi = (int64_t)dlo + (int64_t)sp;
-            rng.start(A.seed, pool[4 * 32 + e], pool[5 * 32 + e]);
-            d64 = (int64_t)MD_WATER_UDA - P;
-            busy = true; grow = true; L = 0; lmask = 0; present = 0; mask = 0; vpos = 0; pos = 0; tries = 0; gleft = 0;
-#pragma unroll
-            for (int a = 0; a < MD_ALPHABET_SIZE; a++) pm[a * kThreads] = 0;
-          }
-        }
-        const uint32_t taken = min((uint32_t)__popc(wants), pool_n);
-        pool_i += taken; pool_n -= taken;
-        __syncwarp();
-        wants = __ballot_sync(0xffffffffu, !busy);
-      }
-      if (__ballot_sync(0xffffffffu, busy) == 0u) break;       // the queue is empty and nobody works
-      // ---- TICK (3): the random-number rings, all lanes together
-      if (busy && rng.count <= kRing - 4u) rng.produce();
+      busy_m = __ballot_sync(0xffffffffu, busy);
     }
-    if (!busy) continue;
-    // ---- which LETTERS have a substitution that strictly reduces |d| follows from d alone (see DecoyTables) ...
-    const int32_t d = (int32_t)d64;
-    const bool dpos = d > 0;
-    const uint32_t x = 2u * (uint32_t)(d < 0 ? -d : d);
-    uint32_t fm;
-    {
-      const uint32_t gofs = dpos ? 0u : kAbove;
-      // number of gaps below x = the table's count at the bucket's first x + the (sorted) gaps of the bucket below x: two
-      // independent probes cover every bucket of the usual tables (padding: 0xFFFFFFFF); deeper buckets take the loop
-      const uint32_t k0 = s_gtab[(dpos ? 0u : kGapTab) + min(x >> gap_shift, kGapTab - 1u)];
-      uint32_t k = k0 + (s_gap[gofs + k0] < x ? 1u : 0u) + (s_gap[gofs + k0 + 1u] < x ? 1u : 0u);
-      if (gap_depth > 2u) { k = k0; for (uint32_t j = 0; j < gap_depth; j++) k += s_gap[gofs + k] < x ? 1u : 0u; }
-      fm = s_gmask[gofs + k];                                                            // d == 0: x == 0, k == 0, empty prefix
-    }
-    // ---- ... and the per-letter position masks give the first position of the pass that can improve: OR of the masks of
-    //      the qualifying letters -- or, when most letters qualify (right after a kick), the complement of the OR over
-    //      the few that do not (every position holds exactly one of the present letters).
-    MaskT cand;
-    {
-      const uint32_t m0 = fm & present, n0 = present & ~fm;
-      const bool inv = __popc(n0) < __popc(m0);
-      MaskT acc = 0;
-      for (uint32_t m = grow ? 0u : (inv ? n0 : m0); m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
-      cand = inv ? ~acc & lmask : acc;
-      cand = (pos < L && !grow) ? cand & (~(MaskT)0 << pos) : (MaskT)0;       // pos == L: the pass ended with a substitution
-    }
-    const bool sub = cand != 0;
-    if (grow && L >= kRows) {            // one more letter would not fit: > 60 residues (VARCHAR(60) would reject it), or > 32 in the narrow pass
-      pending = (kNarrow && L < MD_MAX_PEPTIDE_LEN) ? 3u : 2u; busy = false;
+    if (busy_m == 0) {
+      if (__ballot_sync(0xffffffffu, !drained || pending) == 0) break;
       continue;
     }
-    // ---- the step's random numbers: a fresh word for a kick or when the grow word is used up
-    uint32_t src = gw;
-    if (!sub && (!grow || gleft == 0u)) src = rng.next();
-    if (grow) gleft = gleft == 0u ? 3u : gleft - 1u;
-    const uint64_t rl = (uint64_t)src * (grow ? 1u : L);
-    const uint64_t t21 = (uint64_t)(uint32_t)rl * (uint32_t)MD_ALPHABET_SIZE;
-    gw = (uint32_t)t21;
-    const uint32_t p = sub ? MO::ffs(cand) - 1u : (grow ? L : (uint32_t)(rl >> 32));
-    const uint32_t old = grow ? 31u : (uint32_t)seq.at(p);
-    const int32_t m_old = s_mprime[old];
-    // best single substitution = letter whose (mass+fixed) is closest to mprime[old] - d; strict improvement, ties by
-    // alphabet order (the reference follows HashMap order there); computed for every lane, used by the substituting ones
-    uint32_t c;
-    {
-      const int32_t target = min(max(m_old - d, nn_lo), nn_hi);
-      const int32_t t2 = 2 * target;
-      const uint32_t k0 = s_nntab[(uint32_t)(target - nn_lo) >> nn_shift];
-      uint32_t k = k0 + (t2 > s_thr2[k0] ? 1u : 0u) + (t2 > s_thr2[k0 + 1u] ? 1u : 0u);   // nearest distinct mass (padding: INT32_MAX)
-      if (nn_depth > 2u) { k = k0; for (uint32_t j = 0; j < nn_depth; j++) k += t2 > s_thr2[k] ? 1u : 0u; }
-      c = sub ? (uint32_t)s_nnletter[k] : (uint32_t)(t21 >> 32);
-    }
-#ifdef MD_DECOY_CHECK
-    if (sub) { const int32_t nd = d + s_mprime[c] - m_old; if (!((uint32_t)(nd < 0 ? -nd : nd) < (uint32_t)(d < 0 ? -d : d) && c != old)) flags |= 4u; }
-#endif
-    // ---- put letter c at position p: remove_modification_at + swap + fixed modification of the new letter (:470-482)
-    {
-      const MaskT bit = (MaskT)1 << p;
-      if (VMODE != 0) { if (mask & bit) { d64 -= s_var[old]; mask &= ~bit; } }
-      d64 += s_mprime[c] - m_old;
-      seq.at(p) = (uint8_t)c;
-      if (!grow) { const MaskT v = pm[old * kThreads] & ~bit; pm[old * kThreads] = v; if (v == 0) present &= ~(1u << old); }
-      pm[c * kThreads] |= bit; present |= 1u << c;
-      if (VMODE == 1) vpos = (vpos & ~bit) | ((int)c == va ? bit : (MaskT)0);
-    }
-    if (grow) {
-      L++; lmask = (lmask << 1) | (MaskT)1;
-      if (d64 > dhi) {                   // the weight exceeds the upper limit (== does not stop, modified_peptide.rs:294-300): repair from here
-        grow = false; pos = 0; tries = 0;
-        if (d64 > 0x3FFFFFFF) { flags |= 2u; pending = 2; busy = false; }
+    // ---- keep the random-number rings topped up, all lanes together
+    if (--rng_timer == 0) { rng_timer = kRngPeriod; if (busy && rng.count <= kRing - 4) rng.produce(); }
+    if (busy) {
+      // ---- which LETTERS have a substitution that strictly reduces |d| follows from d alone (see DecoyTables) ...
+      uint32_t fm;
+      {
+        const uint32_t ad = (uint32_t)(d < 0 ? -d : d), x = 2u * ad;
+        const uint32_t gofs = d > 0 ? 0u : kAbove;
+        const uint32_t* g = s_gap + gofs;
+        uint32_t k = s_gtab[(d > 0 ? 0u : kGapTab) + min(x >> gap_shift, kGapTab - 1u)];
+        for (uint32_t gk = g[k]; gk < x; gk = g[k]) k++;                 // number of gaps below x (padding: 0xFFFFFFFF)
+        fm = s_gmask[gofs + k];                                          // d == 0: x == 0, k == 0, empty prefix
       }
-    } else if (sub) {
-      int32_t dn = (int32_t)d64;
-      bool hit = (uint32_t)dn - (uint32_t)dlo <= span;
-      if (VMODE == 1) {
-        if (!hit && vpos) { hit = try_variable_simple_d<MaskT>(M.nvar, vdelta, vpos, dn, mask, dlo, span); d64 = dn; }
-      } else if (VMODE == 2) {
-        if (!hit) {
-          LaneSeqCode<MaskT> sc{seq, T.code_of_a};
-          const int64_t P = (int64_t)(((uint64_t)s_keep[kThreads + tid] << 32) | s_keep[tid]);
-          int64_t w = P + d64; uint64_t m64 = (uint64_t)mask;
-          const int64_t lo = P + dlo;
-          if (md_try_variable(M, sc, L, w, m64, lo, lo + (int64_t)span, A.overflow)) hit = true;
-          d64 = w - P; mask = (MaskT)m64;
+      // ---- ... and the per-letter position masks give the first position of the pass that can improve: OR of the masks of
+      //      the qualifying letters -- or, when most letters qualify (right after a kick), the complement of the OR over
+      //      the few that do not (every position holds exactly one of the present letters).
+      MaskT cand;
+      {
+        const uint32_t m0 = fm & present, n0 = present & ~fm;
+        const bool inv = __popc(n0) < __popc(m0);
+        MaskT acc = 0;
+#ifdef MD_PM_UNROLL2
+        for (uint32_t m = inv ? n0 : m0; m;) {
+          MaskT v = pm[(__ffs(m) - 1) * kThreads]; m &= m - 1;
+          if (m) { v |= pm[(__ffs(m) - 1) * kThreads]; m &= m - 1; }
+          acc |= v;
         }
+#else
+        for (uint32_t m = inv ? n0 : m0; m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
+#endif
+        cand = inv ? ~acc & lmask : acc;
+        cand = pos < L ? cand & (~(MaskT)0 << pos) : (MaskT)0;           // pos == L: the pass ended with a substitution
       }
-      pos = p + 1;
-      if ((uint64_t)(d64 + 0x3FFFFFFF) > 0x7FFFFFFEull) { flags |= 2u; pending = 2; busy = false; }
-      else if (hit) { pending = 1; busy = false; }
-    } else {
-      pos = 0; tries++;
-      if ((uint64_t)(d64 + 0x3FFFFFFF) > 0x7FFFFFFEull) { flags |= 2u; pending = 2; busy = false; }
-      else if (tries == 100) { pending = 2; busy = false; }
+      // ---- the step: substitution at the first improving position (modified_peptide.rs:454-487), else the kick (:489-505)
+      const bool sub = cand != 0;
+      uint32_t p;
+      // the kick takes ONE word r of the attempt's stream: position = high half of r*L, letter = high half of low32(r*L)*21
+      uint32_t kick_lo = 0;
+      if (sub) p = MO::ffs(cand) - 1u;
+      else { const uint64_t rl = (uint64_t)rng.next() * L; p = (uint32_t)(rl >> 32); kick_lo = (uint32_t)rl; }
+      const uint32_t old = seq.at(p);
+      uint32_t c;
+      if (sub) {
+        // best single substitution = letter whose (mass+fixed) is closest to mprime[old] - d; strict improvement,
+        // ties by alphabet order (the reference follows HashMap order there)
+        const int32_t target = min(max(s_mprime[old] - d, nn_lo), nn_hi);
+        const int32_t t2 = 2 * target;
+        uint32_t k = s_nntab[(uint32_t)(target - nn_lo) >> nn_shift];
+        for (int32_t th = s_thr2[k]; t2 > th; th = s_thr2[k]) k++;       // nearest distinct mass (padding: INT32_MAX)
+        c = s_nnletter[k];
+#ifdef MD_DECOY_CHECK   // (debug builds) the letter filter and the nearest-mass search must agree
+        const int32_t nd = d + s_mprime[c] - s_mprime[old];
+        if (!((uint32_t)(nd < 0 ? -nd : nd) < (uint32_t)(d < 0 ? -d : d) && c != old)) { flags |= 4u; c = old; }
+#endif
+      } else {
+        c = (uint32_t)(((uint64_t)kick_lo * MD_ALPHABET_SIZE) >> 32);
+      }
+      // ---- put letter c at position p: remove_modification_at + swap + fixed modification of the new letter (:470-482)
+      {
+        const MaskT bit = (MaskT)1 << p;
+        if (VMODE != 0) { if (mask & bit) { d -= s_var[old]; mask &= ~bit; } }
+        d += s_mprime[c] - s_mprime[old];
+        seq.at(p) = (uint8_t)c; del_letter(old, p); add_letter(c, p);
+        if (VMODE == 1) vpos = (vpos & ~bit) | ((int)c == va ? bit : (MaskT)0);
+      }
+      bool hit = false;
+      if (sub) {
+        hit = (uint32_t)d - (uint32_t)dlo <= span;
+        if (VMODE == 1) {
+          if (!hit && vpos) hit = try_variable_simple_d<MaskT>(M.nvar, vdelta, vpos, d, mask, dlo, span);
+        } else if (VMODE == 2) {
+          if (!hit) {
+            TSeqCode sc{seq, T.code_of_a};
+            int64_t w = P + d; uint64_t m64 = (uint64_t)mask;
+            const int64_t lo = P + dlo;
+            if (md_try_variable(M, sc, L, w, m64, lo, lo + (int64_t)span, A.overflow)) hit = true;
+            const int64_t dd = w - P;
+            if (dd > 0x3FFFFFFF || dd < -0x3FFFFFFF) flags |= 2u;
+            d = (int32_t)dd; mask = (MaskT)m64;
+          }
+        }
+        pos = p + 1;
+      } else {
+        pos = 0; tries++;
+      }
+      if ((uint32_t)d + 0x3FFFFFFFu > 0x7FFFFFFEu) flags |= 2u;
+      if (hit) { pending = 1; busy = false; }
+      else if (!sub && tries == 100) { pending = 2; busy = false; }
     }
   }
   if (flags) atomicMax(A.overflow, (flags & 4u) ? 3 : 2);
-}
-
-// Attempt records -> what the selection and the score kernel read: the row as residue codes (padded to 16-byte chunks),
-// the 64-bit sequence hash, and Decoy::is_peptide (decoy.rs:49-60) -- a sequence that is a real peptide is no decoy.
-__global__ void __launch_bounds__(256) k_attempt_finish(uint32_t total, const uint8_t* __restrict__ rec_seq, const __grid_constant__ DecoyTables T, AttemptOut O,
-                                                        PeptideView PV) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const uint32_t L = O.len[i];
-  if (L == 0) return;
-  const uint4* src = reinterpret_cast<const uint4*>(rec_seq + (size_t)i * MD_DECOY_ROW);
-  uint8_t ascii[MD_DECOY_ROW];
-  uint4* row = reinterpret_cast<uint4*>(O.rows + (size_t)i * MD_DECOY_ROW);
-  uint64_t h = md_hash_init();
-  const uint32_t pad = MD_CODE_OTHER * 0x01010101u;
-#pragma unroll
-  for (uint32_t q = 0; q < MD_DECOY_ROW / 16; q++) {
-    uint4 out = make_uint4(pad, pad, pad, pad);
-    if (q * 16 < L) {
-      const uint4 v = __ldg(src + q);
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-      uint32_t o4[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t idx = q * 16 + k * 4 + j;
-          uint32_t code = MD_CODE_OTHER;
-          if (idx < L) {
-            code = T.code_of_a[(w4[k] >> (8 * j)) & 31u];
-            const uint8_t ch = md_letter_of(code);
-            ascii[idx] = ch; h = md_hash_step(h, ch);
-          }
-          o |= code << (8 * j);
-        }
-        o4[k] = o;
-      }
-      out = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-    }
-    row[q] = out;
-  }
-  h = md_hash_fin(h, L);
-  if (is_peptide(ascii, L, h, PV.ht_key, PV.ht_val, PV.ht_mask, PV.seq, PV.off, PV.len)) { O.len[i] = 0; return; }
-  O.hash[i] = h;
 }
 
 // vary_targets (decoy_generator.rs:265-296), counter-based: attempt a shuffles target (a mod T) of the spectrum
@@ -537,7 +439,9 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
 // earlier success), in attempt order, until the spectrum has n_per decoys (HashSet<Decoy>, decoy_generator.rs:40,164).
 // Linear time: accepted decoys and successes go into a shared-memory hash set keyed by the 64-bit sequence hash, each
 // entry remembering the lowest ordinal (accepted decoys first, then attempts in order) that carried the key; a success
-// is kept iff it is that first carrier.  (Sequences are identified by their 64-bit hash here.)  The attempt hashes are
+// is kept iff it is that first carrier.  A success that is NOT the first carrier of its hash is compared with that carrier
+// byte for byte: equal = a duplicate (the usual case); different = two sequences share a 64-bit hash, and the CTA redoes
+// the spectrum with exact comparisons (HashSet<Decoy> compares strings, decoy_generator.rs:40,164).  The attempt hashes are
 // read from HBM once (staged in shared memory); the kept rows are copied by the whole CTA, four lanes per 64-byte row.
 __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
                                                       const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, uint32_t max_na, AttemptOut A,
@@ -549,17 +453,37 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
   uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_hash + max_na); // slots
   uint16_t* s_list = reinterpret_cast<uint16_t*>(s_ord + slots);  // max_na: kept attempts, in order
   __shared__ uint32_t s_wsum[8];
+  __shared__ uint32_t s_collision;
   const uint32_t li = blockIdx.x, s = list[li];
   const uint32_t a0 = att_off[li], na = att_off[li + 1] - a0;
   const uint32_t have = dec_count[s];
   const uint64_t dbase = (uint64_t)s * n_per;
   const uint32_t smask = slots - 1;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_collision = 0;
+  // success `a` of this round against carrier `rep` (an accepted decoy if rep < have, else success rep - have): same sequence?
+  auto same_sequence = [&](uint32_t a, uint32_t rep) -> bool {
+    const uint32_t L = A.len[a0 + a];
+    const uint8_t* mine = A.rows + (uint64_t)(a0 + a) * MD_DECOY_ROW;
+    if (rep < have) {
+      if (dec_len[dbase + rep] != L) return false;
+      for (uint32_t i = 0; i < L; i++) if (dec_rows[md_dec_byte(n_slots, dbase + rep, i)] != mine[i]) return false;
+    } else {
+      if (A.len[a0 + rep - have] != L) return false;
+      const uint8_t* o = A.rows + (uint64_t)(a0 + rep - have) * MD_DECOY_ROW;
+      for (uint32_t i = 0; i < L; i++) if (o[i] != mine[i]) return false;
+    }
+    return true;
+  };
   for (uint32_t i = tid; i < slots; i += 256) { s_key[i] = 0ULL; s_ord[i] = 0xFFFFFFFFu; }
+  // MD_SELECT_HASH_MASK (test builds only) keeps a few bits of the hashes, so that colliding sequences are common
+#ifndef MD_SELECT_HASH_MASK
+#define MD_SELECT_HASH_MASK 0xFFFFFFFFFFFFFFFFull
+#endif
 #pragma unroll 4
   for (uint32_t a = tid; a < na; a += 256) {
     const uint32_t L = A.len[a0 + a];
-    unsigned long long h = __ldg(reinterpret_cast<const unsigned long long*>(A.hash) + a0 + a);
+    unsigned long long h = __ldg(reinterpret_cast<const unsigned long long*>(A.hash) + a0 + a) & MD_SELECT_HASH_MASK;
     s_hash[a] = L ? (h ? h : 1ULL) : 0ULL;
   }
   __syncthreads();
@@ -571,7 +495,7 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
       slot = (slot + 1) & smask;
     }
   };
-  for (uint32_t j = tid; j < have; j += 256) { const unsigned long long h = dec_hash[dbase + j]; insert(h ? h : 1ULL, j); }
+  for (uint32_t j = tid; j < have; j += 256) { const unsigned long long h = dec_hash[dbase + j] & MD_SELECT_HASH_MASK; insert(h ? h : 1ULL, j); }
   for (uint32_t a = tid; a < na; a += 256) { const unsigned long long h = s_hash[a]; if (h) insert(h, have + a); }
   __syncthreads();
   // keep flags + ordered compaction: thread t owns the contiguous chunk [t*per, (t+1)*per), per <= 16
@@ -585,8 +509,20 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
       uint32_t slot = (uint32_t)h & smask;
       while (s_key[slot] != h) slot = (slot + 1) & smask;
       keep = s_ord[slot] == have + a;
+      if (!keep && !same_sequence(a, s_ord[slot])) s_collision = 1;    // not a duplicate after all
     }
     if (keep) { keepbits |= 1u << (a - cb); c++; }
+  }
+  __syncthreads();
+  if (s_collision) {   // (two sequences with one 64-bit hash: practically never) exact: kept iff no accepted decoy and no earlier success is the same sequence
+    keepbits = 0; c = 0;
+    for (uint32_t a = cb; a < ce; a++) {
+      const unsigned long long h = s_hash[a];
+      bool keep = h != 0ULL;
+      for (uint32_t j = 0; j < have && keep; j++) { const unsigned long long hj = dec_hash[dbase + j] & MD_SELECT_HASH_MASK; if ((hj ? hj : 1ULL) == h && same_sequence(a, j)) keep = false; }
+      for (uint32_t b = 0; b < a && keep; b++) if (s_hash[b] == h && same_sequence(a, have + b)) keep = false;
+      if (keep) { keepbits |= 1u << (a - cb); c++; }
+    }
   }
   uint32_t incl = c;
   for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
@@ -708,26 +644,19 @@ __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restr
 }
 
 template <class MaskT>
-constexpr size_t random_smem_bytes() {
-  constexpr size_t rows = sizeof(MaskT) == 4 ? 32 : MD_MAX_PEPTIDE_LEN, words = (rows + 3) / 4;
-  return (words + kRing + 8 + 4) * kThreads * 4 + sizeof(MaskT) * MD_ALPHABET_SIZE * kThreads + (32 + 32 + 80 + 80 + 40) * 4 + 2 * kGapTab + kNnTab + 32;
-}
-template <class MaskT>
-void launch_random(md_ctx* ctx, int vmode, uint32_t grid, const RandomArgs& RA, const DecoyTables& T, const RecordOut& O) {
-  const size_t smem = random_smem_bytes<MaskT>();   // (the opt-in for it happened in random_occupancy)
-  if (vmode == 0) MD_LAUNCH(ctx, (k_decoy_random<0, MaskT>), grid, kThreads, smem, RA, ctx->mods, T, O);
-  else if (vmode == 1) MD_LAUNCH(ctx, (k_decoy_random<1, MaskT>), grid, kThreads, smem, RA, ctx->mods, T, O);
-  else MD_LAUNCH(ctx, (k_decoy_random<2, MaskT>), grid, kThreads, smem, RA, ctx->mods, T, O);
+void launch_random(md_ctx* ctx, int vmode, uint32_t grid, const RandomArgs& RA, const DecoyTables& T, const AttemptOut& O, const PeptideView& PV) {
+  if (vmode == 0) MD_LAUNCH(ctx, (k_decoy_random<0, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
+  else if (vmode == 1) MD_LAUNCH(ctx, (k_decoy_random<1, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
+  else MD_LAUNCH(ctx, (k_decoy_random<2, MaskT>), grid, kThreads, 0, RA, ctx->mods, T, O, PV);
 }
 template <class MaskT>
 int random_occupancy(int vmode) {
   static int cached[3] = {0, 0, 0};     // (a property of the kernel image: queried once per process)
   if (cached[vmode]) return cached[vmode];
   int occ = 0;
-  const size_t smem = random_smem_bytes<MaskT>();
-  if (vmode == 0) { MD_CUDA(cudaFuncSetAttribute(k_decoy_random<0, MaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<0, MaskT>, kThreads, smem)); }
-  else if (vmode == 1) { MD_CUDA(cudaFuncSetAttribute(k_decoy_random<1, MaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<1, MaskT>, kThreads, smem)); }
-  else { MD_CUDA(cudaFuncSetAttribute(k_decoy_random<2, MaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<2, MaskT>, kThreads, smem)); }
+  if (vmode == 0) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<0, MaskT>, kThreads, 0));
+  else if (vmode == 1) MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<1, MaskT>, kThreads, 0));
+  else MD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decoy_random<2, MaskT>, kThreads, 0));
   cached[vmode] = occ > 0 ? occ : 1;
   return cached[vmode];
 }
@@ -788,17 +717,6 @@ DecoyTables make_tables(const ModTables& M) {
         T.gap_tab[sgn][b] = (uint8_t)c;
       }
     }
-    // residual steps: gaps that share a bucket with its first x (the table holds the count at the bucket's first x)
-    T.gap_depth = 0;
-    for (int sgn = 0; sgn < 2; sgn++) {
-      const uint32_t* g = sgn == 0 ? T.gapb_sorted : T.gapa_sorted;
-      for (uint32_t b = 0; b < kGapTab; b++) {
-        const uint64_t x1 = b + 1 == kGapTab ? ~0ull : ((uint64_t)(b + 1) << T.gap_shift);   // the last bucket takes every larger x
-        uint32_t c = T.gap_tab[sgn][b], e = c;
-        while (e < MD_ALPHABET_SIZE && g[e] != 0xFFFFFFFFu && (uint64_t)g[e] < x1) e++;
-        T.gap_depth = std::max(T.gap_depth, e - c);
-      }
-    }
   }
   // nearest-mass tables
   {
@@ -815,13 +733,6 @@ DecoyTables make_tables(const ModTables& M) {
       uint32_t c = 0;
       while (c + 1 < (uint32_t)n && 2 * t0 > (int64_t)T.nn_thr2[c]) c++;
       T.nn_tab[b] = (uint8_t)c;
-    }
-    T.nn_depth = 0;
-    for (uint32_t b = 0; b < kNnTab; b++) {
-      const int64_t t1 = (int64_t)T.nn_lo + ((int64_t)(b + 1) << T.nn_shift) - 1;          // last t of the bucket
-      uint32_t c = T.nn_tab[b], e = c;
-      while (e + 1 < (uint32_t)n && 2 * std::min<int64_t>(t1, T.nn_hi) > (int64_t)T.nn_thr2[e]) e++;
-      T.nn_depth = std::max(T.nn_depth, e - c);
     }
   }
   return T;
@@ -900,7 +811,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   std::vector<uint32_t> list, off, base, blk;
   const double later_factor = getenv("MD_DECOY_LATER_PCT") ? std::max(100, atoi(getenv("MD_DECOY_LATER_PCT"))) / 100.0 : 1.05;   // head room of the later rounds (swept on C2: 100..180 %)
   const uint32_t want0_pct = getenv("MD_DECOY_WANT0_PCT") ? (uint32_t)std::max(100, atoi(getenv("MD_DECOY_WANT0_PCT"))) : 110u;   // round 0 asks for n * 1.10 + 32 attempts (swept on C2: 100..160 %)
-  for (int round = 0; round < 64; round++) {
+  for (int round = 0;; round++) {   // until every spectrum has its decoys or has used up its attempts (every round makes progress)
     list.clear(); off.assign(1, 0); base.clear();
     // How many attempts each unfinished spectrum gets this round.  A spectrum's decoys are its first n distinct successes
     // in attempt order, so asking for too many only wastes work; asking for too few costs another round, and a round
@@ -938,11 +849,9 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     MD_CUDA(cudaMemcpyAsync(d_base.p, base.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (mode == MD_DECOY_REFERENCE_RANDOM) {
-      // narrow pass (32-bit position masks) over every attempt, then the wide pass over those that grew past 32 residues;
-      // both leave attempt records, which k_attempt_finish turns into score rows + hashes (and drops real peptides)
+      // narrow pass (32-bit position masks) over every attempt, then the wide pass over those that grew past 32 residues
       MD_CUDA(cudaMemsetAsync(d_queue.p, 0, 4 * sizeof(uint32_t), ctx->stream));
-      W.t_spill.need(2 * (size_t)total + 2);
-      W.rec_seq.need((size_t)total * MD_DECOY_ROW + 64);
+      W.t_spill.need((size_t)total + 1);
       RandomArgs RA;
       {   // coarse index: entry of every 1024th work item (+ one past the end)
         const uint32_t nb = (total >> kBlkLog) + 2;
@@ -957,20 +866,16 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
         MD_CUDA(cudaMemcpyAsync(W.t_blk.p, blk.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
       }
       RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total; RA.att_blk = W.t_blk.p;
-      RA.seed = seed; RA.overflow = d_ovf.p; RA.gap_depth = T.gap_depth; RA.nn_depth = T.nn_depth;
-      const RecordOut RO{W.rec_seq.p, W.att_len.p, W.att_mask.p, W.att_w.p};
-      uint2* spill = reinterpret_cast<uint2*>(W.t_spill.p);
-      const uint32_t want_ctas = (total + kThreads - 1) / kThreads;
+      RA.seed = seed; RA.overflow = d_ovf.p;
       if (!wide_only) {
-        RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = spill; RA.spill_n = d_queue.p + 1;
-        launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>(want_ctas, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, RO);
-        RA.queue = d_queue.p + 2; RA.remap = spill; RA.remap_n = d_queue.p + 1; RA.spill = nullptr; RA.spill_n = nullptr;
-        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>(want_ctas, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, RO);
+        RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = W.t_spill.p; RA.spill_n = d_queue.p + 1;
+        launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, O, PV);
+        RA.queue = d_queue.p + 2; RA.remap = W.t_spill.p; RA.remap_n = d_queue.p + 1; RA.spill = nullptr; RA.spill_n = nullptr;
+        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, O, PV);
       } else {
         RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = nullptr; RA.spill_n = nullptr;
-        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>(want_ctas, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, RO);
+        launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, O, PV);
       }
-      MD_LAUNCH(ctx, k_attempt_finish, blocks(total), 256, 0, total, W.rec_seq.p, T, O, PV);
     } else {
       MD_LAUNCH(ctx, k_decoy_permute, blocks(total, kThreads), kThreads, 0, W.prec.p, d_list.p, d_off.p, d_base.p, n_list, total, seed, T, W.cand_off.p,
                 W.cand_desc.p, W.cand_mask.p, W.cand_w.p, ctx->index.rows.p, O, PV);

@@ -420,3 +420,36 @@ def test_gather_psms_single_rank_and_device_pointers(gpu):
     gpu.sync()
     assert allr.cpu().numpy().tobytes() == want.tobytes()
     gpu.comm_destroy()
+
+
+def test_decoy_selection_is_exact_when_hashes_collide(cpu, tmp_path):
+    """k_decoy_select finds duplicates through a hash set; a success whose hash is already carried by a different sequence
+    must still be kept.  A test build of the library that keeps only 6 bits of the hashes makes such collisions the rule:
+    its decoys must still equal the oracle's (which compares strings)."""
+    import os
+    import shutil
+    import subprocess
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "max-decoy_b200", "csrc")
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("no nvcc to make the test build")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    obj, so = str(tmp_path / "decoy_hash6.o"), str(tmp_path / "libmaxdecoy_hash6.so")
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-cudart", "static"]
+    subprocess.check_call([nvcc] + flags + ["-DMD_SELECT_HASH_MASK=0x3Full", "-c", os.path.join(csrc, "decoy.cu"), "-o", obj])
+    others = [os.path.join(csrc, f) for f in ("api.o", "comm.o", "digest.o", "index.o", "exhaustive.o", "score.o")]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", so, obj] + others + ["-ldl"])
+    g = maxdecoy.Engine(lib=maxdecoy.load(so))
+    try:
+        prots = list(wl.proteins(300))
+        for e in (g, cpu):
+            e.digest(prots, 2, 5, 50)
+            e.set_modifications([synth.CAM], 0)
+            e.index_build()
+        sp, _ = wl.spectra(300, 24, 2)
+        pre = wl.precursors_of(g, sp)
+        dg = g.generate_decoys(pre, 200, seed=11)
+        dc = cpu.generate_decoys(pre, 200, seed=11)
+        assert len(dg["attempt"]) > 3000
+        assert_tables_equal(dg, dc)
+    finally:
+        g.close()
