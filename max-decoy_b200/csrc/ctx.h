@@ -64,6 +64,8 @@ struct IdentifyWorkspace {
   DevBuf<int32_t> pk_bin; DevBuf<int32_t> pk_yq; DevBuf<uint32_t> pk_count; DevBuf<int32_t> pk_hbin;
   // scores
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
+  DevBuf<uint32_t> left_list;        // spectra the pipelined score kernel left to k_score
+  DevBuf<uint8_t> tab_pool, tab_desc; DevBuf<uint16_t> cand_order;   // k_build_tables / k_cand_order -> k_score_pipe
   DevBuf<unsigned long long> part_top; DevBuf<uint32_t> parts_done;   // spectra split into parts (open searches): per-part top-k keys, arrival counters
   DevBuf<uint8_t> cub_tmp;
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)

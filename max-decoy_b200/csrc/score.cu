@@ -31,6 +31,8 @@
 // caller asks for all scores.
 #include "cubx.cuh"
 
+#include <algorithm>
+
 namespace {
 
 inline uint32_t blocks(uint64_t n, uint32_t bs = 256) { return (uint32_t)((n + bs - 1) / bs); }
@@ -199,18 +201,25 @@ struct ScoreArgs {
   // chunks each; a part leaves its K best keys in part_top and the last part to finish (parts_done) writes the PSM rows
   uint32_t parts; unsigned long long* part_top; uint32_t* parts_done;
   uint16_t* gmap; uint32_t* gbits; uint32_t gmap_stride;   // per-CTA block map / block bitmap in HBM for tables beyond kMapCap blocks
+  // work items: n_work spectra, work item i = spectrum remap[i] (or i itself without a list).  The pipelined kernel leaves the
+  // spectra it cannot hold in left_list / left_n; k_score then runs over that list.
+  uint32_t n_work; const uint32_t* remap; uint32_t* left_list; uint32_t* left_n;
+  const uint32_t* n_work_dev;   // if set: the number of work items is read from device memory (the list another kernel has just left)
 };
 
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0xAAAAAAABu) >> 1; }
 
+// (not volatile: the table does not change while candidates are scored against it, and the scheduler must be free to issue
+// the independent loads of a residue's fragments back to back instead of one dependent map -> table pair after the other;
+// the addresses derive from candidate rows loaded behind the barrier that publishes the table, so no load can move above it)
 __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
   int32_t v;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void acc_wide(int64_t& acc, int32_t v) {  // acc += v as one IMAD.WIDE
@@ -229,6 +238,14 @@ __device__ __forceinline__ int32_t gather(uint32_t bin, const TableView& V) {
   const uint32_t t = e & (bin | ~(kBlk - 1u));
   return lds_s32(V.tab_s + (t << 2));
 }
+// the two halves of a gather: fragment bin -> table index (block map), table index -> entry
+template <bool MAPG>
+__device__ __forceinline__ uint32_t gather_index(uint32_t bin, const TableView& V) {
+  const uint32_t blk = min(bin >> kBlkShift, V.nblk);
+  const uint32_t e = MAPG ? (uint32_t)V.gmap[blk] : lds_u16(V.map_s + 2u * blk);
+  return e & (bin | ~(kBlk - 1u));
+}
+__device__ __forceinline__ int32_t gather_entry(uint32_t t, const TableView& V) { return lds_s32(V.tab_s + (t << 2)); }
 struct LaneTab { uint32_t q, r, vq, vr; };      // lane = residue code
 constexpr uint32_t kStop = 1u << 30;            // added to the running bin at the last residue: every later bin misses
 
@@ -263,8 +280,12 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   const uint32_t nsplit = cr.len > 0 ? cr.len - 1 : 0;   // residues 0..len-2 are followed by a split
   if (nsplit == 0) QB += kStop;
   int64_t acc = 0;
+  // (the first two 16-residue chunks are requested together: one round trip to L2 / HBM instead of two for the usual 17..32-residue candidate)
+  const uint4 v0 = __ldg(cr.row);
+  uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+  if (nword > 4) v1 = __ldg(cr.row + 1);
   for (uint32_t c = 0; c * 4 < nword; c++) {
-    const uint4 v = __ldg(c < 2 ? cr.row + c : cr.row_hi + (c - 2));
+    const uint4 v = c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)));
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -281,16 +302,21 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         QB += q; R1 += r;
         if (R1 >= w) { R1 -= w; QB++; }
         // |T| <= 151 * 50 * 2^16 < 2^29: up to four entries add up in 32 bits, then one IMAD.WIDE into the 64-bit score
-        int32_t s4 = gather<MAPG>(QB, V) + gather<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);                // fragment charge 1
+        // all block-map loads of the residue first, then all table loads: the fragments are independent of one another
+        const uint32_t ib1 = gather_index<MAPG>(QB, V), iy1 = gather_index<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);     // fragment charge 1
+        uint32_t ib2 = 0, iy2 = 0, ib3 = 0, iy3 = 0;
         if (NCH >= 2) {
-          s4 += gather<MAPG>(((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
-          s4 += gather<MAPG>(((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
+          ib2 = gather_index<MAPG>(((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
+          iy2 = gather_index<MAPG>(((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
         }
-        acc_wide(acc, s4);
         if (NCH >= 3) {
-          acc_wide(acc, gather<MAPG>(div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V) +
-                            gather<MAPG>(div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V));
+          ib3 = gather_index<MAPG>(div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V);
+          iy3 = gather_index<MAPG>(div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V);
         }
+        int32_t s4 = gather_entry(ib1, V) + gather_entry(iy1, V);
+        if (NCH >= 2) s4 += gather_entry(ib2, V) + gather_entry(iy2, V);
+        acc_wide(acc, s4);
+        if (NCH >= 3) acc_wide(acc, gather_entry(ib3, V) + gather_entry(iy3, V));
         if (pos + 1 == nsplit) QB += kStop;   // the next residue is the last one
       }
     }
@@ -413,7 +439,9 @@ __device__ __noinline__ void prefetch_spectrum(const ScoreArgs& A, SpecShared& s
   uint32_t vn = 0;
   if (lane == 0) vn = atomicAdd(A.work, 1u);
   vn = __shfl_sync(0xffffffffu, vn, 0);
-  const uint32_t sn = vn / A.parts;          // work item -> (spectrum, part); sn >= n_spec ends the CTA
+  const uint32_t wn = vn / A.parts;          // work item -> (spectrum, part); sn >= n_spec ends the CTA
+  const uint32_t n_work = A.n_work_dev ? __ldcg(A.n_work_dev) : A.n_work;
+  const uint32_t sn = wn < n_work ? (A.remap ? A.remap[wn] : wn) : A.n_spec;
   SpecMeta m;
   m.part = vn % A.parts; m.c_lo = 0; m.c_hi = 0;
   m.s = sn; m.pre_blocks = 0; m.nact = 0; m.nt = 0; m.nd = 0; m.npk = 0; m.hbin = -1; m.t0c = 0; m.pk0 = 0;
@@ -808,6 +836,420 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   if (lane == 0 && wp) { atomicAdd(&A.stat64[0], wp); atomicAdd(&A.stat64[1], wb); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4, pipelined: tables are built ahead by their own kernel, a loader warp streams them into shared memory with bulk
+// asynchronous copies, and the scorer warps never meet at a barrier
+// ------------------------------------------------------------------------------------------------
+// k_score above runs a spectrum's phases one after the other behind block-wide barriers (stage, sort, build, score,
+// top-k), so the shared-memory pipe and the issue slots idle through every phase change and behind the slowest warp of
+// the scoring phase.  Here the phases are taken apart:
+//   k_build_tables  one CTA per spectrum, the whole GPU at once: number the occupied 64-bin blocks, write the block map
+//                   and fill the table DIRECTLY -- T[b] = 151*y[b] - sum of y over the peaks within 75 bins, evaluated per
+//                   bin from the few peaks that reach it: no zero fill, no difference array, no scan -- into one
+//                   contiguous record per spectrum in HBM: [block map][all-zero block][occupied blocks].  It depends on
+//                   the spectra only.
+//   k_cand_order    one CTA per spectrum: the candidates counting-sorted by length, longest first (units of 32 then hold
+//                   candidates of one length).
+//   k_score_pipe    one persistent CTA per SM.  A LOADER warp takes the next spectrum from the queue, finds room for its
+//                   table in a RING of shared-memory blocks (two spectra are resident whenever their tables fit side by
+//                   side) and issues cp.async.bulk copies of map, table and candidate order that complete on the slot's
+//                   mbarrier.  23 SCORER warps each pull 32-candidate units of the current spectrum, keep their K best
+//                   keys in registers, and when the units run out leave them in shared memory and walk on to the next
+//                   spectrum if its table has landed; the last warp to leave a spectrum merges the lists, writes the PSM
+//                   rows and releases the slot (empty mbarrier).
+// Same arithmetic as k_score (score_one): bit-identical rows.  Batches this path does not take (top_k > 8, spectra split
+// into parts) use k_score; a spectrum it cannot hold (more than 512 binned peaks, a block map beyond 4096 entries, a table
+// beyond the ring) goes onto a list that k_score works off afterwards.
+#ifndef MD_PIPE_THREADS
+#define MD_PIPE_THREADS 768
+#endif
+constexpr uint32_t kPipeThreads = MD_PIPE_THREADS, kPipeWarps = kPipeThreads / 32;
+constexpr uint32_t kScoreWarps = kPipeWarps - 1, kLoaderWarp = kPipeWarps - 1;
+constexpr uint32_t kPMapCap = 4096;        // block-map entries per slot (262k bins)
+constexpr uint32_t kPOrder = 2048;         // candidates that are sorted by length (spectra with more are walked in their natural order)
+constexpr uint32_t kPPeaks = 512;          // binned peaks k_build_tables stages
+constexpr uint32_t kPoolBlocks = 856;      // most 64-bin blocks (the all-zero block included) of a table the pipelined kernel takes
+constexpr uint32_t kRingBytes = 214 * 1024; // shared-memory ring that holds the table records (block map + table) of two spectra
+constexpr uint32_t kPipeEnd = 0xFFFFFFFFu, kTabLeft = 0xFFFFFFFFu;
+constexpr uint32_t kTabThreads = 256;
+
+// where a spectrum's table record lies in the pool.  nblk == 0: the spectrum is not scored (too few peaks); nact == kTabLeft: k_score takes it
+struct TabDesc { unsigned long long off; uint32_t nact, nblk; };
+__host__ __device__ inline uint32_t tab_map_bytes(uint32_t nblk) { return ((nblk + 1u) * 2u + 15u) & ~15u; }
+constexpr size_t kTabMaxBytes = (((size_t)kPMapCap + 1) * 2 + 15) / 16 * 16 + (size_t)kPoolBlocks * kBlk * 4;
+
+__global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __restrict__ peak_off, const int32_t* __restrict__ pk_bin, const int32_t* __restrict__ pk_yq,
+                                                              const uint32_t* __restrict__ pk_count, const int32_t* __restrict__ pk_hbin, uint8_t* __restrict__ pool,
+                                                              unsigned long long* __restrict__ pool_top, TabDesc* __restrict__ desc) {
+  __shared__ int32_t s_bin[kPPeaks], s_yq[kPPeaks];
+  __shared__ uint32_t s_bits[kPMapCap / 32], s_pre[kPMapCap / 32];
+  __shared__ uint16_t s_blk[kPoolBlocks];
+  __shared__ uint32_t s_nact;
+  __shared__ unsigned long long s_base;
+  const uint32_t s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int32_t hbin = pk_hbin[s];
+  const uint32_t npk = pk_count[s];
+  const uint64_t pk0 = peak_off[s];
+  const uint32_t NB = hbin >= 0 ? (uint32_t)hbin + kXcorrOffset + 1 : 0u;       // table bins [0, NB)
+  const uint32_t nblk = (NB + kBlk - 1) >> kBlkShift, nwords = (nblk + 31) >> 5;
+  if (hbin < 0 || NB > kMaxBins) { if (tid == 0) desc[s] = TabDesc{0ull, 0u, 0u}; return; }
+  if (npk > kPPeaks || nblk > kPMapCap) { if (tid == 0) desc[s] = TabDesc{0ull, kTabLeft, nblk}; return; }
+  for (uint32_t i = tid; i < npk; i += kTabThreads) { s_bin[i] = pk_bin[pk0 + i]; s_yq[i] = pk_yq[pk0 + i]; }
+  for (uint32_t i = tid; i < nwords; i += kTabThreads) s_bits[i] = 0;
+  __syncthreads();
+  for (uint32_t p = tid; p < npk; p += kTabThreads) {     // every bin within 75 of a peak
+    const int32_t bp = s_bin[p];
+    const uint32_t b0 = (uint32_t)max(bp - kXcorrOffset, 0) >> kBlkShift, b1 = min((uint32_t)(bp + kXcorrOffset), NB - 1) >> kBlkShift;
+    for (uint32_t k = b0; k <= b1; k++) atomicOr(&s_bits[k >> 5], 1u << (k & 31));
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive popcount prefix over the bitmap words
+    uint32_t run = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
+      const uint32_t i = w0 + lane;
+      const uint32_t c = i < nwords ? (uint32_t)__popc(s_bits[i]) : 0u;
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+      if (i < nwords) s_pre[i] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      s_nact = run;
+      if (run + 1u <= kPoolBlocks && tab_map_bytes(nblk) + (run + 1u) * kBlk * 4u <= kRingBytes) s_base = atomicAdd(pool_top, (unsigned long long)tab_map_bytes(nblk) + (unsigned long long)(run + 1u) * kBlk * 4u);
+    }
+  }
+  __syncthreads();
+  const uint32_t nact = s_nact;
+  if (nact + 1u > kPoolBlocks || tab_map_bytes(nblk) + (nact + 1u) * kBlk * 4u > kRingBytes) { if (tid == 0) desc[s] = TabDesc{0ull, kTabLeft, nblk}; return; }
+  const unsigned long long base = s_base;
+  if (tid == 0) desc[s] = TabDesc{base, nact, nblk};
+  // ---- block map: entry = (block of the record << 6) | 63, block 0 of the record = the all-zero block every miss reads
+  uint16_t* gmap = reinterpret_cast<uint16_t*>(pool + base);
+  const uint32_t map_entries = tab_map_bytes(nblk) / 2u;
+  for (uint32_t k = tid; k < map_entries; k += kTabThreads) {
+    uint32_t m = 0;
+    if (k < nblk) {
+      const uint32_t wd = s_bits[k >> 5];
+      if ((wd >> (k & 31)) & 1u) {
+        const uint32_t c = s_pre[k >> 5] + (uint32_t)__popc(wd & ((1u << (k & 31)) - 1u));
+        m = c + 1u; s_blk[c] = (uint16_t)k;
+      }
+    }
+    gmap[k] = (uint16_t)(m ? (m << kBlkShift) | (kBlk - 1u) : 0u);
+  }
+  int4* gtab = reinterpret_cast<int4*>(pool + base + tab_map_bytes(nblk));
+  if (tid < kBlk / 4) gtab[tid] = make_int4(0, 0, 0, 0);
+  __syncthreads();
+  // ---- the table: eight threads per block, eight bins per thread; the peaks are sorted and unique by bin, those within 75
+  //      bins of the thread's bins are consecutive
+  for (uint32_t wk = tid; wk < nact * 8u; wk += kTabThreads) {
+    const uint32_t c = wk >> 3, sub = wk & 7u;
+    const int32_t x0 = (int32_t)((uint32_t)s_blk[c] << kBlkShift) + (int32_t)(sub * 8u);
+    uint32_t lo = 0, hi = npk;                          // first peak with bin >= x0 - 75
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_bin[mid] < x0 - kXcorrOffset) lo = mid + 1; else hi = mid; }
+    int32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = 0;
+    for (uint32_t p = lo; p < npk; p++) {
+      const int32_t bp = s_bin[p];
+      if (bp > x0 + 7 + kXcorrOffset) break;
+      const int32_t y = s_yq[p];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int32_t d = bp - (x0 + j);
+        t[j] -= (d <= kXcorrOffset && d >= -kXcorrOffset) ? y : 0;
+        t[j] += d == 0 ? 151 * y : 0;
+      }
+    }
+    int4* dst = gtab + (size_t)(c + 1u) * (kBlk / 4) + sub * 2u;
+    dst[0] = make_int4(t[0], t[1], t[2], t[3]); dst[1] = make_int4(t[4], t[5], t[6], t[7]);
+  }
+}
+
+// candidates of every spectrum with at most kPOrder of them, counting-sorted by length (longest first) -> order[s * kPOrder + i]
+__global__ void __launch_bounds__(256) k_cand_order(const ScoreArgs A, uint32_t n_per, uint16_t* __restrict__ order) {
+  __shared__ uint32_t hist[64];
+  const uint32_t s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const uint64_t t0c = A.cand_off[s];
+  const uint32_t nt = (uint32_t)(A.cand_off[s + 1] - t0c), nd = A.dec_count ? A.dec_count[s] : 0u, ncand = nt + nd;
+  if (ncand > kPOrder || A.pk_hbin[s] < 0) return;
+  if (tid < 64) hist[tid] = 0;
+  __syncthreads();
+  uint8_t lens[kPOrder / 256];
+#pragma unroll
+  for (uint32_t h = 0; h < kPOrder / 256; h++) {
+    const uint32_t v = tid + h * 256;
+    lens[h] = v < ncand ? (uint8_t)cand_len(A, s, v, nt, t0c, n_per) : (uint8_t)0;
+  }
+#pragma unroll
+  for (uint32_t h = 0; h < kPOrder / 256; h++) if (tid + h * 256 < ncand) atomicAdd(&hist[63u - min((uint32_t)lens[h], 63u)], 1u);
+  __syncthreads();
+  if (tid < 32) {  // exclusive prefix over the 64 buckets
+    const uint32_t h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
+    uint32_t incl = h0 + h1;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    hist[2 * lane] = incl - h0 - h1; hist[2 * lane + 1] = incl - h1;
+  }
+  __syncthreads();
+  uint16_t* out = order + (size_t)s * kPOrder;
+#pragma unroll
+  for (uint32_t h = 0; h < kPOrder / 256; h++) {
+    const uint32_t v = tid + h * 256;
+    if (v < ncand) out[atomicAdd(&hist[63u - min((uint32_t)lens[h], 63u)], 1u)] = (uint16_t)v;
+  }
+}
+
+struct PipeSlot {
+  md_precursor pr;
+  uint64_t t0c;
+  uint32_t s, nt, nd, ncand, nunits, nblk, scored, sorted, left, base;
+  uint32_t unit;      // next unit of the spectrum (scorers)
+  uint32_t done;      // scorer warps that have left the spectrum
+};
+struct PipeShared {
+  PipeSlot slot[2];
+  unsigned long long ready[2], empty[2];                       // mbarriers
+  unsigned long long wtop[2][kScoreWarps][kFastTopK];
+  uint32_t state[2];   // (diagnosis) 0 = the slot's spectrum has left, 1 = the loader is on its next one, 2 = copies issued
+  uint32_t blocked[2]; // (diagnosis) the loader is waiting for the ring to drain before it can place this slot's record
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk asynchronous copy (the TMA engine moves the bytes; they count towards the mbarrier's transaction)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+               "r"(smem_u32(bar)) : "memory");
+}
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint runs out), so a
+// waiting warp takes no issue slots from the warps it is waiting for
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+  return ok != 0;
+}
+// (a wait that lasts seconds is a protocol error: stop the kernel with a launch failure instead of hanging the device)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) { if (++spins > 4000u) __trap(); }
+}
+// one lane polls for its warp (32 pollers per warp would take the issue slots of the warps that are being waited for)
+__device__ __forceinline__ void mbar_wait_warp(unsigned long long* bar, uint32_t parity) {
+  if ((threadIdx.x & 31u) == 0u) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
+constexpr size_t kPipeSmem = (size_t)kRingBytes + 2 * (size_t)kPOrder * 2;
+
+struct PipeArgs { const TabDesc* desc; const uint8_t* pool; const uint16_t* order; };
+
+template <bool HASVAR>
+__global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C, const PipeArgs T) {
+  extern __shared__ __align__(128) uint8_t ring[];                                      // kRingBytes: table records [block map][all-zero block][occupied blocks]
+  uint16_t* s_order0 = reinterpret_cast<uint16_t*>(ring + kRingBytes);                  // 2 x kPOrder
+  __shared__ PipeShared sh;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) { mbar_init(&sh.ready[b], 1); mbar_init(&sh.empty[b], 1); sh.slot[b].done = 0; sh.slot[b].unit = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kLoaderWarp) {
+    // =============================================================================== loader (one lane works; the warp keeps it company)
+    if (lane == 0) {
+      uint32_t prev_need = 0;                          // ring bytes of the previous spectrum's record (it lies at the other end of the ring)
+      long long t_wait = 0;
+      const long long t_begin = A.timing ? clock64() : 0;
+      for (uint32_t q = 0;; q++) {
+        const uint32_t b = q & 1, use = q >> 1;
+        PipeSlot& S = sh.slot[b];
+        const uint32_t s = atomicAdd(A.work, 1u);
+        const bool end = s >= A.n_spec;
+        // (what the spectrum needs is fetched before the slot is waited for)
+        md_precursor pr; pr.mass = 0; pr.lo = 0; pr.hi = 0; pr.charge = 0; pr.spectrum_id = 0;
+        uint64_t t0c = 0; uint32_t nt = 0, nd = 0;
+        TabDesc d{0ull, 0u, 0u};
+        if (!end) { pr = A.prec[s]; t0c = A.cand_off[s]; nt = (uint32_t)(A.cand_off[s + 1] - t0c); nd = A.dec_count ? A.dec_count[s] : 0u; d = T.desc[s]; }
+        const uint32_t ncand = nt + nd;
+        if (use > 0) { const long long t0 = A.timing ? clock64() : 0; mbar_wait(&sh.empty[b], (use - 1) & 1); if (A.timing) t_wait += clock64() - t0; }   // the slot's previous spectrum has left
+        if (A.timing) sh.state[b] = 1;
+        if (end) {
+          S.s = kPipeEnd; __threadfence_block(); mbar_arrive(&sh.ready[b]);
+          if (A.timing) { const long long all = clock64() - t_begin; atomicAdd(&A.timing[0], (unsigned long long)(all - t_wait)); atomicAdd(&A.timing[1], (unsigned long long)t_wait); }
+          break;
+        }
+        bool scored = d.nblk != 0u, left = false;
+        if (scored && ncand > 0xFFFFFFu) { *A.error = 1; scored = false; }
+        if (scored && d.nact == kTabLeft) { left = true; scored = false; }
+        const bool sorted = scored && ncand <= kPOrder;
+        uint32_t base = 0, need = 0;
+        if (scored) {
+          // ---- room for the record in the ring: records alternate between its two ends, so two spectra are resident whenever
+          //      their records fit side by side; if they do not, the previous spectrum has to leave first
+          need = tab_map_bytes(d.nblk) + (d.nact + 1u) * kBlk * 4u;
+          if (prev_need + need > kRingBytes && q > 0) {
+            const long long t0 = A.timing ? clock64() : 0;
+            if (A.timing) sh.blocked[b] = 1;
+            mbar_wait(&sh.empty[b ^ 1u], ((q - 1) >> 1) & 1);
+            if (A.timing) sh.blocked[b] = 0;
+            if (A.timing) { t_wait += clock64() - t0; atomicAdd(&A.timing[6], 1ull); }
+          }
+          base = b ? kRingBytes - need : 0u;
+        }
+        S.pr = pr; S.t0c = t0c; S.s = s; S.nt = nt; S.nd = nd; S.ncand = ncand; S.nunits = (ncand + 31) >> 5; S.nblk = d.nblk;
+        S.scored = scored ? 1u : 0u; S.sorted = sorted ? 1u : 0u; S.unit = 0; S.left = left ? 1u : 0u; S.base = base;
+        if (left) A.left_list[atomicAdd(A.left_n, 1u)] = s;
+        __threadfence_block();
+        if (scored) {
+          const uint32_t obytes = sorted ? ((ncand * 2u + 15u) & ~15u) : 0u;
+          mbar_arrive_expect_tx(&sh.ready[b], need + obytes);
+          const uint8_t* src = T.pool + d.off;
+          uint8_t* dst = ring + base;
+          for (uint32_t left_b = need; left_b;) {      // (pieces of at most 64 KB)
+            const uint32_t piece = min(left_b, 65536u);
+            bulk_g2s(dst, src, piece, &sh.ready[b]);
+            dst += piece; src += piece; left_b -= piece;
+          }
+          if (sorted) bulk_g2s(s_order0 + b * kPOrder, T.order + (size_t)s * kPOrder, obytes, &sh.ready[b]);
+          prev_need = need;
+          if (A.timing) sh.state[b] = 2;
+          if (A.timing) { const long long t0 = clock64(); mbar_wait(&sh.ready[b], use & 1); atomicAdd(&A.timing[7], (unsigned long long)(clock64() - t0)); atomicAdd(&A.timing[4], (unsigned long long)need); }   // (diagnosis: how long the copies take)
+        } else {
+          mbar_arrive(&sh.ready[b]);
+          prev_need = 0;
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================================================================= scorers
+  const LaneTab L{C.tq[lane], C.tr[lane], C.vq[lane], C.vr[lane]};   // per-letter (q, r) tables in registers: lane = residue code
+  uint32_t my_pairs = 0, my_bytes = 0;
+  const uint32_t K = C.top_k;
+  long long s_wait = 0, w_cause[4] = {0, 0, 0, 0};
+  const long long s_begin = A.timing ? clock64() : 0;
+  for (uint32_t q = 0;; q++) {
+    const uint32_t b = q & 1, use = q >> 1;
+    {
+      const long long t0 = A.timing ? clock64() : 0;
+      const uint32_t st0 = A.timing ? ((volatile uint32_t*)sh.state)[b] : 0u, bl0 = A.timing ? ((volatile uint32_t*)sh.blocked)[b] : 0u;
+      mbar_wait_warp(&sh.ready[b], use & 1);
+      if (A.timing) { const long long dt = clock64() - t0; s_wait += dt; if (bl0) w_cause[3] += dt; else w_cause[st0 < 3 ? st0 : 2] += dt; }
+    }
+    PipeSlot& S = sh.slot[b];
+    const uint32_t s = S.s;
+    if (s == kPipeEnd) break;
+    const md_precursor pr = S.pr;
+    const uint64_t t0c = S.t0c;
+    const uint32_t nt = S.nt, nd = S.nd, ncand = S.ncand, nunits = S.nunits;
+    const bool scored = S.scored != 0, sorted = S.sorted != 0, left_out = S.left != 0;
+    const uint16_t* order = s_order0 + b * kPOrder;
+    uint32_t nch = pr.charge > 1 ? pr.charge - 1 : 1;
+    if (nch > C.max_frag_charge) nch = C.max_frag_charge;
+    if (nch < 1) nch = 1;
+    TableView V;
+    V.map_s = smem_u32(ring + S.base); V.tab_s = V.map_s + tab_map_bytes(S.nblk); V.nblk = S.nblk; V.gmap = nullptr;
+    unsigned long long mine = 0ull;     // lane r: this warp's r-th best key of the spectrum
+    if (scored || (A.tscore && !left_out)) {
+      uint32_t u = 0;
+      if (lane == 0) u = atomicAdd(&S.unit, 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      while (u < nunits) {
+        // the warp's next unit is drawn one ahead, and what it will read first is requested into L2 while this unit is scored
+        uint32_t un = 0;
+        if (lane == 0) un = atomicAdd(&S.unit, 1u);
+        un = __shfl_sync(0xffffffffu, un, 0);
+        if (scored && un < nunits) {
+          const uint32_t i2 = un * 32 + lane;
+          if (i2 < ncand) {
+            const uint32_t v2 = sorted ? (uint32_t)order[i2] : i2;
+            if (v2 < nt) { prefetch_l2(A.cand_desc + t0c + v2); prefetch_l2(A.cand_w + t0c + v2); }
+            else { const uint64_t j = (uint64_t)s * C.n_per + (v2 - nt); prefetch_l2(A.dec_rows + j * MD_DECOY_HALF); prefetch_l2(A.dec_len + j); prefetch_l2(A.dec_w + j); }
+          }
+        }
+        const uint32_t i = u * 32 + lane;
+        CandRef cr;
+        cr.row = reinterpret_cast<const uint4*>(A.idx_rows); cr.row_hi = cr.row; cr.len = 0; cr.mask = 0; cr.modw = 0;
+        uint32_t v = 0;
+        const bool valid = i < ncand;
+        if (valid) {
+          v = sorted ? (uint32_t)order[i] : i;
+          if (scored) { cr = cand_ref<HASVAR>(A, s, v, nt, t0c, C.n_per); my_pairs++; my_bytes += 14 + cr.len; }
+        }
+        int64_t score = 0;
+        if (scored) {
+          const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
+          switch (nch) {
+            case 1: score = score_one<1, HASVAR, false>(cr, maxlen, V, C, L); break;
+            case 2: score = score_one<2, HASVAR, false>(cr, maxlen, V, C, L); break;
+            default: score = score_one<3, HASVAR, false>(cr, maxlen, V, C, L); break;
+          }
+        }
+        if (A.tscore && valid) { if (v < nt) A.tscore[t0c + v] = score; else A.dscore[(uint64_t)s * C.n_per + (v - nt)] = score; }
+        if (scored && K) {
+          // the unit's keys against the warp's running list: nothing to do unless the best new key beats the K-th best kept
+          unsigned long long nk = valid ? psm_key(score, v) : 0ull;
+          const unsigned long long kth = __shfl_sync(0xffffffffu, mine, (int)K - 1);
+          if (warp_max_u64(nk) > kth) {
+            unsigned long long carry = lane < K ? mine : 0ull, out = 0ull;
+            for (uint32_t r = 0; r < K; r++) {
+              const unsigned long long wm = warp_max_u64(nk > carry ? nk : carry);
+              if (wm != 0ull) { if (nk == wm) nk = 0ull; else if (carry == wm) carry = 0ull; }
+              if (lane == r) out = wm;
+            }
+            mine = out;
+          }
+        }
+        u = un;
+      }
+    }
+    // ---- leave the spectrum: the warp's list goes to shared memory; the last warp merges all lists and writes the PSM rows
+    if (lane < kFastTopK) sh.wtop[b][warp][lane] = lane < K ? mine : 0ull;
+    __threadfence_block();
+    __syncwarp();
+    uint32_t left = 0;
+    if (lane == 0) left = atomicAdd(&S.done, 1u);
+    left = __shfl_sync(0xffffffffu, left, 0);
+    if (left == kScoreWarps - 1) {
+      __threadfence_block();
+      unsigned long long best = 0ull;
+      if (scored && K) {
+        uint32_t idx = 0;
+        for (uint32_t r = 0; r < K; r++) {
+          const unsigned long long head = (lane < kScoreWarps && idx < K) ? sh.wtop[b][lane][idx] : 0ull;
+          const unsigned long long wm = warp_max_u64(head);
+          if (wm != 0ull && head == wm) idx++;
+          if (lane == r) best = wm;
+        }
+      }
+      if (lane < K && !left_out) write_psm_row(A, C, pr, s, lane, best, nt, nd, t0c);
+      __syncwarp();
+      if (lane == 0) { S.done = 0; if (A.timing) sh.state[b] = 0; __threadfence_block(); mbar_arrive(&sh.empty[b]); }
+    }
+  }
+  if (A.timing && tid == 0) { for (int k = 0; k < 4; k++) atomicAdd(&A.timing[8 + k], (unsigned long long)w_cause[k]); }
+  if (A.timing && tid == 0) { const long long all = clock64() - s_begin; atomicAdd(&A.timing[2], (unsigned long long)s_wait); atomicAdd(&A.timing[3], (unsigned long long)(all - s_wait)); }
+  unsigned long long wp = my_pairs, wb = my_bytes;
+  for (int o = 16; o; o >>= 1) { wp += __shfl_xor_sync(0xffffffffu, wp, o); wb += __shfl_xor_sync(0xffffffffu, wb, o); }
+  if (lane == 0 && wp) { atomicAdd(&A.stat64[0], wp); atomicAdd(&A.stat64[1], wb); }
+}
+
 __global__ void k_max_i32(const int32_t* __restrict__ v, uint32_t n, int32_t* __restrict__ out) {
   int32_t m = INT32_MIN;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
@@ -902,8 +1344,8 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   }
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
-  W.stat64.need(16);
-  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  W.stat64.need(32);
+  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
   const bool timing = getenv("MD_SCORE_TIMING") != nullptr;
   ScoreArgs A;
   A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
@@ -914,6 +1356,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   A.error = d_flag.p + 1; A.timing = timing ? W.stat64.p + 8 : nullptr;
   A.gmap = gstride ? W.gmap.p : nullptr; A.gbits = gstride ? W.gbits.p : nullptr; A.gmap_stride = gstride;
   A.parts = parts; A.part_top = nullptr; A.parts_done = nullptr;
+  A.n_work = n; A.remap = nullptr; A.left_list = nullptr; A.left_n = nullptr; A.n_work_dev = nullptr;
   if (parts > 1) {
     W.part_top.need((size_t)n * parts * kFastTopK); W.parts_done.need(n);
     MD_CUDA(cudaMemsetAsync(W.parts_done.p, 0, n * sizeof(uint32_t), ctx->stream));
@@ -927,16 +1370,75 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     MD_LAUNCH(ctx, kernel, grid, kScoreThreads, smem, A, C);
   };
   const bool single = parts == 1 && h_pre[3] <= (int)kCandChunk;     // every spectrum fits one chunk of candidates
-  if (has_var) { if (parts > 1) launch(k_score<true, 2>); else if (single) launch(k_score<true, 0>); else launch(k_score<true, 1>); }
-  else { if (parts > 1) launch(k_score<false, 2>); else if (single) launch(k_score<false, 0>); else launch(k_score<false, 1>); }
-  MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+  auto launch_classic = [&]() {
+    if (has_var) { if (parts > 1) launch(k_score<true, 2>); else if (single) launch(k_score<true, 0>); else launch(k_score<true, 1>); }
+    else { if (parts > 1) launch(k_score<false, 2>); else if (single) launch(k_score<false, 0>); else launch(k_score<false, 1>); }
+  };
+  // the pipelined kernel (builders + scorers) takes whole-spectrum work items with at most 8 PSM rows; MD_SCORE_CLASSIC=1 forces k_score
+  const bool pipe = parts == 1 && p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  if (pipe) {
+    W.left_list.need(n + 1);
+    A.left_list = W.left_list.p; A.left_n = work.p + 1;
+    // tables (they depend on the binned spectra only) and the length-sorted candidate order, each by the whole GPU at once
+    W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); W.cand_order.need((size_t)n * kPOrder + 16);
+    MD_CUDA(cudaMemsetAsync(W.stat64.p + 4, 0, sizeof(unsigned long long), ctx->stream));
+    MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p));
+    MD_LAUNCH(ctx, k_cand_order, n, 256, 0, A, n_per, W.cand_order.p);
+    MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p};
+    auto launch_pipe = [&](auto kernel) {
+      MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+      MD_LAUNCH(ctx, kernel, grid, kPipeThreads, kPipeSmem, A, C, PA);
+    };
+    if (has_var) launch_pipe(k_score_pipe<true>); else launch_pipe(k_score_pipe<false>);
+    // spectra the pipelined kernel could not hold (dense spectra: peaks / block map / table record beyond its staging) are on
+    // left_list now: k_score works the list off -- launched unconditionally, the count is read on the device (usually 0)
+    {
+      MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+      A.n_work = 0; A.n_work_dev = work.p + 1; A.remap = W.left_list.p; A.work = work.p + 2;
+      const uint32_t g2 = std::min<uint32_t>(n, 16u);
+      auto launch2 = [&](auto kernel) {
+        MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MD_LAUNCH(ctx, kernel, g2, kScoreThreads, smem, A, C);
+      };
+      if (has_var) { if (single) launch2(k_score<true, 0>); else launch2(k_score<true, 1>); }
+      else { if (single) launch2(k_score<false, 0>); else launch2(k_score<false, 1>); }
+    }
+    MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+    if (ctx->trace) {
+      unsigned long long top = 0;
+      uint32_t n_left = 0;
+      MD_CUDA(cudaMemcpy(&top, W.stat64.p + 4, sizeof(top), cudaMemcpyDeviceToHost));
+      MD_CUDA(cudaMemcpy(&n_left, work.p + 1, sizeof(n_left), cudaMemcpyDeviceToHost));
+      float ms_pipe = 0, ms_left = 0; cudaEventElapsedTime(&ms_pipe, ctx->ev[6], ctx->ev[5]); cudaEventElapsedTime(&ms_left, ctx->ev[5], ctx->ev[7]);
+      fprintf(stderr, "[md_trace]   score: k_score_pipe %.3f ms, k_score over the %u spectra left %.3f ms\n", ms_pipe, n_left, ms_left);
+      std::vector<TabDesc> hd(n);
+      MD_CUDA(cudaMemcpy(hd.data(), W.tab_desc.p, n * sizeof(TabDesc), cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> na; for (auto& d : hd) if (d.nblk && d.nact != kTabLeft) na.push_back(d.nact);
+      std::sort(na.begin(), na.end());
+      if (!na.empty()) fprintf(stderr, "[md_trace]   score tables: %.1f KB per spectrum; occupied blocks p10=%u p50=%u p90=%u p99=%u max=%u\n", (double)top / n / 1024.0,
+                               na[na.size() / 10], na[na.size() / 2], na[na.size() * 9 / 10], na[na.size() * 99 / 100], na.back());
+    }
+    MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+  } else {
+    launch_classic();
+    MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+  }
   unsigned long long h_stat[2] = {0, 0};
   int h_flag[2] = {0, 0};
   MD_CUDA(cudaMemcpyAsync(h_stat, W.stat64.p, sizeof(h_stat), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof(h_flag), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->acc_ms_kscore += ms; ctx->acc_pairs += h_stat[0]; ctx->acc_score_bytes += h_stat[1]; }
-  if (timing) {
+  if (timing && pipe) {
+    unsigned long long t[12];
+    MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[md_score_timing] scorer warp 0 waits by cause, cycles/CTA: slot still in use=%.0f, loader preparing=%.0f, copies in flight=%.0f, ring full=%.0f\n",
+            (double)t[8] / grid, (double)t[9] / grid, (double)t[10] / grid, (double)t[11] / grid);
+    fprintf(stderr, "[md_score_timing] pipelined, grid=%u: cycles/CTA loader work=%.0f wait=%.0f (ring full %.1f per CTA); scorer warp 0 wait=%.0f work=%.0f; bulk copies %.0f cycles for %.0f bytes per CTA\n", grid,
+            (double)t[0] / grid, (double)t[1] / grid, (double)t[6] / grid, (double)t[2] / grid, (double)t[3] / grid, (double)t[7] / grid, (double)t[4] / grid);
+  }
+  if (timing && !pipe) {
     unsigned long long t[8];
     MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));
     double tot = 0; for (int k = 0; k < 7; k++) tot += (double)t[k];

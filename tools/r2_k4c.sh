@@ -1,0 +1,6 @@
+set -x
+for cfg in c2 c1; do
+MD_TRACE=1 MD_SCORE_TIMING=1 timeout 600 python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu-baseline --no-c4 > gpurun_out/b_${cfg}_pipe.json 2> gpurun_out/b_${cfg}_pipe.err; echo "$cfg rc=$?"
+grep "md_score_timing\|md_trace\]   score" gpurun_out/b_${cfg}_pipe.err | tail -3
+python -c "import json; d=json.load(open('gpurun_out/b_${cfg}_pipe.json')); s=d['stage_ms_per_step']; print('$cfg pipe', 'step ms', round(d['ms_per_step'],2), 'score', round(s['score'],3), 'kscore', round(d['roofline']['launch_ms'],3), 'frac', round(d['roofline']['frac'],4), 'crc', d['psm_crc'])"
+done
