@@ -85,6 +85,7 @@ void identify_batch(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md
   MD_CUDA(cudaEventRecord(ctx->ev[0], s));
   precursors_dev(ctx, S, p, id_base);
   ctx->mark("precursors");
+  score_prepare_dev(ctx, S, n_peaks, p);        // (side stream)
   const uint64_t n_targets = index_candidates_dev(ctx, S.n);
   ctx->mark("candidates");
   MD_CUDA(cudaEventRecord(ctx->ev[1], s));
@@ -187,6 +188,9 @@ int md_create(const md_config* cfg, md_ctx** out) {
     c->n_sm = prop.multiProcessorCount;
     c->trace = getenv("MD_TRACE") != nullptr;
     MD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    MD_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    MD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    MD_CUDA(cudaEventCreateWithFlags(&c->ev_prep, cudaEventDisableTiming));
     for (auto& ev : c->ev) MD_CUDA(cudaEventCreate(&ev));
     *out = c;
     return MD_OK;
@@ -200,6 +204,9 @@ void md_destroy(md_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_prep) cudaEventDestroy(ctx->ev_prep);
   comm_release(ctx);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStream_t s = ctx->stream;

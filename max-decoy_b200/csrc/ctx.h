@@ -66,6 +66,7 @@ struct IdentifyWorkspace {
   DevBuf<int64_t> tscore; DevBuf<int64_t> dscore;
   DevBuf<uint32_t> left_list;        // spectra the pipelined score kernel left to k_score
   DevBuf<uint8_t> tab_pool, tab_desc; DevBuf<uint16_t> cand_order;   // k_build_tables / k_cand_order -> k_score_pipe
+  DevBuf<uint32_t> sched_key, sched_val, sched;                      // the order in which k_score_pipe takes the spectra
   DevBuf<unsigned long long> part_top; DevBuf<uint32_t> parts_done;   // spectra split into parts (open searches): per-part top-k keys, arrival counters
   DevBuf<uint8_t> cub_tmp;
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
@@ -90,6 +91,8 @@ struct md_ctx {
   int device = 0;
   int n_sm = MD_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // side stream: work that depends on the spectra alone runs beside the decoy generation
+  cudaEvent_t ev_fork = nullptr, ev_prep = nullptr;
   cudaEvent_t ev[8] = {};
   // modifications
   bool mods_set = false;
@@ -152,6 +155,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
 void decoys_export(md_ctx* ctx, uint32_t n, uint32_t n_per, md_decoy_table* out);
 // bins the n spectra (device SoA), scores targets+decoys, writes PSM rows
 struct SpectraDev { uint32_t n; const double* pmz; const uint8_t* charge; const uint32_t* sid; const uint64_t* peak_off; const double* peak_mz; const float* peak_int; };
+void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p);
 void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev, bool want_all);
 void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p, uint32_t id_base);
 

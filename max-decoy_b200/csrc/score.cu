@@ -258,7 +258,9 @@ struct CandRef { const uint4* row; const uint4* row_hi; uint32_t len; uint64_t m
 // unsigned min.  The last residue is never a prefix: at position len-1 kStop is added to QB, which throws every later
 // b and y bin of every charge out of the table -- no per-residue length predicate.  The loop runs in 4-residue words up
 // to the longest candidate of the warp.
-template <int NCH, bool HASVAR, bool MAPG>
+// STREAM (the pipelined kernel): the first two row chunks are requested together and a residue's block-map loads all go out
+// before its table loads; k_score keeps the plain order (the extra live values would spill at its register budget).
+template <int NCH, bool HASVAR, bool MAPG, bool STREAM = false>
 __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen, const TableView& V, const ScoreConst& C, const LaneTab& L) {
   const uint32_t w = C.w;
   const uint32_t K2 = C.qp - 1u, K3 = C.q2p - 1u;
@@ -281,11 +283,10 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   if (nsplit == 0) QB += kStop;
   int64_t acc = 0;
   // (the first two 16-residue chunks are requested together: one round trip to L2 / HBM instead of two for the usual 17..32-residue candidate)
-  const uint4 v0 = __ldg(cr.row);
-  uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
-  if (nword > 4) v1 = __ldg(cr.row + 1);
+  uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+  if (STREAM) { v0 = __ldg(cr.row); if (nword > 4) v1 = __ldg(cr.row + 1); }
   for (uint32_t c = 0; c * 4 < nword; c++) {
-    const uint4 v = c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)));
+    const uint4 v = STREAM ? (c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)))) : __ldg(c < 2 ? cr.row + c : cr.row_hi + (c - 2));
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -302,6 +303,18 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         QB += q; R1 += r;
         if (R1 >= w) { R1 -= w; QB++; }
         // |T| <= 151 * 50 * 2^16 < 2^29: up to four entries add up in 32 bits, then one IMAD.WIDE into the 64-bit score
+        if (!STREAM) {
+          int32_t s4 = gather<MAPG>(QB, V) + gather<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);                // fragment charge 1
+          if (NCH >= 2) {
+            s4 += gather<MAPG>(((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
+            s4 += gather<MAPG>(((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
+          }
+          acc_wide(acc, s4);
+          if (NCH >= 3) {
+            acc_wide(acc, gather<MAPG>(div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V) +
+                              gather<MAPG>(div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V));
+          }
+        } else {
         // all block-map loads of the residue first, then all table loads: the fragments are independent of one another
         const uint32_t ib1 = gather_index<MAPG>(QB, V), iy1 = gather_index<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);     // fragment charge 1
         uint32_t ib2 = 0, iy2 = 0, ib3 = 0, iy3 = 0;
@@ -317,6 +330,7 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         if (NCH >= 2) s4 += gather_entry(ib2, V) + gather_entry(iy2, V);
         acc_wide(acc, s4);
         if (NCH >= 3) acc_wide(acc, gather_entry(ib3, V) + gather_entry(iy3, V));
+        }
         if (pos + 1 == nsplit) QB += kStop;   // the next residue is the last one
       }
     }
@@ -867,7 +881,7 @@ constexpr uint32_t kPipeThreads = MD_PIPE_THREADS, kPipeWarps = kPipeThreads / 3
 constexpr uint32_t kScoreWarps = kPipeWarps - 1, kLoaderWarp = kPipeWarps - 1;
 constexpr uint32_t kPMapCap = 4096;        // block-map entries per slot (262k bins)
 constexpr uint32_t kPOrder = 2048;         // candidates that are sorted by length (spectra with more are walked in their natural order)
-constexpr uint32_t kPPeaks = 512;          // binned peaks k_build_tables stages
+constexpr uint32_t kPPeaks = 1024;         // binned peaks k_build_tables stages
 constexpr uint32_t kPoolBlocks = 856;      // most 64-bin blocks (the all-zero block included) of a table the pipelined kernel takes
 constexpr uint32_t kRingBytes = 214 * 1024; // shared-memory ring that holds the table records (block map + table) of two spectra
 constexpr uint32_t kPipeEnd = 0xFFFFFFFFu, kTabLeft = 0xFFFFFFFFu;
@@ -966,6 +980,23 @@ __global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __
   }
 }
 
+// The order in which the persistent CTAs take the spectra: pairs of (large record, small record) -- the p-th largest with the
+// p-th smallest -- so that two consecutive spectra of a CTA nearly always fit the ring side by side and every pair is about
+// the same amount of work.  k_table_keys: record size per spectrum (the sort key); k_pair_schedule: sorted order -> pairs.
+__global__ void k_table_keys(const TabDesc* __restrict__ desc, uint32_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const TabDesc d = desc[s];
+  key[s] = (d.nblk != 0u && d.nact != kTabLeft) ? tab_map_bytes(d.nblk) + (d.nact + 1u) * kBlk * 4u : 0u;
+  val[s] = s;
+}
+__global__ void k_pair_schedule(const uint32_t* __restrict__ asc, uint32_t n, uint32_t* __restrict__ sched) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;   // pair
+  if (2 * p >= n) return;
+  sched[2 * p] = asc[n - 1 - p];
+  if (2 * p + 1 < n) sched[2 * p + 1] = asc[p];
+}
+
 // candidates of every spectrum with at most kPOrder of them, counting-sorted by length (longest first) -> order[s * kPOrder + i]
 __global__ void __launch_bounds__(256) k_cand_order(const ScoreArgs A, uint32_t n_per, uint16_t* __restrict__ order) {
   __shared__ uint32_t hist[64];
@@ -1055,7 +1086,7 @@ __device__ __forceinline__ void mbar_wait_warp(unsigned long long* bar, uint32_t
 
 constexpr size_t kPipeSmem = (size_t)kRingBytes + 2 * (size_t)kPOrder * 2;
 
-struct PipeArgs { const TabDesc* desc; const uint8_t* pool; const uint16_t* order; };
+struct PipeArgs { const TabDesc* desc; const uint8_t* pool; const uint16_t* order; const uint32_t* sched; };
 
 template <bool HASVAR>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C, const PipeArgs T) {
@@ -1075,11 +1106,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
       uint32_t prev_need = 0;                          // ring bytes of the previous spectrum's record (it lies at the other end of the ring)
       long long t_wait = 0;
       const long long t_begin = A.timing ? clock64() : 0;
+      uint32_t pend = kPipeEnd;                        // second spectrum of the pair that was drawn last
       for (uint32_t q = 0;; q++) {
         const uint32_t b = q & 1, use = q >> 1;
         PipeSlot& S = sh.slot[b];
-        const uint32_t s = atomicAdd(A.work, 1u);
-        const bool end = s >= A.n_spec;
+        // work items are PAIRS of the schedule (large record, then small record)
+        uint32_t s = pend;
+        pend = kPipeEnd;
+        if (s == kPipeEnd) {
+          const uint32_t t = atomicAdd(A.work, 1u);
+          if (2ull * t < A.n_spec) { s = T.sched[2 * t]; if (2 * t + 1 < A.n_spec) pend = T.sched[2 * t + 1]; }
+        }
+        const bool end = s == kPipeEnd;
         // (what the spectrum needs is fetched before the slot is waited for)
         md_precursor pr; pr.mass = 0; pr.lo = 0; pr.hi = 0; pr.charge = 0; pr.spectrum_id = 0;
         uint64_t t0c = 0; uint32_t nt = 0, nd = 0;
@@ -1196,9 +1234,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
         if (scored) {
           const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
           switch (nch) {
-            case 1: score = score_one<1, HASVAR, false>(cr, maxlen, V, C, L); break;
-            case 2: score = score_one<2, HASVAR, false>(cr, maxlen, V, C, L); break;
-            default: score = score_one<3, HASVAR, false>(cr, maxlen, V, C, L); break;
+            case 1: score = score_one<1, HASVAR, false, true>(cr, maxlen, V, C, L); break;
+            case 2: score = score_one<2, HASVAR, false, true>(cr, maxlen, V, C, L); break;
+            default: score = score_one<3, HASVAR, false, true>(cr, maxlen, V, C, L); break;
           }
         }
         if (A.tscore && valid) { if (v < nt) A.tscore[t0c + v] = score; else A.dscore[(uint64_t)s * C.n_per + (v - nt)] = score; }
@@ -1281,23 +1319,50 @@ void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p,
   MD_LAUNCH(ctx, k_precursors, blocks(S.n), 256, 0, S.pmz, S.charge, S.sid, S.n, p.lower_ppm, p.upper_ppm, p.abs_lower_uda, p.abs_upper_uda, id_base, ctx->ws.prec.p);
 }
 
-void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev, bool want_all) {
+// What the scoring needs from the spectra alone -- binned peaks (K4a) and, for the pipelined kernel, the table records -- runs on
+// the ctx's side stream from the moment the precursors are known, i.e. beside the candidate lookup and the decoy generation
+// (which keep the SMs' issue slots busy but leave HBM idle); score_run_dev waits for it.
+void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p) {
   IdentifyWorkspace& W = ctx->ws;
   const uint32_t n = S.n;
   if (!n) return;
   const int64_t w = (int64_t)llround(p.fragment_tolerance * 1000000.0);
+  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
+  DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
+  W.stat64.need(32);
+  const bool tables = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  if (tables) { W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); }
+  cudaStream_t main = ctx->stream, side = ctx->stream2;
+  MD_CUDA(cudaEventRecord(ctx->ev_fork, main));
+  MD_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+  ctx->stream = side;     // (MD_LAUNCH launches on ctx->stream)
+  try {
+    MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 4 * sizeof(int), side));
+    MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), side));
+    MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
+              W.pk_count.p, W.pk_hbin.p, d_flag.p);
+    // the largest table of the batch decides whether the block maps fit shared memory
+    MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
+    if (tables) {
+      MD_CUDA(cudaMemsetAsync(W.stat64.p + 4, 0, sizeof(unsigned long long), side));
+      MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p));
+    }
+    MD_CUDA(cudaEventRecord(ctx->ev_prep, side));
+  } catch (...) { ctx->stream = main; throw; }
+  ctx->stream = main;
+}
+
+void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_search_params& p, uint32_t n_per, md_psm* psm_dev, bool want_all) {
+  IdentifyWorkspace& W = ctx->ws;
+  const uint32_t n = S.n;
+  if (!n) return;
+  (void)n_peaks;
+  const int64_t w = (int64_t)llround(p.fragment_tolerance * 1000000.0);
   const uint32_t mfc = p.max_fragment_charge ? p.max_fragment_charge : 3;
   MD_REQUIRE(mfc <= 3, MD_ERR_UNSUPPORTED, "max_fragment_charge > 3 (the reference fixes it to 3: comet_parameter.rs:55)");
   MD_REQUIRE(p.top_k <= kMaxTopK, MD_ERR_UNSUPPORTED, "top_k > 128");
-  // ---- K4a
-  W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
-  DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
-  MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 4 * sizeof(int), ctx->stream));
-  MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), ctx->stream));
-  MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
-            W.pk_count.p, W.pk_hbin.p, d_flag.p);
-  // the largest table of the batch decides whether the block maps fit shared memory
-  MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
+  DevBuf<int>& d_flag = W.t_unsorted;
+  MD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_prep, 0));      // K4a and the table records (score_prepare_dev)
   MD_LAUNCH(ctx, k_max_candidates, std::min<uint32_t>(blocks(n), 64), 256, 0, W.cand_off.p, n_per ? W.dec_count.p : nullptr, n, d_flag.p + 3);
   int h_pre[4] = {0, 0, 0, 0};
   MD_CUDA(cudaMemcpyAsync(h_pre, d_flag.p, sizeof(h_pre), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1344,8 +1409,8 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   }
   DevBuf<uint32_t>& work = W.counters; work.need(4);
   MD_CUDA(cudaMemsetAsync(work.p, 0, 4 * sizeof(uint32_t), ctx->stream));
-  W.stat64.need(32);
-  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
+  MD_CUDA(cudaMemsetAsync(W.stat64.p, 0, 4 * sizeof(unsigned long long), ctx->stream));                    // [0..1] statistics; [4] = the table pool's fill (score_prepare_dev)
+  MD_CUDA(cudaMemsetAsync(W.stat64.p + 8, 0, 24 * sizeof(unsigned long long), ctx->stream));
   const bool timing = getenv("MD_SCORE_TIMING") != nullptr;
   ScoreArgs A;
   A.prec = W.prec.p; A.n_spec = n; A.peak_off = S.peak_off; A.pk_bin = W.pk_bin.p; A.pk_yq = W.pk_yq.p; A.pk_count = W.pk_count.p; A.pk_hbin = W.pk_hbin.p;
@@ -1379,13 +1444,15 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   if (pipe) {
     W.left_list.need(n + 1);
     A.left_list = W.left_list.p; A.left_n = work.p + 1;
-    // tables (they depend on the binned spectra only) and the length-sorted candidate order, each by the whole GPU at once
-    W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); W.cand_order.need((size_t)n * kPOrder + 16);
-    MD_CUDA(cudaMemsetAsync(W.stat64.p + 4, 0, sizeof(unsigned long long), ctx->stream));
-    MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p));
+    // the table records are there (score_prepare_dev); the length-sorted candidate order and the schedule, each by the whole GPU at once
+    W.cand_order.need((size_t)n * kPOrder + 16);
     MD_LAUNCH(ctx, k_cand_order, n, 256, 0, A, n_per, W.cand_order.p);
+    W.sched_key.need(2 * (size_t)n + 2); W.sched_val.need(2 * (size_t)n + 2); W.sched.need(n + 2);
+    MD_LAUNCH(ctx, k_table_keys, blocks(n), 256, 0, reinterpret_cast<const TabDesc*>(W.tab_desc.p), n, W.sched_key.p, W.sched_val.p);
+    cubx_sort_pairs<uint32_t, uint32_t>(ctx, W.sched_key.p, W.sched_key.p + n, W.sched_val.p, W.sched_val.p + n, n);
+    MD_LAUNCH(ctx, k_pair_schedule, blocks((n + 1) / 2), 256, 0, W.sched_val.p + n, n, W.sched.p);
     MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
-    const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p};
+    const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p, W.sched.p};
     auto launch_pipe = [&](auto kernel) {
       MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
       MD_LAUNCH(ctx, kernel, grid, kPipeThreads, kPipeSmem, A, C, PA);
