@@ -258,9 +258,7 @@ struct CandRef { const uint4* row; const uint4* row_hi; uint32_t len; uint64_t m
 // unsigned min.  The last residue is never a prefix: at position len-1 kStop is added to QB, which throws every later
 // b and y bin of every charge out of the table -- no per-residue length predicate.  The loop runs in 4-residue words up
 // to the longest candidate of the warp.
-// STREAM (the pipelined kernel): the first two row chunks are requested together and a residue's block-map loads all go out
-// before its table loads; k_score keeps the plain order (the extra live values would spill at its register budget).
-template <int NCH, bool HASVAR, bool MAPG, bool STREAM = false>
+template <int NCH, bool HASVAR, bool MAPG>
 __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen, const TableView& V, const ScoreConst& C, const LaneTab& L) {
   const uint32_t w = C.w;
   const uint32_t K2 = C.qp - 1u, K3 = C.q2p - 1u;
@@ -283,10 +281,11 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   if (nsplit == 0) QB += kStop;
   int64_t acc = 0;
   // (the first two 16-residue chunks are requested together: one round trip to L2 / HBM instead of two for the usual 17..32-residue candidate)
-  uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-  if (STREAM) { v0 = __ldg(cr.row); if (nword > 4) v1 = __ldg(cr.row + 1); }
+  const uint4 v0 = __ldg(cr.row);
+  uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+  if (nword > 4) v1 = __ldg(cr.row + 1);
   for (uint32_t c = 0; c * 4 < nword; c++) {
-    const uint4 v = STREAM ? (c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)))) : __ldg(c < 2 ? cr.row + c : cr.row_hi + (c - 2));
+    const uint4 v = c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)));
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -303,18 +302,6 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         QB += q; R1 += r;
         if (R1 >= w) { R1 -= w; QB++; }
         // |T| <= 151 * 50 * 2^16 < 2^29: up to four entries add up in 32 bits, then one IMAD.WIDE into the 64-bit score
-        if (!STREAM) {
-          int32_t s4 = gather<MAPG>(QB, V) + gather<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);                // fragment charge 1
-          if (NCH >= 2) {
-            s4 += gather<MAPG>(((QB + K2 + (R1 + C.rp >= w ? 1u : 0u)) >> 1) + 1u, V);
-            s4 += gather<MAPG>(((Y2 - QB - (Rt2 < R1 ? 1u : 0u)) >> 1) + 1u, V);
-          }
-          acc_wide(acc, s4);
-          if (NCH >= 3) {
-            acc_wide(acc, gather<MAPG>(div3(QB + K3 + (R1 + C.r2p >= w ? 1u : 0u)) + 1u, V) +
-                              gather<MAPG>(div3(Y3 - QB - (Rt3 < R1 ? 1u : 0u)) + 1u, V));
-          }
-        } else {
         // all block-map loads of the residue first, then all table loads: the fragments are independent of one another
         const uint32_t ib1 = gather_index<MAPG>(QB, V), iy1 = gather_index<MAPG>(Y1 - QB - (Rt1 < R1 ? 1u : 0u), V);     // fragment charge 1
         uint32_t ib2 = 0, iy2 = 0, ib3 = 0, iy3 = 0;
@@ -330,7 +317,6 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
         if (NCH >= 2) s4 += gather_entry(ib2, V) + gather_entry(iy2, V);
         acc_wide(acc, s4);
         if (NCH >= 3) acc_wide(acc, gather_entry(ib3, V) + gather_entry(iy3, V));
-        }
         if (pos + 1 == nsplit) QB += kStop;   // the next residue is the last one
       }
     }
@@ -1234,9 +1220,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
         if (scored) {
           const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
           switch (nch) {
-            case 1: score = score_one<1, HASVAR, false, true>(cr, maxlen, V, C, L); break;
-            case 2: score = score_one<2, HASVAR, false, true>(cr, maxlen, V, C, L); break;
-            default: score = score_one<3, HASVAR, false, true>(cr, maxlen, V, C, L); break;
+            case 1: score = score_one<1, HASVAR, false>(cr, maxlen, V, C, L); break;
+            case 2: score = score_one<2, HASVAR, false>(cr, maxlen, V, C, L); break;
+            default: score = score_one<3, HASVAR, false>(cr, maxlen, V, C, L); break;
           }
         }
         if (A.tscore && valid) { if (v < nt) A.tscore[t0c + v] = score; else A.dscore[(uint64_t)s * C.n_per + (v - nt)] = score; }
@@ -1276,9 +1262,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
           if (lane == r) best = wm;
         }
       }
+      // the slot is free as soon as the lists are merged: the rows (an FP64 division each, thousands of cycles on this part)
+      // are written from registers while the loader already brings the slot's next spectrum
+#ifdef MD_PIPE_LATE_RELEASE
       if (lane < K && !left_out) write_psm_row(A, C, pr, s, lane, best, nt, nd, t0c);
       __syncwarp();
       if (lane == 0) { S.done = 0; if (A.timing) sh.state[b] = 0; __threadfence_block(); mbar_arrive(&sh.empty[b]); }
+#else
+      __syncwarp();
+      if (lane == 0) { S.done = 0; if (A.timing) sh.state[b] = 0; __threadfence_block(); mbar_arrive(&sh.empty[b]); }
+      if (lane < K && !left_out) write_psm_row(A, C, pr, s, lane, best, nt, nd, t0c);
+#endif
     }
   }
   if (A.timing && tid == 0) { for (int k = 0; k < 4; k++) atomicAdd(&A.timing[8 + k], (unsigned long long)w_cause[k]); }

@@ -141,12 +141,9 @@ def cmd_substitution(args):
 def cmd_spectrum_splitup(args):
     """`spectrum-splitup` (src/main.rs:183-206): one mzML per MS2 spectrum (kept for users who still run Comet)."""
     from maxdecoy import mzml
-    spectra, ids = mzml.read_ms_two_spectra(args.mz_ml_file)
-    os.makedirs(args.destination_folder, exist_ok=True)
-    for i, sid in enumerate(ids):
-        name = (sid[1] or sid[0]).replace("/", "_").replace(" ", "_") + args.file_suffix + ".mzML"
-        mzml.write_mzml(spectra.subset([i]), os.path.join(args.destination_folder, name))
-    print("%d MS2 spectra -> %s" % (len(ids), args.destination_folder))
+    with open(args.mz_ml_file) as fh:
+        names = mzml.spectrum_splitup(fh.read(), args.destination_folder, args.file_suffix)
+    print("found and write %d MS2-spectra -> %s" % (len(names), args.destination_folder))
 
 
 def main(argv=None):

@@ -106,15 +106,18 @@ def read_ms_two_spectra(path_or_text):
                    cat(mzs, np.float64), cat(ints, np.float32)), ids
 
 
-def write_mzml(spectra, path=None, compress=True):
-    """Minimal indexed-less mzML writer for tests and for feeding the generated candidate sets to Comet."""
+def write_mzml(spectra, path=None, compress=True, indexed=False):
+    """Minimal mzML writer for tests and for feeding the generated candidate sets to Comet.  `indexed` wraps the document in
+    an <indexedmzML> root (without an index) -- the nesting `spectrum-splitup` expects of its input."""
     def enc(a, dtype):
         raw = np.asarray(a, dtype=dtype).tobytes()
         if compress:
             raw = zlib.compress(raw)
         return base64.b64encode(raw).decode()
-    out = ['<?xml version="1.0" encoding="utf-8"?>', '<mzML xmlns="http://psi.hupo.org/ms/mzml" version="1.1.0">',
-           '<run id="synthetic"><spectrumList count="%d">' % len(spectra)]
+    out = ['<?xml version="1.0" encoding="utf-8"?>']
+    if indexed:
+        out.append('<indexedmzML xmlns="http://psi.hupo.org/ms/mzml">')
+    out += ['<mzML xmlns="http://psi.hupo.org/ms/mzml" version="1.1.0">', '<run id="synthetic"><spectrumList count="%d">' % len(spectra)]
     for s in range(len(spectra)):
         a, b = int(spectra.peak_off[s]), int(spectra.peak_off[s + 1])
         out.append('<spectrum index="%d" id="controllerType=0 controllerNumber=1 scan=%d" defaultArrayLength="%d">' % (s, s + 1, b - a))
@@ -132,8 +135,174 @@ def write_mzml(spectra, path=None, compress=True):
             out.append('<cvParam cvRef="MS" accession="%s" name="%s"/><binary>%s</binary></binaryDataArray>' % (acc, name, enc(data, dt)))
         out.append('</binaryDataArrayList></spectrum>')
     out.append('</spectrumList></run></mzML>')
+    if indexed:
+        out.append('</indexedmzML>')
     text = "\n".join(out) + "\n"
     if path:
         with open(path, "w") as fh:
             fh.write(text)
     return text
+
+
+# ------------------------------------------------------------------------------------------------
+# spectrum-splitup in the reference's own output format
+# ------------------------------------------------------------------------------------------------
+_INDENT = "    "                       # utility/mz_ml/mod.rs:6
+_TOKEN = re.compile(r"<\?.*?\?>|<!--.*?-->|<!\[CDATA\[.*?\]\]>|<![^>]*>|</[^>]*>|<[^>]*?/>|<[^>]*>|[^<]+", re.S)
+# url::percent_encoding::DEFAULT_ENCODE_SET: C0 controls, space, " # < > ` ? { } and everything above '~'
+_KEEP = set(chr(c) for c in range(0x21, 0x7F)) - set('"#<>`?{}')
+
+
+def _events(text):
+    """(kind, raw) for every XML event quick-xml would report: 'decl', 'start', 'empty', 'end', 'text', 'other'."""
+    for m in _TOKEN.finditer(text):
+        t = m.group(0)
+        if t.startswith("<?"):
+            yield "decl", t
+        elif t.startswith("<!"):
+            yield "other", t
+        elif t.startswith("</"):
+            yield "end", t
+        elif t.endswith("/>"):
+            yield "empty", t
+        elif t.startswith("<"):
+            yield "start", t
+        else:
+            yield "text", t
+
+
+def _name(tag):
+    return re.match(r"</?\s*([^\s/>]+)", tag).group(1)
+
+
+def _attr(tag, key):
+    m = re.search(r'\b%s\s*=\s*"([^"]*)"' % re.escape(key), tag) or re.search(r"\b%s\s*=\s*'([^']*)'" % re.escape(key), tag)
+    return m.group(1) if m else None
+
+
+def content_before_spectrum_list(text):
+    """MzMlReader::get_content_before_spectrum_list (mz_ml_reader.rs:102-143): every declaration, start, empty and end tag
+    in front of <spectrumList>, one per line, indented by nesting level; text nodes are dropped."""
+    out, level = [], 0
+    for kind, raw in _events(text):
+        if kind == "start":
+            if _name(raw) == "spectrumList":
+                break
+            out.append(_INDENT * level + raw + "\n")
+            level += 1
+        elif kind in ("empty", "decl"):
+            out.append(_INDENT * level + raw + "\n")
+        elif kind == "end":
+            level -= 1
+            out.append(_INDENT * level + raw + "\n")
+    return "".join(out)
+
+
+def ms_two_spectrum_xml(text):
+    """MzMlReader::get_ms_two_spectra (mz_ml_reader.rs:24-100): [(xml, indent_level)] of the spectra whose first `ms level`
+    cvParam has value "2"; the xml is re-indented tag by tag, <binary> payloads stay on the line of their tag."""
+    out, level, inside, in_binary, buf = [], 0, False, False, []
+    for kind, raw in _events(text):
+        if kind == "start":
+            n = _name(raw)
+            if n == "spectrum":
+                inside = True
+                buf.append(_INDENT * level + raw + "\n")
+            elif n == "binary":
+                buf.append(_INDENT * level + raw)
+                in_binary = True
+            elif inside:
+                buf.append(_INDENT * level + raw + "\n")
+            level += 1
+        elif kind == "empty":
+            if inside:
+                buf.append(_INDENT * level + raw + "\n")
+        elif kind == "text":
+            if inside and in_binary:
+                buf.append(raw)
+        elif kind == "end":
+            level -= 1
+            n = _name(raw)
+            if n == "spectrum" and inside:
+                buf.append(_INDENT * level + raw)
+                xml = "".join(buf)
+                ms2 = None
+                for k2, r2 in _events(xml):                       # is_ms_two_spectrum: the first cvParam named "ms level" decides
+                    if k2 == "empty" and _name(r2) == "cvParam" and _attr(r2, "name") == "ms level" and _attr(r2, "value") is not None:
+                        ms2 = _attr(r2, "value") == "2"
+                        break
+                if ms2:
+                    out.append((xml, level))
+                buf, inside = [], False
+            elif n == "binary":
+                in_binary = False
+                buf.append(raw + "\n")
+            elif inside:
+                buf.append(_INDENT * level + raw + "\n")
+    return out
+
+
+def split_filename(spectrum_id, file_suffix=""):
+    """Spectrum::get_filename + the suffix / extension handling of to_mz_ml (spectrum.rs:160-167,215-222): the scan id (or the
+    whole id) percent-encoded, `_suffix`, and Path::set_extension("mzML") -- which REPLACES whatever follows the last dot."""
+    name = scan_id_of_reference(spectrum_id) or spectrum_id
+    enc = "".join(c if c in _KEEP else "".join("%%%02X" % b for b in c.encode()) for c in name)
+    if file_suffix:
+        enc += "_" + file_suffix
+    stem = enc
+    if "." in enc[1:]:
+        stem = enc[:enc.rindex(".")]
+    return stem + ".mzML"
+
+
+def scan_id_of_reference(spectrum_id):
+    """Spectrum::exctract_scan_id_from_spectrum_id (spectrum.rs:243-255): the match of `scan=.*\\b` (greedy, to the last word
+    boundary), then what follows its last '='."""
+    best = None
+    i = spectrum_id.find("scan=")
+    if i < 0:
+        return ""
+    tail = spectrum_id[i:]
+    for end in range(len(tail), 4, -1):          # longest prefix of the tail that ends at a word boundary
+        a = tail[end - 1]
+        b = tail[end] if end < len(tail) else ""
+        wa, wb = a.isalnum() or a == "_", (b.isalnum() or b == "_") if b else False
+        if wa != wb:
+            best = tail[:end]
+            break
+    return best.split("=")[-1] if best is not None else ""
+
+
+def to_mz_ml(xml, indent_level, spectrum_id, before):
+    """Spectrum::to_mz_ml (spectrum.rs:170-231): an indexedmzML file with this one spectrum -- byte offsets of the spectrum and
+    of the index list, SHA-1 over everything up to and including the opening <fileChecksum> tag."""
+    import hashlib
+    index_list = _INDENT + '<indexList count="1">\n' + _INDENT * 2 + '<index name="spectrum">\n'
+    content = before + _INDENT * (indent_level - 1) + '<spectrumList count="1" defaultDataProcessingRef="pwiz_Reader_conversion">\n'
+    offset = len(content.encode()) + xml.index("<")
+    index_list += _INDENT * 3 + '<offset idRef="%s">%d</offset>\n' % (spectrum_id, offset)
+    content += xml + "\n" + _INDENT * (indent_level - 1) + "</spectrumList>\n" + _INDENT * 2 + "</run>\n" + _INDENT + "</mzML>\n"
+    index_list += _INDENT * 2 + "</index>\n" + _INDENT + "</indexList>\n"
+    offset = len(content.encode()) + index_list.index("<")
+    content += index_list + _INDENT + "<indexListOffset>%d</indexListOffset>\n" % offset + _INDENT + "<fileChecksum>"
+    digest = hashlib.sha1(content.encode()).hexdigest()
+    return content + digest + "</fileChecksum>\n</indexedmzML>"
+
+
+def spectrum_splitup(text, destination_folder, file_suffix=""):
+    """`spectrum-splitup` (src/main.rs:183-206): one indexedmzML file per MS2 spectrum, named and laid out as the reference
+    does it.  Returns the file names."""
+    import os
+    before = content_before_spectrum_list(text)
+    os.makedirs(destination_folder, exist_ok=True)
+    names = []
+    for xml, level in ms_two_spectrum_xml(text):
+        first = next(r for k, r in _events(xml) if k == "start")
+        sid = _attr(first, "id")
+        if sid is None:
+            raise ValueError("spectrum without id")              # the reference panics (spectrum.rs:84-90)
+        name = split_filename(sid, file_suffix)
+        with open(os.path.join(destination_folder, name), "w", newline="") as fh:
+            fh.write(to_mz_ml(xml, level, sid, before))
+        names.append(name)
+    return names

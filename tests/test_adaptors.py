@@ -114,6 +114,66 @@ def test_mzml_missing_precursor_is_an_error():
         mzml.read_ms_two_spectra(bad)
 
 
+_SPLIT_SRC = """<?xml version="1.0" encoding="utf-8"?>
+<indexedmzML xmlns="http://psi.hupo.org/ms/mzml">
+  <mzML id="x" version="1.1.0">
+    <cvList count="1">
+      <cv id="MS" fullName="PSI MS"/>
+    </cvList>
+    <run id="r1">
+      <spectrumList count="3" defaultDataProcessingRef="pwiz_Reader_conversion">
+        <spectrum index="0" id="controllerType=0 controllerNumber=1 scan=7" defaultArrayLength="2">
+          <cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="2"/>
+          <precursorList count="1"><precursor><selectedIonList count="1"><selectedIon>
+            <cvParam cvRef="MS" name="selected ion m/z" value="500.25"/>
+            <cvParam cvRef="MS" name="charge state" value="2"/>
+          </selectedIon></selectedIonList></precursor></precursorList>
+          <binaryDataArrayList count="1"><binaryDataArray encodedLength="4"><binary>AAAA</binary></binaryDataArray></binaryDataArrayList>
+        </spectrum>
+        <spectrum index="1" id="scan=8" defaultArrayLength="0">
+          <cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="1"/>
+        </spectrum>
+        <spectrum index="2" id="sample 9.raw" defaultArrayLength="0">
+          <cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="2"/>
+          <precursorList count="1"><precursor><selectedIonList count="1"><selectedIon>
+            <cvParam cvRef="MS" name="selected ion m/z" value="600.5"/><cvParam cvRef="MS" name="charge state" value="3"/>
+          </selectedIon></selectedIonList></precursor></precursorList>
+        </spectrum>
+      </spectrumList>
+    </run>
+  </mzML>
+</indexedmzML>
+"""
+
+
+def test_spectrum_splitup_writes_the_reference_layout(tmp_path):
+    """`spectrum-splitup` (src/main.rs:183-206; Spectrum::to_mz_ml, utility/mz_ml/spectrum.rs:170-231): one indexedmzML per
+    MS2 spectrum -- header re-indented tag by tag (mz_ml_reader.rs:102-143), byte offsets of the spectrum and of the index
+    list, SHA-1 over everything up to and including the opening <fileChecksum> tag, percent-encoded file names."""
+    import hashlib
+    import re
+    names = mzml.spectrum_splitup(_SPLIT_SRC, str(tmp_path), "part")
+    assert names == ["7_part.mzML", "sample%209.mzML"]       # scan id, or the encoded id; set_extension replaces ".raw_part"
+    raw = (tmp_path / names[0]).read_bytes()
+    text = raw.decode()
+    assert text.startswith('<?xml version="1.0" encoding="utf-8"?>\n<indexedmzML xmlns="http://psi.hupo.org/ms/mzml">\n    <mzML id="x" version="1.1.0">\n'
+                           '        <cvList count="1">\n            <cv id="MS" fullName="PSI MS"/>\n        </cvList>\n        <run id="r1">\n'
+                           '            <spectrumList count="1" defaultDataProcessingRef="pwiz_Reader_conversion">\n'
+                           '                <spectrum index="0" id="controllerType=0 controllerNumber=1 scan=7" defaultArrayLength="2">\n')
+    assert '                            <binary>AAAA</binary>\n' in text          # payload stays on the line of its tag
+    assert text.endswith('</fileChecksum>\n</indexedmzML>')
+    off = int(re.search(r'<offset idRef="controllerType=0 controllerNumber=1 scan=7">(\d+)</offset>', text).group(1))
+    assert raw[off:off + 9] == b"<spectrum"
+    ioff = int(re.search(r"<indexListOffset>(\d+)</indexListOffset>", text).group(1))
+    assert raw[ioff:ioff + 10] == b"<indexList"
+    upto = raw.index(b"<fileChecksum>") + len(b"<fileChecksum>")
+    assert hashlib.sha1(raw[:upto]).hexdigest().encode() == raw[upto:upto + 40]
+    # the split files are what our own reader takes
+    back, ids = mzml.read_ms_two_spectra(str(tmp_path / names[1]))
+    assert len(back) == 1 and ids[0][0] == "sample 9.raw" and float(back.precursor_mz[0]) == 600.5 and int(back.charge[0]) == 3
+    assert mzml.scan_id_of_reference("controllerType=0 controllerNumber=1 scan=7") == "7" and mzml.scan_id_of_reference("no scan here") == ""
+
+
 # ------------------------------------------------------------------------------------------ PostgreSQL CSV
 def test_pg_csv_exports(cpu):
     prots = list(wl.proteins(30))

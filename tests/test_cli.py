@@ -41,8 +41,8 @@ def test_native_host_reports_errors_instead_of_falling_back(tmp_path):
 def test_spectrum_splitup(tmp_path):
     sp, _ = wl.spectra(40, 4, 2)
     src = tmp_path / "run.mzML"
-    mzml.write_mzml(sp, str(src))
-    subprocess.check_call(CLI + ["spectrum-splitup", "-m", str(src), "-d", str(tmp_path / "split"), "-s", "_x"])
+    mzml.write_mzml(sp, str(src), indexed=True)
+    subprocess.check_call(CLI + ["spectrum-splitup", "-m", str(src), "-d", str(tmp_path / "split"), "-s", "x"])
     files = sorted(os.listdir(tmp_path / "split"))
     assert files == ["1_x.mzML", "2_x.mzML", "3_x.mzML", "4_x.mzML"]
     one, ids = mzml.read_ms_two_spectra(str(tmp_path / "split" / "3_x.mzML"))
