@@ -534,6 +534,7 @@ __device__ __noinline__ void finish_spectrum(const ScoreArgs& A, const ScoreCons
 // known at compile time); 1: general; 2: general, and spectra are divided into parts (ScoreArgs::parts > 1)
 template <bool HASVAR, int MODE>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C) {
+  if (A.n_work_dev && __ldcg(A.n_work_dev) == 0u) return;            // (launched behind k_score_pipe for the spectra it left: usually none)
   extern __shared__ __align__(16) int32_t tab[];                     // kTileBins
   int64_t* s_score = reinterpret_cast<int64_t*>(tab + kTileBins);    // kCandChunk
   int32_t* s_bin = reinterpret_cast<int32_t*>(s_score + kCandChunk); // 2 x kPeakCap
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 // into parts) use k_score; a spectrum it cannot hold (more than 512 binned peaks, a block map beyond 4096 entries, a table
 // beyond the ring) goes onto a list that k_score works off afterwards.
 #ifndef MD_PIPE_THREADS
-#define MD_PIPE_THREADS 768
+#define MD_PIPE_THREADS 640     // swept on C2 / C3: 448 .. 1024 threads; 640 (19 scorer warps at up to 102 registers) is the fastest
 #endif
 constexpr uint32_t kPipeThreads = MD_PIPE_THREADS, kPipeWarps = kPipeThreads / 32;
 constexpr uint32_t kScoreWarps = kPipeWarps - 1, kLoaderWarp = kPipeWarps - 1;
@@ -880,7 +881,8 @@ constexpr size_t kTabMaxBytes = (((size_t)kPMapCap + 1) * 2 + 15) / 16 * 16 + (s
 
 __global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __restrict__ peak_off, const int32_t* __restrict__ pk_bin, const int32_t* __restrict__ pk_yq,
                                                               const uint32_t* __restrict__ pk_count, const int32_t* __restrict__ pk_hbin, uint8_t* __restrict__ pool,
-                                                              unsigned long long* __restrict__ pool_top, TabDesc* __restrict__ desc) {
+                                                              unsigned long long* __restrict__ pool_top, TabDesc* __restrict__ desc,
+                                                              uint32_t* __restrict__ left_list, uint32_t* __restrict__ left_n) {
   __shared__ int32_t s_bin[kPPeaks], s_yq[kPPeaks];
   __shared__ uint32_t s_bits[kPMapCap / 32], s_pre[kPMapCap / 32];
   __shared__ uint16_t s_blk[kPoolBlocks];
@@ -893,7 +895,7 @@ __global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __
   const uint32_t NB = hbin >= 0 ? (uint32_t)hbin + kXcorrOffset + 1 : 0u;       // table bins [0, NB)
   const uint32_t nblk = (NB + kBlk - 1) >> kBlkShift, nwords = (nblk + 31) >> 5;
   if (hbin < 0 || NB > kMaxBins) { if (tid == 0) desc[s] = TabDesc{0ull, 0u, 0u}; return; }
-  if (npk > kPPeaks || nblk > kPMapCap) { if (tid == 0) desc[s] = TabDesc{0ull, kTabLeft, nblk}; return; }
+  if (npk > kPPeaks || nblk > kPMapCap) { if (tid == 0) { desc[s] = TabDesc{0ull, kTabLeft, nblk}; left_list[atomicAdd(left_n, 1u)] = s; } return; }
   for (uint32_t i = tid; i < npk; i += kTabThreads) { s_bin[i] = pk_bin[pk0 + i]; s_yq[i] = pk_yq[pk0 + i]; }
   for (uint32_t i = tid; i < nwords; i += kTabThreads) s_bits[i] = 0;
   __syncthreads();
@@ -920,7 +922,7 @@ __global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __
   }
   __syncthreads();
   const uint32_t nact = s_nact;
-  if (nact + 1u > kPoolBlocks || tab_map_bytes(nblk) + (nact + 1u) * kBlk * 4u > kRingBytes) { if (tid == 0) desc[s] = TabDesc{0ull, kTabLeft, nblk}; return; }
+  if (nact + 1u > kPoolBlocks || tab_map_bytes(nblk) + (nact + 1u) * kBlk * 4u > kRingBytes) { if (tid == 0) { desc[s] = TabDesc{0ull, kTabLeft, nblk}; left_list[atomicAdd(left_n, 1u)] = s; } return; }
   const unsigned long long base = s_base;
   if (tid == 0) desc[s] = TabDesc{base, nact, nblk};
   // ---- block map: entry = (block of the record << 6) | 63, block 0 of the record = the all-zero block every miss reads
@@ -1137,7 +1139,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
         }
         S.pr = pr; S.t0c = t0c; S.s = s; S.nt = nt; S.nd = nd; S.ncand = ncand; S.nunits = (ncand + 31) >> 5; S.nblk = d.nblk;
         S.scored = scored ? 1u : 0u; S.sorted = sorted ? 1u : 0u; S.unit = 0; S.left = left ? 1u : 0u; S.base = base;
-        if (left) A.left_list[atomicAdd(A.left_n, 1u)] = s;
         __threadfence_block();
         if (scored) {
           const uint32_t obytes = sorted ? ((ncand * 2u + 15u) & ~15u) : 0u;
@@ -1325,7 +1326,7 @@ void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const
   DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
   W.stat64.need(32);
   const bool tables = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
-  if (tables) { W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); }
+  if (tables) { W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); W.left_list.need(n + 2); }
   cudaStream_t main = ctx->stream, side = ctx->stream2;
   MD_CUDA(cudaEventRecord(ctx->ev_fork, main));
   MD_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
@@ -1339,7 +1340,9 @@ void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const
     MD_LAUNCH(ctx, k_max_i32, std::min<uint32_t>(blocks(n), 64), 256, 0, W.pk_hbin.p, n, d_flag.p + 2);
     if (tables) {
       MD_CUDA(cudaMemsetAsync(W.stat64.p + 4, 0, sizeof(unsigned long long), side));
-      MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p));
+      MD_CUDA(cudaMemsetAsync(W.left_list.p + n, 0, sizeof(uint32_t), side));                  // [n] = how many spectra k_build_tables leaves to k_score
+      MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p),
+                W.left_list.p, W.left_list.p + n);
     }
     MD_CUDA(cudaEventRecord(ctx->ev_prep, side));
   } catch (...) { ctx->stream = main; throw; }
@@ -1359,7 +1362,10 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_prep, 0));      // K4a and the table records (score_prepare_dev)
   MD_LAUNCH(ctx, k_max_candidates, std::min<uint32_t>(blocks(n), 64), 256, 0, W.cand_off.p, n_per ? W.dec_count.p : nullptr, n, d_flag.p + 3);
   int h_pre[4] = {0, 0, 0, 0};
+  uint32_t n_left = 0;           // spectra k_build_tables found too dense for the pipelined kernel
   MD_CUDA(cudaMemcpyAsync(h_pre, d_flag.p, sizeof(h_pre), cudaMemcpyDeviceToHost, ctx->stream));
+  const bool tables_built = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  if (tables_built) MD_CUDA(cudaMemcpyAsync(&n_left, W.left_list.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   // ---- K4
   ScoreConst C;
   memset(&C, 0, sizeof(C));
@@ -1436,8 +1442,6 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   // the pipelined kernel (builders + scorers) takes whole-spectrum work items with at most 8 PSM rows; MD_SCORE_CLASSIC=1 forces k_score
   const bool pipe = parts == 1 && p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
   if (pipe) {
-    W.left_list.need(n + 1);
-    A.left_list = W.left_list.p; A.left_n = work.p + 1;
     // the table records are there (score_prepare_dev); the length-sorted candidate order and the schedule, each by the whole GPU at once
     W.cand_order.need((size_t)n * kPOrder + 16);
     MD_LAUNCH(ctx, k_cand_order, n, 256, 0, A, n_per, W.cand_order.p);
@@ -1446,33 +1450,41 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     cubx_sort_pairs<uint32_t, uint32_t>(ctx, W.sched_key.p, W.sched_key.p + n, W.sched_val.p, W.sched_val.p + n, n);
     MD_LAUNCH(ctx, k_pair_schedule, blocks((n + 1) / 2), 256, 0, W.sched_val.p + n, n, W.sched.p);
     MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    if (n_left) {
+      // spectra too dense for the pipelined kernel (more binned peaks / a larger block map / a larger table record than it stages):
+      // k_score works them off on the side stream, beside the pipelined kernel (one CTA's worth of an SM for a moment)
+      MD_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[6], 0));
+      ScoreArgs A2 = A;
+      A2.n_work = n_left; A2.remap = W.left_list.p; A2.work = work.p + 2;
+      const uint32_t g2 = std::min<uint32_t>(std::min<uint32_t>(n_left, grid), std::max<uint32_t>(1u, grid / 8));
+      cudaStream_t main = ctx->stream;
+      ctx->stream = ctx->stream2;
+      try {
+        auto launch2 = [&](auto kernel) {
+          MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          MD_LAUNCH(ctx, kernel, g2, kScoreThreads, smem, A2, C);
+        };
+        if (has_var) { if (single) launch2(k_score<true, 0>); else launch2(k_score<true, 1>); }
+        else { if (single) launch2(k_score<false, 0>); else launch2(k_score<false, 1>); }
+        MD_CUDA(cudaEventRecord(ctx->ev_prep, ctx->stream2));
+      } catch (...) { ctx->stream = main; throw; }
+      ctx->stream = main;
+      if (ctx->trace) fprintf(stderr, "[md_trace]   score: %u of %u spectra left to k_score\n", n_left, n);
+    }
     const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p, W.sched.p};
     auto launch_pipe = [&](auto kernel) {
       MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-      MD_LAUNCH(ctx, kernel, grid, kPipeThreads, kPipeSmem, A, C, PA);
+      // (the persistent CTAs leave an SM to each CTA of the k_score launch beside them: it would otherwise wait for the first of them to end)
+      const uint32_t g2 = n_left ? std::min<uint32_t>(std::min<uint32_t>(n_left, grid), std::max<uint32_t>(1u, grid / 8)) : 0u;
+      MD_LAUNCH(ctx, kernel, grid > g2 ? grid - g2 : grid, kPipeThreads, kPipeSmem, A, C, PA);
     };
     if (has_var) launch_pipe(k_score_pipe<true>); else launch_pipe(k_score_pipe<false>);
-    // spectra the pipelined kernel could not hold (dense spectra: peaks / block map / table record beyond its staging) are on
-    // left_list now: k_score works the list off -- launched unconditionally, the count is read on the device (usually 0)
-    {
-      MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
-      A.n_work = 0; A.n_work_dev = work.p + 1; A.remap = W.left_list.p; A.work = work.p + 2;
-      const uint32_t g2 = std::min<uint32_t>(n, 16u);
-      auto launch2 = [&](auto kernel) {
-        MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MD_LAUNCH(ctx, kernel, g2, kScoreThreads, smem, A, C);
-      };
-      if (has_var) { if (single) launch2(k_score<true, 0>); else launch2(k_score<true, 1>); }
-      else { if (single) launch2(k_score<false, 0>); else launch2(k_score<false, 1>); }
-    }
+    if (n_left) MD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_prep, 0));
     MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
     if (ctx->trace) {
       unsigned long long top = 0;
-      uint32_t n_left = 0;
       MD_CUDA(cudaMemcpy(&top, W.stat64.p + 4, sizeof(top), cudaMemcpyDeviceToHost));
-      MD_CUDA(cudaMemcpy(&n_left, work.p + 1, sizeof(n_left), cudaMemcpyDeviceToHost));
-      float ms_pipe = 0, ms_left = 0; cudaEventElapsedTime(&ms_pipe, ctx->ev[6], ctx->ev[5]); cudaEventElapsedTime(&ms_left, ctx->ev[5], ctx->ev[7]);
-      fprintf(stderr, "[md_trace]   score: k_score_pipe %.3f ms, k_score over the %u spectra left %.3f ms\n", ms_pipe, n_left, ms_left);
+
       std::vector<TabDesc> hd(n);
       MD_CUDA(cudaMemcpy(hd.data(), W.tab_desc.p, n * sizeof(TabDesc), cudaMemcpyDeviceToHost));
       std::vector<uint32_t> na; for (auto& d : hd) if (d.nblk && d.nact != kTabLeft) na.push_back(d.nact);
@@ -1480,7 +1492,6 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
       if (!na.empty()) fprintf(stderr, "[md_trace]   score tables: %.1f KB per spectrum; occupied blocks p10=%u p50=%u p90=%u p99=%u max=%u\n", (double)top / n / 1024.0,
                                na[na.size() / 10], na[na.size() / 2], na[na.size() * 9 / 10], na[na.size() * 99 / 100], na.back());
     }
-    MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
   } else {
     launch_classic();
     MD_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
