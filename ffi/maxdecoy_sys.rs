@@ -43,6 +43,7 @@ pub enum md_ctx {}
     pub n_spectra: u64, pub n_targets: u64, pub n_decoys: u64, pub n_less_decoys: u64, pub n_kernel_launches: u64,
     pub ms_lookup: f64, pub ms_decoys: f64, pub ms_score: f64, pub ms_total: f64, pub ms_kernel_score: f64,
     pub ms_kernel_decoy: f64, pub n_attempts: u64, pub n_pairs: u64, pub score_bytes: u64,
+    pub ms_score_prepare: f64, pub n_score_left: u64, pub score_pipelined: u32, pub _pad: u32,
 }
 
 extern "C" {

@@ -299,6 +299,12 @@ typedef struct md_identify_stats {
   uint64_t n_attempts;        /* decoy attempts run */
   uint64_t n_pairs;           /* (spectrum, candidate) pairs scored */
   uint64_t score_bytes;       /* algorithmic bytes of the score kernel: sum over pairs of (14 + len) */
+  /* the pipelined score path: device time of what runs beside the decoy generation on the side
+   * stream (spectrum binning + table records), spectra the pipelined kernel left to the classic one, and which kernel ran */
+  double ms_score_prepare;
+  uint64_t n_score_left;
+  uint32_t score_pipelined;   /* 1: k_score_pipe scored the batch; 0: k_score */
+  uint32_t _pad;
 } md_identify_stats;
 
 /* identification_task for a batch of spectra (tasks/identification.rs:201-368), with the

@@ -160,6 +160,7 @@ void fill_kernel_stats(md_ctx* ctx, md_identify_stats* st) {
   st->n_kernel_launches = ctx->launches;
   st->ms_kernel_score = ctx->acc_ms_kscore; st->ms_kernel_decoy = ctx->acc_ms_kdecoy;
   st->n_attempts = ctx->acc_attempts; st->n_pairs = ctx->acc_pairs; st->score_bytes = ctx->acc_score_bytes;
+  st->ms_score_prepare = ctx->acc_ms_prepare; st->n_score_left = ctx->acc_left; st->score_pipelined = ctx->acc_pipelined;
 }
 
 }  // namespace
@@ -191,6 +192,7 @@ int md_create(const md_config* cfg, md_ctx** out) {
     MD_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     MD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     MD_CUDA(cudaEventCreateWithFlags(&c->ev_prep, cudaEventDisableTiming));
+    MD_CUDA(cudaEventCreate(&c->ev_side0)); MD_CUDA(cudaEventCreate(&c->ev_side1));
     for (auto& ev : c->ev) MD_CUDA(cudaEventCreate(&ev));
     *out = c;
     return MD_OK;
@@ -207,6 +209,8 @@ void md_destroy(md_ctx* ctx) {
   if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_prep) cudaEventDestroy(ctx->ev_prep);
+  if (ctx->ev_side0) cudaEventDestroy(ctx->ev_side0);
+  if (ctx->ev_side1) cudaEventDestroy(ctx->ev_side1);
   comm_release(ctx);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStream_t s = ctx->stream;

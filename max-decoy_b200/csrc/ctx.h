@@ -92,7 +92,7 @@ struct md_ctx {
   int n_sm = MD_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;          // side stream: work that depends on the spectra alone runs beside the decoy generation
-  cudaEvent_t ev_fork = nullptr, ev_prep = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_prep = nullptr, ev_side0 = nullptr, ev_side1 = nullptr;   // (ev_side*: timing of the side stream's work)
   cudaEvent_t ev[8] = {};
   // modifications
   bool mods_set = false;
@@ -120,14 +120,15 @@ struct md_ctx {
   uint64_t launches = 0;   // hand-written kernels launched by the current call
   uint64_t cub_calls = 0;  // CUB primitive invocations (scan/select/sort), counted separately
   // per-call accumulators reported through md_identify_stats
-  double acc_ms_kscore = 0, acc_ms_kdecoy = 0;
+  double acc_ms_kscore = 0, acc_ms_kdecoy = 0, acc_ms_prepare = 0;
+  uint64_t acc_left = 0; uint32_t acc_pipelined = 0;
   uint64_t acc_attempts = 0, acc_pairs = 0, acc_score_bytes = 0;
   // MD_TRACE=1: host wall-clock marks of the current call, dumped to stderr at its end
   bool trace = false;
   std::vector<std::pair<const char*, double>> marks;
   void mark(const char* what);
   void dump_marks(const char* call);
-  void reset_counters() { launches = 0; cub_calls = 0; acc_ms_kscore = acc_ms_kdecoy = 0; acc_attempts = acc_pairs = acc_score_bytes = 0; }
+  void reset_counters() { launches = 0; cub_calls = 0; acc_ms_kscore = acc_ms_kdecoy = acc_ms_prepare = 0; acc_attempts = acc_pairs = acc_score_bytes = 0; acc_left = 0; acc_pipelined = 0; }
 };
 
 // per-call helper: count our own kernel launches (bench.py reports it as gpu_launches)

@@ -1332,6 +1332,7 @@ void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const
   MD_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
   ctx->stream = side;     // (MD_LAUNCH launches on ctx->stream)
   try {
+    MD_CUDA(cudaEventRecord(ctx->ev_side0, side));
     MD_CUDA(cudaMemsetAsync(d_flag.p, 0, 4 * sizeof(int), side));
     MD_CUDA(cudaMemsetAsync(W.pk_yq.p, 0, (n_peaks + 1) * sizeof(int32_t), side));
     MD_LAUNCH(ctx, k_bin_spectra, blocks((uint64_t)n * 32, 128), 128, 0, S.peak_off, S.peak_mz, S.peak_int, W.prec.p, n, w, p.min_peaks, W.pk_bin.p, W.pk_yq.p,
@@ -1344,6 +1345,7 @@ void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const
       MD_LAUNCH(ctx, k_build_tables, n, kTabThreads, 0, S.peak_off, W.pk_bin.p, W.pk_yq.p, W.pk_count.p, W.pk_hbin.p, W.tab_pool.p, W.stat64.p + 4, reinterpret_cast<TabDesc*>(W.tab_desc.p),
                 W.left_list.p, W.left_list.p + n);
     }
+    MD_CUDA(cudaEventRecord(ctx->ev_side1, side));
     MD_CUDA(cudaEventRecord(ctx->ev_prep, side));
   } catch (...) { ctx->stream = main; throw; }
   ctx->stream = main;
@@ -1502,6 +1504,8 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   MD_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof(h_flag), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaStreamSynchronize(ctx->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->acc_ms_kscore += ms; ctx->acc_pairs += h_stat[0]; ctx->acc_score_bytes += h_stat[1]; }
+  { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev_side0, ctx->ev_side1) == cudaSuccess) ctx->acc_ms_prepare += ms; else cudaGetLastError(); }
+  ctx->acc_left += pipe ? n_left : 0u; ctx->acc_pipelined = pipe ? 1u : 0u;
   if (timing && pipe) {
     unsigned long long t[12];
     MD_CUDA(cudaMemcpy(t, W.stat64.p + 8, sizeof(t), cudaMemcpyDeviceToHost));

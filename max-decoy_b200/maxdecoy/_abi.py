@@ -102,7 +102,8 @@ class md_identify_stats(C.Structure):
                 ("n_less_decoys", C.c_uint64), ("n_kernel_launches", C.c_uint64),
                 ("ms_lookup", C.c_double), ("ms_decoys", C.c_double), ("ms_score", C.c_double),
                 ("ms_total", C.c_double), ("ms_kernel_score", C.c_double), ("ms_kernel_decoy", C.c_double),
-                ("n_attempts", C.c_uint64), ("n_pairs", C.c_uint64), ("score_bytes", C.c_uint64)]
+                ("n_attempts", C.c_uint64), ("n_pairs", C.c_uint64), ("score_bytes", C.c_uint64),
+                ("ms_score_prepare", C.c_double), ("n_score_left", C.c_uint64), ("score_pipelined", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 # numpy dtype with the exact md_psm layout (for zero-copy views of PSM buffers)

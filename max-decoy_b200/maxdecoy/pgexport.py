@@ -105,3 +105,75 @@ def psms_csv(psms, ids, sequences_of_candidate, modres_of_candidate, precursor_m
                          int(row["mod_weight"]), int(precursor_masses[s]), int(row["charge"]), repr(float(row["score"])),
                          int(row["n_targets"]) + int(row["n_decoys"])))
     return _csv(rows)
+
+
+# ------------------------------------------------------------------------------------------------
+# .env / PGSQL_URL (utility/database_connection.rs:8-20) and the way back from the database
+# ------------------------------------------------------------------------------------------------
+def database_url(env_path=".env", environ=None):
+    """DatabaseConnection::get_database_url: load `.env` (dotenv semantics: KEY=VALUE lines, `#` comments, optional quotes,
+    variables already in the environment win) and return PGSQL_URL.  Raises where the reference panics."""
+    import os
+    environ = os.environ if environ is None else environ
+    values = {}
+    try:
+        with open(env_path) as fh:
+            for line in fh:
+                line = line.strip()
+                if not line or line.startswith("#") or "=" not in line:
+                    continue
+                if line.startswith("export "):
+                    line = line[7:].lstrip()
+                k, v = line.split("=", 1)
+                v = v.strip()
+                if len(v) >= 2 and v[0] == v[-1] and v[0] in "\"'":
+                    v = v[1:-1]
+                values[k.strip()] = v
+    except OSError as err:
+        raise RuntimeError("Could not load .env-file, reason: %s" % err)
+    url = environ.get("PGSQL_URL", values.get("PGSQL_URL"))
+    if not url:
+        raise RuntimeError("Variable 'PGSQL_URL' must be set in .env")
+    return url
+
+
+TABLE_COLUMNS = {
+    "proteins": "id, accession, header, aa_sequence, is_completely_digested",
+    "peptides": "id, aa_sequence, length, number_of_missed_cleavages, weight, " + ", ".join(c + "_count" for c in COUNT_COLUMNS),
+    "peptides_proteins": "peptide_id, protein_id",
+    "decoys": "id, aa_sequence, length, number_of_missed_cleavages, weight, " + ", ".join(c + "_count" for c in COUNT_COLUMNS),
+    "psms": "spectrum_id, scan_id, rank, is_decoy, peptide_id, aa_sequence, modres, weight, precursor_mass, charge, score, n_candidates",
+}
+
+
+def load_script(directory, tables=("proteins", "peptides", "peptides_proteins", "decoys", "psms"), env_path=None):
+    """The psql script that loads the exported CSV files into the reference's schema (db/schema.sql) in dependency order --
+    `\\copy` runs client side, so the files need not be readable by the server.  With `env_path` the command line that
+    feeds it to the database of the reference's `.env` is returned too: (script, command)."""
+    import os
+    lines = ["-- load the tables exported by the B200 hot path into the max-decoy schema (db/schema.sql)", "BEGIN;"]
+    if "psms" in tables:
+        lines.append(PSMS_DDL.replace("CREATE TABLE psms", "CREATE TABLE IF NOT EXISTS psms").rstrip())
+    for t in tables:
+        path = os.path.join(directory, t + ".csv")
+        lines.append("\\copy %s (%s) FROM '%s' WITH (FORMAT csv)" % (t, TABLE_COLUMNS[t], path))
+    for t in ("proteins", "peptides", "decoys"):
+        if t in tables:      # the serial ids were given explicitly: move the sequences behind them
+            lines.append("SELECT setval(pg_get_serial_sequence('%s', 'id'), (SELECT COALESCE(MAX(id), 1) FROM %s));" % (t, t))
+    lines.append("COMMIT;")
+    script = "\n".join(lines) + "\n"
+    if env_path is None:
+        return script
+    return script, ["psql", database_url(env_path), "-v", "ON_ERROR_STOP=1", "-f", os.path.join(directory, "load.sql")]
+
+
+def unload_script(directory, tables=("peptides", "decoys")):
+    """The other direction: `\\copy ... TO` for the tables the hot path takes as input (`peptides` for a digest done by the
+    reference, `decoys` for md_decoy_store_set / --stored-decoys), in the column order the readers here expect."""
+    import os
+    return "".join("\\copy (SELECT %s FROM %s ORDER BY id) TO '%s' WITH (FORMAT csv)\n" % (TABLE_COLUMNS[t], t, os.path.join(directory, t + ".csv")) for t in tables)
+
+
+def read_sequences_csv(text):
+    """aa_sequence column (second field) of a `peptides` / `decoys` CSV as exported above or by unload_script."""
+    return [row[1] for row in csv.reader(io.StringIO(text)) if len(row) > 1 and row[1] and row[1].isalpha()]

@@ -208,3 +208,27 @@ def test_pg_csv_exports(cpu):
     out = pgexport.psms_csv(psms, ids, lambda s_, r: "SEQ", lambda s_, r: "", [p[0] for p in wl.precursors_of(cpu, sp)])
     lines = out.splitlines()
     assert len(lines) == int((psms["rank"] > 0).sum()) and lines[0].startswith("scan=1,1,1,")
+
+
+def test_env_file_and_database_scripts(tmp_path):
+    """`.env` -> PGSQL_URL as DatabaseConnection::get_database_url reads it (utility/database_connection.rs:8-20), the psql
+    load script for the exported tables in dependency order, and the way back (decoys table -> stored decoys)."""
+    env = tmp_path / ".env"
+    env.write_text("# comment\nPGSQL_URL=postgres://u:p@localhost:5432/maxdecoy\nPGSQL_TLS_MODE=NONE\n")
+    assert pgexport.database_url(str(env), environ={}) == "postgres://u:p@localhost:5432/maxdecoy"
+    assert pgexport.database_url(str(env), environ={"PGSQL_URL": "postgres://other"}) == "postgres://other"      # the environment wins (dotenv)
+    env.write_text('export PGSQL_URL="postgres://quoted/db"\n')
+    assert pgexport.database_url(str(env), environ={}) == "postgres://quoted/db"
+    env.write_text("PGSQL_TLS_MODE=NONE\n")
+    with pytest.raises(RuntimeError, match="PGSQL_URL"):
+        pgexport.database_url(str(env), environ={})
+    with pytest.raises(RuntimeError, match="Could not load"):
+        pgexport.database_url(str(tmp_path / "missing.env"), environ={})
+    env.write_text("PGSQL_URL=postgres://u@h/db\n")
+    script, cmd = pgexport.load_script(str(tmp_path), env_path=str(env))
+    order = [ln.split()[1] for ln in script.splitlines() if ln.startswith("\\copy")]
+    assert order == ["proteins", "peptides", "peptides_proteins", "decoys", "psms"]
+    assert "a_count) FROM" in script and script.index("r_count") < script.index("a_count")            # schema order: a_count last
+    assert cmd[:2] == ["psql", "postgres://u@h/db"] and "CREATE TABLE IF NOT EXISTS psms" in script
+    assert "\\copy (SELECT id, aa_sequence" in pgexport.unload_script(str(tmp_path))
+    assert pgexport.read_sequences_csv("1,AAGK,4,0,1,0\n2,DECJY,5,0,1\nbad\n") == ["AAGK", "DECJY"]
