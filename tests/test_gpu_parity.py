@@ -297,12 +297,15 @@ def _dense_spectra(n, n_peaks, seed=1):
 
 
 @pytest.mark.parametrize("case", ["wide_window_chunked", "wide_window_running_lists", "wide_window_split", "top_k_generic", "dense_peaks", "low_res_bins", "high_charge",
-                                  "few_peaks_and_empty"])
+                                  "few_peaks_and_empty", "classic_kernel", "many_decoys_unsorted"])
 def test_identify_kernel_paths(gpu, cpu, case, monkeypatch):
     """The branches of k_score the 10-ppm / top-5 cases never reach: candidate chunks beyond shared memory with the
     generic top-k merge, the same with per-warp running top-k lists (top_k <= 8), spectra split into parts over several CTAs
     (what an open search over few spectra does), top_k > 8, spectra whose binned peaks do not fit shared memory, 1.0005-Da bins (one tile),
-    fragment charges up to 3, and spectra that are not scored at all."""
+    fragment charges up to 3, and spectra that are not scored at all.  Since round 2 the usual batch goes through k_score_pipe
+    (tables prebuilt, streamed in): `classic_kernel` forces k_score for it, `many_decoys_unsorted` gives every spectrum more
+    candidates than k_cand_order sorts (natural order), `dense_peaks` are the spectra the pipelined kernel leaves to k_score on
+    the side stream, `wide_window_running_lists` its many-units-per-spectrum case."""
     for e in (gpu, cpu):
         _setup(e, 600, 2, (synth.CAM, synth.OXM), 2)
     sp, _ = wl.spectra(600, 24, 2, with_ox=True)
@@ -316,6 +319,10 @@ def test_identify_kernel_paths(gpu, cpu, case, monkeypatch):
         monkeypatch.setenv("MD_SCORE_SPLIT_MIN", "1")
     elif case == "top_k_generic":
         kw.update(top_k=40)
+    elif case == "classic_kernel":
+        monkeypatch.setenv("MD_SCORE_CLASSIC", "1")
+    elif case == "many_decoys_unsorted":
+        kw.update(n_decoys=2300, top_k=8)
     elif case == "dense_peaks":
         sp = _dense_spectra(12, 2500)
     elif case == "low_res_bins":
