@@ -873,6 +873,7 @@ constexpr uint32_t kPoolBlocks = 856;      // most 64-bin blocks (the all-zero b
 constexpr uint32_t kRingBytes = 214 * 1024; // shared-memory ring that holds the table records (block map + table) of two spectra
 constexpr uint32_t kPipeEnd = 0xFFFFFFFFu, kTabLeft = 0xFFFFFFFFu;
 constexpr uint32_t kTabThreads = 256;
+constexpr uint32_t kPipeMaxParts = 16;     // most work items the pipelined kernel splits a spectrum into
 
 // where a spectrum's table record lies in the pool.  nblk == 0: the spectrum is not scored (too few peaks); nact == kTabLeft: k_score takes it
 struct TabDesc { unsigned long long off; uint32_t nact, nblk; };
@@ -971,16 +972,21 @@ __global__ void __launch_bounds__(kTabThreads) k_build_tables(const uint64_t* __
 // The order in which the persistent CTAs take the spectra: pairs of (large record, small record) -- the p-th largest with the
 // p-th smallest -- so that two consecutive spectra of a CTA nearly always fit the ring side by side and every pair is about
 // the same amount of work.  k_table_keys: record size per spectrum (the sort key); k_pair_schedule: sorted order -> pairs.
-__global__ void k_table_keys(const TabDesc* __restrict__ desc, uint32_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+// A split batch (parts > 1) is scheduled by work instead: the spectra with the most candidates first.
+__global__ void k_table_keys(const TabDesc* __restrict__ desc, uint32_t n, const uint64_t* __restrict__ cand_off, const uint32_t* __restrict__ dec_count, bool by_work,
+                             uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   const TabDesc d = desc[s];
-  key[s] = (d.nblk != 0u && d.nact != kTabLeft) ? tab_map_bytes(d.nblk) + (d.nact + 1u) * kBlk * 4u : 0u;
+  const bool scored = d.nblk != 0u && d.nact != kTabLeft;
+  if (by_work) key[s] = scored ? (uint32_t)min(cand_off[s + 1] - cand_off[s] + (dec_count ? dec_count[s] : 0u), (uint64_t)0xFFFFFFFFu) : 0u;
+  else key[s] = scored ? tab_map_bytes(d.nblk) + (d.nact + 1u) * kBlk * 4u : 0u;
   val[s] = s;
 }
-__global__ void k_pair_schedule(const uint32_t* __restrict__ asc, uint32_t n, uint32_t* __restrict__ sched) {
+__global__ void k_pair_schedule(const uint32_t* __restrict__ asc, uint32_t n, bool descending, uint32_t* __restrict__ sched) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;   // pair
   if (2 * p >= n) return;
+  if (descending) { sched[2 * p] = asc[n - 1 - 2 * p]; if (2 * p + 1 < n) sched[2 * p + 1] = asc[n - 2 - 2 * p]; return; }
   sched[2 * p] = asc[n - 1 - p];
   if (2 * p + 1 < n) sched[2 * p + 1] = asc[p];
 }
@@ -1018,10 +1024,44 @@ __global__ void __launch_bounds__(256) k_cand_order(const ScoreArgs A, uint32_t 
   }
 }
 
+// A spectrum split into parts: the work item leaves its K best keys; the last part of the spectrum to arrive merges them all
+// (lane r returns with the spectrum's r-th best key) and writes the rows.  False: another part will.
+__device__ __noinline__ bool merge_parts(const ScoreArgs& A, uint32_t s, uint32_t part, uint32_t parts, uint32_t K, unsigned long long& best) {
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned long long* pt = A.part_top + (size_t)s * parts * kFastTopK;
+  if (lane < kFastTopK) pt[part * kFastTopK + lane] = lane < K ? best : 0ull;
+  __threadfence();
+  __syncwarp();
+  uint32_t arrived = 0;
+  if (lane == 0) arrived = atomicAdd(&A.parts_done[s], 1u);
+  arrived = __shfl_sync(0xffffffffu, arrived, 0);
+  if (arrived + 1 != parts) return false;
+  __threadfence();
+  static_assert(kPipeMaxParts * kFastTopK <= 128, "a lane merges at most four keys of the parts' lists");
+  unsigned long long k[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) k[j] = lane + 32u * j < parts * kFastTopK ? __ldcg(pt + lane + 32u * j) : 0ull;
+  best = 0ull;
+  for (uint32_t r = 0; r < K; r++) {
+    unsigned long long m = k[0];
+#pragma unroll
+    for (int j = 1; j < 4; j++) m = k[j] > m ? k[j] : m;
+    const unsigned long long wm = warp_max_u64(m);
+    if (wm != 0ull) {
+      bool gone = false;     // (keys are unique: at most one of the lane's four matches)
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (!gone && k[j] == wm) { k[j] = 0ull; gone = true; }
+    }
+    if (lane == r) best = wm;
+  }
+  return true;
+}
+
 struct PipeSlot {
   md_precursor pr;
   uint64_t t0c;
   uint32_t s, nt, nd, ncand, nunits, nblk, scored, sorted, left, base;
+  uint32_t part, u_hi; // the work item's part of the spectrum, and where its units end (the whole spectrum unless the batch is split)
   uint32_t unit;      // next unit of the spectrum (scorers)
   uint32_t done;      // scorer warps that have left the spectrum
 };
@@ -1074,7 +1114,7 @@ __device__ __forceinline__ void mbar_wait_warp(unsigned long long* bar, uint32_t
 
 constexpr size_t kPipeSmem = (size_t)kRingBytes + 2 * (size_t)kPOrder * 2;
 
-struct PipeArgs { const TabDesc* desc; const uint8_t* pool; const uint16_t* order; const uint32_t* sched; };
+struct PipeArgs { const TabDesc* desc; const uint8_t* pool; const uint16_t* order; const uint32_t* sched; uint32_t parts; };
 
 template <bool HASVAR>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_constant__ ScoreArgs A, const __grid_constant__ ScoreConst C, const PipeArgs T) {
@@ -1099,11 +1139,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
         const uint32_t b = q & 1, use = q >> 1;
         PipeSlot& S = sh.slot[b];
         // work items are PAIRS of the schedule (large record, then small record)
-        uint32_t s = pend;
+        // (a split batch -- few spectra, very many candidates each -- has parts x spectra items instead: consecutive tickets are
+        //  the parts of one spectrum, which different CTAs then score at the same time)
+        uint32_t s = pend, part = 0;
         pend = kPipeEnd;
         if (s == kPipeEnd) {
           const uint32_t t = atomicAdd(A.work, 1u);
-          if (2ull * t < A.n_spec) { s = T.sched[2 * t]; if (2 * t + 1 < A.n_spec) pend = T.sched[2 * t + 1]; }
+          if (T.parts > 1) { if (t < (unsigned long long)A.n_spec * T.parts) { s = T.sched[t / T.parts]; part = t % T.parts; } }
+          else if (2ull * t < A.n_spec) { s = T.sched[2 * t]; if (2 * t + 1 < A.n_spec) pend = T.sched[2 * t + 1]; }
         }
         const bool end = s == kPipeEnd;
         // (what the spectrum needs is fetched before the slot is waited for)
@@ -1138,7 +1181,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
           base = b ? kRingBytes - need : 0u;
         }
         S.pr = pr; S.t0c = t0c; S.s = s; S.nt = nt; S.nd = nd; S.ncand = ncand; S.nunits = (ncand + 31) >> 5; S.nblk = d.nblk;
-        S.scored = scored ? 1u : 0u; S.sorted = sorted ? 1u : 0u; S.unit = 0; S.left = left ? 1u : 0u; S.base = base;
+        S.scored = scored ? 1u : 0u; S.sorted = sorted ? 1u : 0u; S.left = left ? 1u : 0u; S.base = base;
+        {
+          const uint32_t nunits = (ncand + 31) >> 5, per = (nunits + T.parts - 1) / T.parts;
+          const uint32_t u_lo = min(nunits, part * per);
+          S.part = part; S.unit = u_lo; S.u_hi = min(nunits, u_lo + per);
+        }
         __threadfence_block();
         if (scored) {
           const uint32_t obytes = sorted ? ((ncand * 2u + 15u) & ~15u) : 0u;
@@ -1182,8 +1230,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
     if (s == kPipeEnd) break;
     const md_precursor pr = S.pr;
     const uint64_t t0c = S.t0c;
-    const uint32_t nt = S.nt, nd = S.nd, ncand = S.ncand, nunits = S.nunits;
+    const uint32_t nt = S.nt, nd = S.nd, ncand = S.ncand, nunits = S.u_hi;
     const bool scored = S.scored != 0, sorted = S.sorted != 0, left_out = S.left != 0;
+    const uint32_t S_part = S.part;
     const uint16_t* order = s_order0 + b * kPOrder;
     uint32_t nch = pr.charge > 1 ? pr.charge - 1 : 1;
     if (nch > C.max_frag_charge) nch = C.max_frag_charge;
@@ -1272,6 +1321,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_score_pipe(const __grid_con
 #else
       __syncwarp();
       if (lane == 0) { S.done = 0; if (A.timing) sh.state[b] = 0; __threadfence_block(); mbar_arrive(&sh.empty[b]); }
+      if (T.parts > 1 && !left_out) { if (!merge_parts(A, s, S_part, T.parts, K, best)) continue; }
       if (lane < K && !left_out) write_psm_row(A, C, pr, s, lane, best, nt, nd, t0c);
 #endif
     }
@@ -1393,6 +1443,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   // chunks: split every spectrum into `parts` work items (contiguous ranges of candidate chunks; each builds the table
   // itself, which is cheap beside the chunks), about two items per SM.  MD_SCORE_SPLIT_MIN = candidates per spectrum
   // (batch average) from which that is done (tests lower it).
+  const bool pipe_path = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr && getenv("MD_SCORE_SPLIT_CLASSIC") == nullptr;
   uint32_t parts = 1;
   {
     uint64_t n_cand = (uint64_t)n * n_per, split_min = 16ull * kCandChunk;
@@ -1401,6 +1452,17 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     if (n < (uint32_t)ctx->n_sm && p.top_k <= kFastTopK && n_cand / n >= split_min)
       parts = std::min<uint32_t>(std::min<uint32_t>(8u, (2u * (uint32_t)ctx->n_sm + n - 1) / n), (uint32_t)((n_cand / n + kCandChunk - 1) / kCandChunk));
     parts = std::max(parts, 1u);
+    // the pipelined kernel merges up to kPipeMaxParts lists: of the part counts that leave every scorer warp a few units, the one
+    // whose items fill whole rounds of the persistent CTAs best
+    if (parts > 1 && pipe_path) {
+      const uint64_t units = (n_cand / n + 31) / 32;
+      double best_fill = 0;
+      for (uint32_t k = parts; k <= kPipeMaxParts && units / k >= 8ull * kScoreWarps; k++) {
+        const double rounds = (double)n * k / ctx->n_sm, fill = rounds / std::ceil(rounds);
+        if (fill > best_fill + 0.02) { best_fill = fill; parts = k; }
+      }
+    }
+    if (const char* env = getenv("MD_SCORE_PARTS")) parts = std::min<uint32_t>(std::max(1, atoi(env)), pipe_path ? kPipeMaxParts : 8u);   // (tests)
   }
   const uint32_t grid = std::min<uint32_t>(n * parts, (uint32_t)ctx->n_sm);
   const uint32_t max_nblk = h_pre[2] >= 0 ? ((uint32_t)h_pre[2] + kXcorrOffset + 1 + kBlk - 1) / kBlk : 0;
@@ -1442,22 +1504,23 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     else { if (parts > 1) launch(k_score<false, 2>); else if (single) launch(k_score<false, 0>); else launch(k_score<false, 1>); }
   };
   // the pipelined kernel (builders + scorers) takes whole-spectrum work items with at most 8 PSM rows; MD_SCORE_CLASSIC=1 forces k_score
-  const bool pipe = parts == 1 && p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  const bool pipe = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr && (parts == 1 || pipe_path);
   if (pipe) {
     // the table records are there (score_prepare_dev); the length-sorted candidate order and the schedule, each by the whole GPU at once
     W.cand_order.need((size_t)n * kPOrder + 16);
     MD_LAUNCH(ctx, k_cand_order, n, 256, 0, A, n_per, W.cand_order.p);
     W.sched_key.need(2 * (size_t)n + 2); W.sched_val.need(2 * (size_t)n + 2); W.sched.need(n + 2);
-    MD_LAUNCH(ctx, k_table_keys, blocks(n), 256, 0, reinterpret_cast<const TabDesc*>(W.tab_desc.p), n, W.sched_key.p, W.sched_val.p);
+    MD_LAUNCH(ctx, k_table_keys, blocks(n), 256, 0, reinterpret_cast<const TabDesc*>(W.tab_desc.p), n, W.cand_off.p, n_per ? W.dec_count.p : nullptr, parts > 1, W.sched_key.p,
+              W.sched_val.p);
     cubx_sort_pairs<uint32_t, uint32_t>(ctx, W.sched_key.p, W.sched_key.p + n, W.sched_val.p, W.sched_val.p + n, n);
-    MD_LAUNCH(ctx, k_pair_schedule, blocks((n + 1) / 2), 256, 0, W.sched_val.p + n, n, W.sched.p);
+    MD_LAUNCH(ctx, k_pair_schedule, blocks((n + 1) / 2), 256, 0, W.sched_val.p + n, n, parts > 1, W.sched.p);
     MD_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     if (n_left) {
       // spectra too dense for the pipelined kernel (more binned peaks / a larger block map / a larger table record than it stages):
       // k_score works them off on the side stream, beside the pipelined kernel (one CTA's worth of an SM for a moment)
       MD_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[6], 0));
       ScoreArgs A2 = A;
-      A2.n_work = n_left; A2.remap = W.left_list.p; A2.work = work.p + 2;
+      A2.n_work = n_left; A2.remap = W.left_list.p; A2.work = work.p + 2; A2.parts = 1;
       const uint32_t g2 = std::min<uint32_t>(std::min<uint32_t>(n_left, grid), std::max<uint32_t>(1u, grid / 8));
       cudaStream_t main = ctx->stream;
       ctx->stream = ctx->stream2;
@@ -1473,7 +1536,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
       ctx->stream = main;
       if (ctx->trace) fprintf(stderr, "[md_trace]   score: %u of %u spectra left to k_score\n", n_left, n);
     }
-    const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p, W.sched.p};
+    const PipeArgs PA{reinterpret_cast<const TabDesc*>(W.tab_desc.p), W.tab_pool.p, W.cand_order.p, W.sched.p, parts};
     auto launch_pipe = [&](auto kernel) {
       MD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
       // (the persistent CTAs leave an SM to each CTA of the k_score launch beside them: it would otherwise wait for the first of them to end)

@@ -297,13 +297,13 @@ def _dense_spectra(n, n_peaks, seed=1):
 
 
 @pytest.mark.parametrize("case", ["wide_window_chunked", "wide_window_running_lists", "wide_window_split", "top_k_generic", "dense_peaks", "low_res_bins", "high_charge",
-                                  "few_peaks_and_empty", "classic_kernel", "many_decoys_unsorted"])
+                                  "few_peaks_and_empty", "classic_kernel", "many_decoys_unsorted", "wide_window_split_classic", "wide_window_split_16"])
 def test_identify_kernel_paths(gpu, cpu, case, monkeypatch):
     """The branches of k_score the 10-ppm / top-5 cases never reach: candidate chunks beyond shared memory with the
     generic top-k merge, the same with per-warp running top-k lists (top_k <= 8), spectra split into parts over several CTAs
     (what an open search over few spectra does), top_k > 8, spectra whose binned peaks do not fit shared memory, 1.0005-Da bins (one tile),
     fragment charges up to 3, and spectra that are not scored at all.  Since round 2 the usual batch goes through k_score_pipe
-    (tables prebuilt, streamed in): `classic_kernel` forces k_score for it, `many_decoys_unsorted` gives every spectrum more
+    (tables prebuilt, streamed in; split batches too, `wide_window_split_classic` is k_score's split): `classic_kernel` forces k_score for it, `many_decoys_unsorted` gives every spectrum more
     candidates than k_cand_order sorts (natural order), `dense_peaks` are the spectra the pipelined kernel leaves to k_score on
     the side stream, `wide_window_running_lists` its many-units-per-spectrum case."""
     for e in (gpu, cpu):
@@ -317,6 +317,13 @@ def test_identify_kernel_paths(gpu, cpu, case, monkeypatch):
     elif case == "wide_window_split":
         kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=8)
         monkeypatch.setenv("MD_SCORE_SPLIT_MIN", "1")
+    elif case == "wide_window_split_classic":
+        kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=8)
+        monkeypatch.setenv("MD_SCORE_SPLIT_MIN", "1")
+        monkeypatch.setenv("MD_SCORE_SPLIT_CLASSIC", "1")
+    elif case == "wide_window_split_16":
+        kw.update(abs_lower_uda=60_000_000, abs_upper_uda=60_000_000, n_decoys=10, top_k=8)
+        monkeypatch.setenv("MD_SCORE_PARTS", "16")
     elif case == "top_k_generic":
         kw.update(top_k=40)
     elif case == "classic_kernel":
