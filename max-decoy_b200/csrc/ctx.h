@@ -33,6 +33,7 @@ struct MassIndex {
   DevBuf<uint64_t> varpos;  // positions whose letter has a variable modification
   DevBuf<uint64_t> desc;    // score-row descriptor: row offset/16 | len << 40
   DevBuf<uint8_t> rows;     // residue codes, 16-byte padded rows, index order
+  DevBuf<int16_t> lcnt;     // per entry: the peptide's counts of the modifiable letters (ModTables::letter_alpha order)
   // MD_VARMOD_EXPANDED: the same entries ordered by wfix (stable over index order)
   DevBuf<int64_t> fkey;     // wfix, ascending
   DevBuf<uint32_t> fent;    // index entry of that key

@@ -87,6 +87,15 @@ __device__ uint64_t warp_bound(const int64_t* __restrict__ key, uint64_t n, int6
 }
 
 // one warp per precursor: [begin, end) = { i : lo <= W*[i] <= hi }
+// per index entry: the peptide's counts of the modifiable letters (what the filter's fan-out test reads), in index order
+__global__ void k_index_letter_counts(const uint32_t* __restrict__ pep, uint32_t n, const int16_t* __restrict__ counts, const __grid_constant__ ModTables M,
+                                      int16_t* __restrict__ lcnt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = pep[i];
+  for (int k = 0; k < M.n_letters; k++) lcnt[(uint64_t)i * M.n_letters + k] = counts[(size_t)p * MD_ALPHABET_SIZE + M.letter_alpha[k]];
+}
+
 __global__ void k_window_search(const int64_t* __restrict__ key, uint64_t n, const md_precursor* __restrict__ prec, uint32_t n_prec,
                                 uint64_t* __restrict__ begin, uint64_t* __restrict__ end) {
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -122,7 +131,7 @@ struct RowSeq {
 // The ModifiedPeptide filter for every entry of every window (identification.rs:231-257,374-403).
 __global__ void k_filter(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, const md_precursor* __restrict__ prec, uint32_t n_spec,
                          uint64_t n_entries, const uint32_t* __restrict__ idx_pep, const int64_t* __restrict__ idx_wfix, const uint64_t* __restrict__ idx_varpos,
-                         const uint64_t* __restrict__ idx_desc, const uint8_t* __restrict__ rows, const int16_t* __restrict__ counts,
+                         const uint64_t* __restrict__ idx_desc, const uint8_t* __restrict__ rows, const int16_t* __restrict__ lcnt,
                          const int16_t* __restrict__ specK, const __grid_constant__ ModTables M, uint32_t* __restrict__ flag, uint64_t* __restrict__ emask,
                          int64_t* __restrict__ ew, int* __restrict__ overflow) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,11 +142,11 @@ __global__ void k_filter(const uint64_t* __restrict__ flat_off, const uint64_t* 
   const uint32_t s = lo;
   const uint64_t i = rbegin[s] + (e - flat_off[s]);
   const md_precursor pr = prec[s];
-  const uint32_t p = idx_pep[i];
+  (void)idx_pep;
   bool ok = M.n_letters > 0;  // no modifiable letter -> the recursion emits no query (identification.rs:375-379)
   int64_t cur_lo = pr.lo;
   for (int k = 0; k < M.n_letters && ok; k++) {
-    int16_t c = counts[(size_t)p * MD_ALPHABET_SIZE + M.letter_alpha[k]];
+    int16_t c = lcnt[i * (uint64_t)M.n_letters + k];         // the peptide's count of the k-th modifiable letter, in index order (k_index_letter_counts)
     if (!(c < specK[s * MD_ALPHABET_SIZE + k])) ok = false;   // 0..max_modification_count (exclusive, :381)
     if (!(cur_lo > 0)) ok = false;                           // :387
     cur_lo -= (int64_t)c * M.letter_delta[k];
@@ -153,22 +162,21 @@ __global__ void k_filter(const uint64_t* __restrict__ flat_off, const uint64_t* 
     }
   }
   flag[e] = ok ? 1u : 0u;
-  emask[e] = mask;
-  ew[e] = w;
+  if (emask) { emask[e] = mask; ew[e] = w; }     // (NULL: no variable modification is configured, an accepted entry is (0, wfix))
 }
 
 __global__ void k_scatter_candidates(const uint64_t* __restrict__ flat_off, const uint64_t* __restrict__ rbegin, uint32_t n_spec, uint64_t n_entries,
                                      const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, const uint64_t* __restrict__ emask,
                                      const int64_t* __restrict__ ew, const uint32_t* __restrict__ idx_pep, const uint64_t* __restrict__ idx_desc,
-                                     uint64_t* __restrict__ cand_desc, uint64_t* __restrict__ cand_mask, int64_t* __restrict__ cand_w,
-                                     uint32_t* __restrict__ cand_pep) {
+                                     const int64_t* __restrict__ idx_wfix, uint64_t* __restrict__ cand_desc, uint64_t* __restrict__ cand_mask,
+                                     int64_t* __restrict__ cand_w, uint32_t* __restrict__ cand_pep) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_entries || !flag[e]) return;
   uint32_t lo = 0, hi = n_spec;
   while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (flat_off[mid] <= e) lo = mid; else hi = mid; }
   const uint64_t i = rbegin[lo] + (e - flat_off[lo]);
   uint32_t o = pos[e];
-  cand_desc[o] = idx_desc[i]; cand_mask[o] = emask[e]; cand_w[o] = ew[e]; cand_pep[o] = idx_pep[i];
+  cand_desc[o] = idx_desc[i]; cand_mask[o] = emask ? emask[e] : 0ull; cand_w[o] = emask ? ew[e] : idx_wfix[i]; cand_pep[o] = idx_pep[i];
 }
 
 // accepted window entries of the decoy store -> the first decoy slots of their spectrum (rank within the spectrum < n_per)
@@ -337,6 +345,8 @@ static void index_build_for(md_ctx* ctx, PeptideStore& P, MassIndex& X) {
   X.row_bytes = (uint64_t)total16 * 16;
   X.rows.need(X.row_bytes + 64);
   MD_LAUNCH(ctx, k_index_rows, blocks(n), 256, 0, X.pep.p, n, P.seq.p, P.seq_off.p, P.len.p, d_rowoff.p, X.rows.p, X.desc.p);
+  X.lcnt.need((size_t)n * std::max(1, ctx->mods.n_letters));
+  MD_LAUNCH(ctx, k_index_letter_counts, blocks(n), 256, 0, X.pep.p, n, P.counts.p, ctx->mods, X.lcnt.p);
   int64_t mm[2];
   MD_CUDA(cudaMemcpyAsync(&mm[0], X.key.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   MD_CUDA(cudaMemcpyAsync(&mm[1], X.key.p + (n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -373,7 +383,7 @@ void index_window_search_dev(md_ctx* ctx, const md_precursor* prec_dev, uint32_t
 // Window search + ModifiedPeptide filter of the n precursors in ws.prec against one index: leaves the flattened windows
 // (ws.rbegin, ws.flat_off), the per-entry results (t_flag, emask, ew) and the exclusive scan of the flags (t_pos, E+1
 // entries) in the workspace; returns the number of window entries E and the number of accepted ones.
-static uint64_t filter_windows(md_ctx* ctx, const MassIndex& X, const int16_t* counts, uint32_t n, uint32_t* total_out) {
+static uint64_t filter_windows(md_ctx* ctx, const MassIndex& X, uint32_t n, uint32_t* total_out, bool* lean_io = nullptr) {
   IdentifyWorkspace& W = ctx->ws;
   W.rbegin.need(n + 1); W.rend.need(n + 1); W.flat_off.need(n + 2);
   MD_LAUNCH(ctx, k_window_search, blocks((uint64_t)n * 32, 128), 128, 0, X.key.p, X.n, W.prec.p, n, W.rbegin.p, W.rend.p);
@@ -387,13 +397,19 @@ static uint64_t filter_windows(md_ctx* ctx, const MassIndex& X, const int16_t* c
   MD_LAUNCH(ctx, k_spectrum_limits, blocks((uint64_t)n * MD_ALPHABET_SIZE), 256, 0, W.prec.p, n, ctx->mods, d_K.p);
   DevBuf<uint32_t>& d_flag = W.t_flag; DevBuf<uint32_t>& d_pos = W.t_pos; DevBuf<int>& d_ovf = W.t_ovf;
   d_flag.need(E + 1); d_pos.need(E + 1); d_ovf.need(1);
-  W.emask.need(E + 1); W.ew.need(E + 1);
+  // lean: the caller takes (0, wfix) for an accepted entry when no variable modification can apply (md_try_variable then never
+  // changes an entry), and the per-entry mask / weight are neither written nor read
+  bool any_var = false;
+  for (int c = 0; c < MD_NCODES; c++) any_var |= ctx->mods.has_var[c] != 0;
+  const bool lean = lean_io && *lean_io && (ctx->mods.nvar == 0 || !any_var);
+  if (lean_io) *lean_io = lean;
+  if (!lean) { W.emask.need(E + 1); W.ew.need(E + 1); }
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   MD_CUDA(cudaMemsetAsync(d_flag.p + E, 0, sizeof(uint32_t), ctx->stream));
   ctx->mark("  alloc");
   if (E) {
     MD_LAUNCH(ctx, k_filter, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, W.prec.p, n, E, X.pep.p, X.wfix.p, X.varpos.p, X.desc.p, X.rows.p,
-              counts, d_K.p, ctx->mods, d_flag.p, W.emask.p, W.ew.p, d_ovf.p);
+              X.lcnt.p, d_K.p, ctx->mods, d_flag.p, lean ? nullptr : W.emask.p, lean ? nullptr : W.ew.p, d_ovf.p);
   }
   ctx->mark("  filter");
   cubx_exclusive_sum(ctx, d_flag.p, d_pos.p, E + 1);
@@ -466,11 +482,12 @@ uint64_t index_candidates_dev(md_ctx* ctx, uint32_t n) {
   if (!n) return 0;
   if (ctx->var_mode == MD_VARMOD_EXPANDED) return candidates_expanded_dev(ctx, n);
   uint32_t total = 0;
-  const uint64_t E = filter_windows(ctx, X, ctx->peps.counts.p, n, &total);
+  bool lean = true;
+  const uint64_t E = filter_windows(ctx, X, n, &total, &lean);
   W.cand_desc.need(total + 1); W.cand_mask.need(total + 1); W.cand_w.need(total + 1); W.cand_pep.need(total + 1);
   if (E) {
-    MD_LAUNCH(ctx, k_scatter_candidates, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, W.t_flag.p, W.t_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
-              W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
+    MD_LAUNCH(ctx, k_scatter_candidates, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, W.t_flag.p, W.t_pos.p, lean ? nullptr : W.emask.p, lean ? nullptr : W.ew.p,
+              X.pep.p, X.desc.p, X.wfix.p, W.cand_desc.p, W.cand_mask.p, W.cand_w.p, W.cand_pep.p);
   }
   MD_LAUNCH(ctx, k_cand_offsets, blocks(n + 1), 256, 0, W.flat_off.p, W.t_pos.p, n, W.cand_off.p);
   ctx->mark("  scatter");
@@ -483,7 +500,7 @@ void decoys_reuse_dev(md_ctx* ctx, uint32_t n, uint32_t n_per) {
   IdentifyWorkspace& W = ctx->ws; MassIndex& X = ctx->dindex;
   if (!n || !n_per || !X.ready || X.n == 0) return;
   uint32_t total = 0;
-  const uint64_t E = filter_windows(ctx, X, ctx->dstore.counts.p, n, &total);
+  const uint64_t E = filter_windows(ctx, X, n, &total);
   if (E) {
     MD_LAUNCH(ctx, k_scatter_stored_decoys, blocks(E), 256, 0, W.flat_off.p, W.rbegin.p, n, E, W.t_flag.p, W.t_pos.p, W.emask.p, W.ew.p, X.pep.p, X.desc.p,
               X.rows.p, ctx->dstore.hash.p, n_per, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p, W.dec_hash.p, W.dec_attempt.p);

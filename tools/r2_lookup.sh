@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu -k "c5 or c1" 2>&1 | tail -3
+for cfg in c5 c2 c1; do
+  timeout 600 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu-baseline --no-c4 > gpurun_out/b_$cfg.json 2> gpurun_out/b_$cfg.err; echo "$cfg rc=$?"
+  python -c "import json; d=json.load(open('gpurun_out/b_$cfg.json')); s=d['stage_ms_per_step']; print('$cfg', round(d['value']), 'spectra/s', round(d['ms_per_step'],2), 'ms', 'pairs/s', round(d['candidates_per_sec']), 'kscore', round(d['roofline']['launch_ms'],3), 'frac', round(d['roofline']['frac'],4), d['psm_crc'], s)"
+done
+MD_TRACE=1 timeout 600 python bench.py --config c5 --steps 2 --warmup 3 --no-cpu-baseline --no-c4 2>&1 >/dev/null | grep md_trace | tail -40
