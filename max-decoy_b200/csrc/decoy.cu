@@ -20,7 +20,8 @@ namespace {
 inline uint32_t blocks(uint64_t n, uint32_t bs = 256) { return (uint32_t)((n + bs - 1) / bs); }
 
 constexpr int kThreads = 128;          // lanes per CTA of the attempt kernels
-constexpr int kMaxRoundAttempts = 4096;  // per spectrum per round (bounds the selection kernel's shared memory)
+constexpr int kMaxRoundAttempts = 4096;  // per list entry (bounds the selection kernel's shared memory)
+constexpr int kRoundLevels = 4;          // list entries one spectrum can have in a round: its attempts in consecutive chunks, selected one after the other
 
 // letter tables in alphabet-index space, built once per call on the host
 constexpr uint32_t kGapTab = 512, kNnTab = 1024;
@@ -806,7 +807,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   }
   DevBuf<uint32_t>& d_list = W.t_list; DevBuf<uint32_t>& d_off = W.t_off; DevBuf<uint32_t>& d_base = W.t_base; DevBuf<uint32_t>& d_queue = W.t_queue;
   DevBuf<int>& d_ovf = W.t_ovf;
-  d_list.need(n + 1); d_off.need(n + 2); d_base.need(n + 1); d_queue.need(4); d_ovf.need(1);
+  d_list.need((size_t)n * kRoundLevels + 1); d_off.need((size_t)n * kRoundLevels + 2); d_base.need((size_t)n * kRoundLevels + 1); d_queue.need(4); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
   std::vector<uint32_t> list, off, base, blk;
   const double later_factor = getenv("MD_DECOY_LATER_PCT") ? std::max(100, atoi(getenv("MD_DECOY_LATER_PCT"))) / 100.0 : 1.05;   // head room of the later rounds (swept on C2: 100..180 %)
@@ -817,7 +818,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     // in attempt order, so asking for too many only wastes work; asking for too few costs another round, and a round
     // never takes less than one 100-try attempt (~0.3 ms) however small it is.  Round 0 asks for 1.1 n + 32; later rounds use
     // the spectrum's own yield with 5 % head room (their attempts are the expensive ones: hard spectra), and rounds too small to fill the GPU ask for up to 4x that.
-    std::vector<uint32_t> wants;
+    std::vector<uint32_t> wants, todo;
     uint64_t sum = 0;
     for (uint32_t si = 0; si < n; si++) {
       const uint32_t s = by_mass[si];
@@ -828,18 +829,34 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
         double yield = std::max(0.02, (double)count[s] / (double)used[s]);
         want = (uint32_t)((double)(n_per - count[s]) / yield * later_factor) + 48;
       }
-      want = std::min<uint32_t>({want, (uint32_t)kMaxRoundAttempts, cap[s] - used[s]});
-      list.push_back(s); wants.push_back(want); sum += want;
+      want = std::min<uint32_t>({want, (uint32_t)(kMaxRoundAttempts * kRoundLevels), cap[s] - used[s]});
+      todo.push_back(s); wants.push_back(want); sum += want;
     }
     const double boost = round == 0 || sum == 0 ? 1.0 : std::min(4.0, std::max(1.0, 300000.0 / (double)sum));
-    size_t kept = 0;
-    for (size_t i = 0; i < list.size(); i++) {
-      const uint32_t s = list[i];
-      const uint32_t want = std::min<uint32_t>({(uint32_t)((double)wants[i] * boost), (uint32_t)kMaxRoundAttempts, cap[s] - used[s]});
-      if (off.back() + (uint64_t)want > 0x7FFFFFFFull) break;  // the rest waits for the next round
-      base.push_back(used[s]); off.push_back(off.back() + want); kept++;
+    // A list entry is at most kMaxRoundAttempts attempts of one spectrum (the selection kernel's table); a spectrum that gets
+    // more this round -- the hard ones, which would otherwise need a round per 4096 attempts, each round as long as its slowest
+    // attempt however few attempts it has -- has several entries with consecutive attempt ordinals.  The list holds every
+    // spectrum's first entry, then the second entries, ...: k_decoy_select runs once per level, in that order.
+    struct Entry { uint32_t s, n, base; };
+    std::vector<Entry> level[kRoundLevels];
+    uint64_t planned = 0;
+    for (size_t i = 0; i < todo.size(); i++) {
+      const uint32_t s = todo[i];
+      const uint32_t want = std::min<uint32_t>({(uint32_t)((double)wants[i] * boost), (uint32_t)(kMaxRoundAttempts * kRoundLevels), cap[s] - used[s]});
+      if (planned + want > 0x7FFFFFFFull) break;  // the rest waits for the next round
+      planned += want;
+      for (uint32_t c = 0, done = 0; done < want; c++) {
+        const uint32_t chunk = std::min<uint32_t>(want - done, (uint32_t)kMaxRoundAttempts);
+        level[c].push_back(Entry{s, chunk, used[s] + done});
+        done += chunk;
+      }
     }
-    list.resize(kept);
+    uint32_t level_begin[kRoundLevels + 1];
+    for (int c = 0; c < kRoundLevels; c++) {
+      level_begin[c] = (uint32_t)list.size();
+      for (const Entry& e : level[c]) { list.push_back(e.s); base.push_back(e.base); off.push_back(off.back() + e.n); }
+    }
+    level_begin[kRoundLevels] = (uint32_t)list.size();
     if (list.empty()) break;
     const uint32_t n_list = (uint32_t)list.size(), total = off.back();
     W.att_rows.need((size_t)total * MD_DECOY_ROW + 64); W.att_len.need(total + 1); W.att_mask.need(total + 1); W.att_w.need(total + 1); W.att_hash.need(total + 1);
@@ -882,18 +899,20 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     }
     MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->mark("  attempts");
-    {
-      uint32_t need = 1, max_na = 1;                        // most (accepted + attempted) / attempted of one spectrum in this round
-      for (uint32_t i = 0; i < n_list; i++) { need = std::max(need, count[list[i]] + (off[i + 1] - off[i])); max_na = std::max(max_na, off[i + 1] - off[i]); }
+    for (int c = 0; c < kRoundLevels; c++) {
+      const uint32_t lb = level_begin[c], le = level_begin[c + 1];
+      if (lb == le) continue;
+      uint32_t need = 1, max_na = 1;                        // most (accepted + attempted) / attempted of one entry of this level
+      for (uint32_t i = lb; i < le; i++) { need = std::max(need, std::min(n_per, count[list[i]] + c * (uint32_t)kMaxRoundAttempts) + (off[i + 1] - off[i])); max_na = std::max(max_na, off[i + 1] - off[i]); }
       uint32_t slots = 1024; while ((uint64_t)slots * 3 < (uint64_t)need * 4) slots <<= 1;   // load factor <= 0.75 even if every attempt succeeded
       max_na = (max_na + 7u) & ~7u;
       const size_t smem = (size_t)slots * 12 + (size_t)max_na * 10;
       if (smem <= 220 * 1024) {
         MD_CUDA(cudaFuncSetAttribute(k_decoy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MD_LAUNCH(ctx, k_decoy_select, n_list, 256, smem, d_list.p, d_off.p, d_base.p, n_per, slots, max_na, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
-                  W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
+        MD_LAUNCH(ctx, k_decoy_select, le - lb, 256, smem, d_list.p + lb, d_off.p + lb, d_base.p + lb, n_per, slots, max_na, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p,
+                  W.dec_w.p, W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       } else {
-        MD_LAUNCH(ctx, k_decoy_select_n2, n_list, 256, 0, d_list.p, d_off.p, d_base.p, n_per, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
+        MD_LAUNCH(ctx, k_decoy_select_n2, le - lb, 256, 0, d_list.p + lb, d_off.p + lb, d_base.p + lb, n_per, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
                   W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       }
     }
