@@ -4,6 +4,7 @@
   python tools/ncu_summary.py launches gpurun_out/launches.csv            # per-kernel share of the step
   python tools/ncu_summary.py kernel   gpurun_out/prof_score.ncu-rep      # key metrics of one --set full capture
   python tools/ncu_summary.py source   gpurun_out/prof_score.ncu-rep [N]  # top-N source lines by stall samples
+  python tools/ncu_summary.py lanes    gpurun_out/prof_decoy.ncu-rep [N]  # top-N source lines by lost lane slots (divergence)
 """
 import collections
 import csv
@@ -102,11 +103,39 @@ def source(rep, top=40):
         print("%6.2f%% %5s %12d  %-28s %s" % (100 * v / tot, ln, ins, sts, text.strip()[:110]))
 
 
+def lanes(rep, top=40):
+    """CUDA source lines ranked by the lane slots they lose: warp instructions x (32 - active lanes)."""
+    out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    rows = list(csv.reader(io.StringIO(out)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
+    hdr = rows[hi]
+    ii, ti = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    data = []
+    for r in rows[hi + 1:]:
+        if len(r) <= ti or r[2] != "-":
+            continue
+        try:
+            ins, th = float(r[ii] or 0), float(r[ti] or 0)
+        except ValueError:
+            continue
+        if ins > 0:
+            data.append((ins, th, r[0], r[1]))
+    tot, tt = sum(d[0] for d in data), sum(d[1] for d in data)
+    lost = sum(d[0] * 32 - d[1] for d in data) or 1
+    print("# %s" % rows[1][1][:120])
+    print("# warp instructions %.4g, thread instructions %.4g: %.1f of 32 lanes active on average" % (tot, tt, tt / tot))
+    print("%6s %7s %6s %7s  %s" % ("line", "%insts", "lanes", "%lost", "source"))
+    for ins, th, ln, text in sorted(data, key=lambda d: -(d[0] * 32 - d[1]))[:top]:
+        print("%6s %6.1f%% %6.1f %6.1f%%  %s" % (ln, 100 * ins / tot, th / ins, 100 * (ins * 32 - th) / lost, text.strip()[:110]))
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "launches":
         launches(sys.argv[2])
     elif cmd == "kernel":
         kernel(sys.argv[2])
+    elif cmd == "lanes":
+        lanes(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
     else:
         source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
