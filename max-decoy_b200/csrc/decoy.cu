@@ -167,6 +167,19 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
   const uint32_t cnt = MO::popc(allpos);
   const uint32_t nmax = nvar < cnt ? nvar : cnt;
   const int32_t base = d - (int32_t)MO::popc(mask) * delta;
+  // quick reject (nearly always: the window is a few hundredths of a Da wide, delta is many Da): base + n * delta, n = 1..nmax,
+  // lies between its first and its last value, and unless the window meets that range only the failure's side effect is left
+  {
+    const int32_t e1 = base + delta, e2 = base + (int32_t)nmax * delta;
+    const int32_t lo_end = min(e1, e2), hi_end = max(e1, e2);
+    const bool maybe = hi_end >= dlo && (lo_end < dlo || (uint32_t)(lo_end - dlo) <= span);
+    if (!maybe) {
+      MaskT last = allpos;
+      for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;
+      d = e2; mask = last;
+      return false;
+    }
+  }
   MaskT first = 0, rest = allpos;
   for (uint32_t n = 1; n <= nmax; n++) {
     first |= rest & ((MaskT)0 - rest); rest &= rest - 1;
