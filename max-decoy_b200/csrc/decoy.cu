@@ -55,10 +55,22 @@ struct DecoyTables {
 struct TSeq {  // a lane's working sequence in shared memory (alphabet indices), transposed for conflict-free access
   uint8_t* base;
   __device__ __forceinline__ uint8_t& at(uint32_t i) const { return base[i * kThreads]; }
+  __device__ __forceinline__ uint32_t get(uint32_t i) const { return base[i * kThreads]; }
 };
-struct TSeqCode {  // view as residue codes for md_try_variable
-  TSeq s; const uint8_t* code_of_a;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return code_of_a[s.at(i)]; }
+// The same through an explicit 32-bit shared-memory address (k_decoy_random: every access is one IMAD + LDS/STS; through the
+// generic pointer the compiler rebuilt the shared window's address in front of each).  All accesses are volatile asm: ordered
+// among themselves, invisible to the compiler's alias analysis -- the array must not be touched through C++ pointers as well.
+struct SSeq {
+  uint32_t a;
+  __device__ __forceinline__ uint32_t get(uint32_t i) const {
+    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + i * kThreads)); return v;
+  }
+  __device__ __forceinline__ void set(uint32_t i, uint32_t v) const { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + i * kThreads), "r"(v)); }
+};
+template <class SeqT>
+struct SeqCode {  // view as residue codes for md_try_variable
+  SeqT s; const uint8_t* code_of_a;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return code_of_a[s.get(i)]; }
 };
 
 struct AttemptOut {
@@ -66,14 +78,15 @@ struct AttemptOut {
 };
 
 // write one finished attempt (len == 0 -> failure)
-__device__ void store_attempt(const AttemptOut& O, uint64_t slot, const TSeq& seq, uint32_t L, uint64_t mask, int64_t w, const DecoyTables& T,
+template <class SeqT>
+__device__ void store_attempt(const AttemptOut& O, uint64_t slot, const SeqT& seq, uint32_t L, uint64_t mask, int64_t w, const DecoyTables& T,
                               const PeptideView& PV) {
   if (L == 0) { O.len[slot] = 0; return; }
   uint8_t ascii[MD_MAX_PEPTIDE_LEN];
   uint64_t h = md_hash_init();
   uint8_t* row = O.rows + slot * MD_DECOY_ROW;
   for (uint32_t i = 0; i < L; i++) {
-    uint8_t code = T.code_of_a[seq.at(i)];
+    uint8_t code = T.code_of_a[seq.get(i)];
     uint8_t ch = md_letter_of(code);
     ascii[i] = ch; row[i] = code;
     h = md_hash_step(h, ch);
@@ -108,12 +121,13 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ att_
 #endif
 constexpr uint32_t kRing = MD_RNG_RING;   // words per lane (power of two)
 struct RngRing {
-  uint32_t* buf;                 // kRing words, stride kThreads
+  uint32_t addr;                 // shared-memory address of the lane's kRing words, stride kThreads (accessed through volatile asm only)
   uint32_t k0, k1, c0, c1, c2;   // key, next block, attempt, spectrum
   uint32_t head, count;
   __device__ __forceinline__ void start(uint64_t seed, uint32_t spectrum_id, uint32_t attempt) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); c0 = 0; c1 = attempt; c2 = spectrum_id; head = 0; count = 0;
   }
+  __device__ __forceinline__ void put(uint32_t t, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + (t & (kRing - 1)) * (kThreads * 4u)), "r"(v)); }
   __device__ __forceinline__ void produce() {   // one block -> 4 words into the ring (needs count <= kRing - 4)
     uint32_t a = c0, b = c1, c = c2, d = MD_TAG_RANDOM, x = k0, y = k1;
 #pragma unroll
@@ -125,12 +139,12 @@ struct RngRing {
       x += 0x9E3779B9u; y += 0xBB67AE85u;
     }
     const uint32_t t = head + count;
-    buf[((t + 0) & (kRing - 1)) * kThreads] = a; buf[((t + 1) & (kRing - 1)) * kThreads] = b; buf[((t + 2) & (kRing - 1)) * kThreads] = c; buf[((t + 3) & (kRing - 1)) * kThreads] = d;
+    put(t + 0, a); put(t + 1, b); put(t + 2, c); put(t + 3, d);
     c0++; count += 4;
   }
   __device__ __forceinline__ uint32_t next() {
     if (count == 0) produce();
-    const uint32_t v = buf[(head & (kRing - 1)) * kThreads];
+    uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + (head & (kRing - 1)) * (kThreads * 4u)));
     head++; count--;
     return v;
   }
@@ -151,11 +165,15 @@ template <> struct MaskOps<uint32_t> {
   static constexpr uint32_t bits = 32;
   static __device__ __forceinline__ uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }
   static __device__ __forceinline__ uint32_t popc(uint32_t v) { return (uint32_t)__popc(v); }
+  static __device__ __forceinline__ uint32_t ld(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+  static __device__ __forceinline__ void st(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
 };
 template <> struct MaskOps<uint64_t> {
   static constexpr uint32_t bits = 64;
   static __device__ __forceinline__ uint32_t ffs(uint64_t v) { return (uint32_t)__ffsll((long long)v); }
   static __device__ __forceinline__ uint32_t popc(uint64_t v) { return (uint32_t)__popcll(v); }
+  static __device__ __forceinline__ uint64_t ld(uint32_t addr) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr)); return v; }
+  static __device__ __forceinline__ void st(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v)); }
 };
 
 // try_variable_modifications (modified_peptide.rs:512-543) for one variable letter without a fixed modification, on the
@@ -192,6 +210,29 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
   return false;
 }
 
+// The kernel's small lookup tables live in ONE shared-memory block and are read through ld.shared with the table's offset as
+// an immediate: address = (block's shared address + index), one LEA + LDS per lookup.  (Declared as separate __shared__ arrays
+// the compiler rebuilt every table's window address -- S2R CgaCtaId, MOV, VIADD, LEA -- in front of every lookup, under the
+// 48-register cap that buys 10 CTAs per SM: about 20 of the ~290 instructions of a loop pass.)
+namespace tabs {
+constexpr uint32_t kAboveOfs = 40;                                  // offset of the d < 0 tables inside gap / gmask
+constexpr uint32_t mprime = 0;                                       // int32[32], by alphabet index
+constexpr uint32_t var = mprime + 32 * 4;                            // int32[32]
+constexpr uint32_t gap = var + 32 * 4;                               // uint32[kAboveOfs + 32]: d > 0 tables at [0..], d < 0 tables at [kAboveOfs..]
+constexpr uint32_t gmask = gap + (kAboveOfs + 32) * 4;               // uint32[kAboveOfs + 33]
+constexpr uint32_t thr2 = gmask + (kAboveOfs + 33) * 4;              // int32[32]
+constexpr uint32_t nnletter = thr2 + 32 * 4;                         // uint8[32]
+constexpr uint32_t gtab = nnletter + 32;                             // uint8[2 * kGapTab]
+constexpr uint32_t nntab = gtab + 2 * kGapTab;                       // uint8[kNnTab]
+constexpr uint32_t bytes = (nntab + kNnTab + 15u) & ~15u;
+}  // namespace tabs
+template <uint32_t OFF> __device__ __forceinline__ uint32_t tab_u32(uint32_t addr) {
+  uint32_t v; asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF)); return v;
+}
+template <uint32_t OFF> __device__ __forceinline__ uint32_t tab_u8(uint32_t addr) {
+  uint32_t v; asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF)); return v;
+}
+
 struct RandomArgs {
   const md_precursor* prec; const uint32_t* list; const uint32_t* att_off; const uint32_t* att_base;
   const uint32_t* att_blk;              // coarse index into att_off (find_entry_coarse)
@@ -219,30 +260,30 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
   constexpr uint32_t kBits = MO::bits;
   constexpr bool kNarrow = kBits < MD_MAX_PEPTIDE_LEN;
   constexpr uint32_t kRows = kNarrow ? kBits : MD_MAX_PEPTIDE_LEN;
-  constexpr uint32_t kAbove = 40;       // offset of the d < 0 tables
+  constexpr uint32_t kAbove = tabs::kAboveOfs;       // offset of the d < 0 tables
   __shared__ uint8_t sseq[kRows * kThreads];
   __shared__ uint32_t s_rng[kRing * kThreads];
   __shared__ MaskT s_pm[MD_ALPHABET_SIZE * kThreads];   // per lane and letter: the positions holding that letter
-  __shared__ int32_t s_sorted[32];      // (mass + fixed delta) ascending, padded with INT32_MAX
-  __shared__ int32_t s_mprime[32];      // by alphabet index
-  __shared__ int32_t s_var[32];
-  __shared__ uint8_t s_runmin[32];
-  __shared__ uint32_t s_gap[kAbove + 32], s_gmask[kAbove + 33];   // d > 0 tables at [0..], d < 0 tables at [kAbove..]
-  __shared__ uint8_t s_gtab[2 * kGapTab], s_nntab[kNnTab], s_nnletter[32];
-  __shared__ int32_t s_thr2[32];
-  for (uint32_t i = threadIdx.x; i < 2 * kGapTab; i += kThreads) s_gtab[i] = T.gap_tab[i / kGapTab][i % kGapTab];
-  for (uint32_t i = threadIdx.x; i < kNnTab; i += kThreads) s_nntab[i] = T.nn_tab[i];
-  if (threadIdx.x < 33) { s_gmask[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_gmask[kAbove + threadIdx.x] = T.maska_prefix[threadIdx.x]; }
-  if (threadIdx.x < 32) {
-    s_gap[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gap[kAbove + threadIdx.x] = T.gapa_sorted[threadIdx.x];
-    const int64_t sm = T.sorted_m[threadIdx.x];
-    s_sorted[threadIdx.x] = sm > 0x3FFFFFFF ? INT32_MAX : (int32_t)sm;
-    s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
-    s_runmin[threadIdx.x] = T.run_min_a[threadIdx.x];
-    s_thr2[threadIdx.x] = T.nn_thr2[threadIdx.x]; s_nnletter[threadIdx.x] = T.nn_letter[threadIdx.x];
+  __shared__ __align__(16) uint8_t s_tab[tabs::bytes];   // the lookup tables (namespace tabs)
+  {
+    int32_t* s_mprime = reinterpret_cast<int32_t*>(s_tab + tabs::mprime); int32_t* s_var = reinterpret_cast<int32_t*>(s_tab + tabs::var);
+    uint32_t* s_gap = reinterpret_cast<uint32_t*>(s_tab + tabs::gap); uint32_t* s_gmask = reinterpret_cast<uint32_t*>(s_tab + tabs::gmask);
+    int32_t* s_thr2 = reinterpret_cast<int32_t*>(s_tab + tabs::thr2);
+    uint8_t* s_nnletter = s_tab + tabs::nnletter; uint8_t* s_gtab = s_tab + tabs::gtab; uint8_t* s_nntab = s_tab + tabs::nntab;
+    for (uint32_t i = threadIdx.x; i < 2 * kGapTab; i += kThreads) s_gtab[i] = T.gap_tab[i / kGapTab][i % kGapTab];
+    for (uint32_t i = threadIdx.x; i < kNnTab; i += kThreads) s_nntab[i] = T.nn_tab[i];
+    if (threadIdx.x < 33) { s_gmask[threadIdx.x] = T.maskb_prefix[threadIdx.x]; s_gmask[kAbove + threadIdx.x] = T.maska_prefix[threadIdx.x]; }
+    if (threadIdx.x < 32) {
+      s_gap[threadIdx.x] = T.gapb_sorted[threadIdx.x]; s_gap[kAbove + threadIdx.x] = T.gapa_sorted[threadIdx.x];
+      s_mprime[threadIdx.x] = (int32_t)T.mprime[threadIdx.x]; s_var[threadIdx.x] = (int32_t)T.var_a[threadIdx.x];
+      s_thr2[threadIdx.x] = T.nn_thr2[threadIdx.x]; s_nnletter[threadIdx.x] = T.nn_letter[threadIdx.x];
+    }
   }
   __syncthreads();
-  TSeq seq{sseq + threadIdx.x};
+  uint32_t tb;    // the block's shared-memory address (made opaque: it is to stay in a register, not to be rebuilt per lookup)
+  asm volatile("mov.u32 %0, %1;" : "=r"(tb) : "r"((uint32_t)__cvta_generic_to_shared(s_tab)) : "memory");   // (the tables' stores above stay in front of it)
+  SSeq seq;
+  asm volatile("mov.u32 %0, %1;" : "=r"(seq.a) : "r"((uint32_t)__cvta_generic_to_shared(sseq) + threadIdx.x));
   const uint32_t gap_shift = T.gap_shift, nn_shift = T.nn_shift;
   const int32_t nn_lo = T.nn_lo, nn_hi = T.nn_hi;
   const int va = VMODE == 1 ? md_alpha_of_code((uint32_t)M.var_simple_code) : -1;
@@ -252,14 +293,18 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
   bool busy = false, drained = false;
   uint32_t pending = 0;           // 1 = hit, 2 = gave up: the result is written when the free lanes refill together
   uint32_t present = 0;           // letters in the sequence
-  MaskT* pm = s_pm + threadIdx.x;
-  auto add_letter = [&](uint32_t a, uint32_t i) { pm[a * kThreads] |= (MaskT)1 << i; present |= 1u << a; };
-  auto del_letter = [&](uint32_t a, uint32_t i) { const MaskT v = pm[a * kThreads] & ~((MaskT)1 << i); pm[a * kThreads] = v; if (v == 0) present &= ~(1u << a); };
+  // (the position masks, like the sequence and the ring, through explicit shared addresses and volatile asm only)
+  constexpr uint32_t kPmStride = kThreads * (uint32_t)sizeof(MaskT);
+  uint32_t pm_a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(pm_a) : "r"((uint32_t)__cvta_generic_to_shared(s_pm) + (uint32_t)sizeof(MaskT) * threadIdx.x));
+  auto add_letter = [&](uint32_t a, uint32_t i) { const uint32_t ad = pm_a + a * kPmStride; MO::st(ad, MO::ld(ad) | (MaskT)1 << i); present |= 1u << a; };
+  auto del_letter = [&](uint32_t a, uint32_t i) { const uint32_t ad = pm_a + a * kPmStride; const MaskT v = MO::ld(ad) & ~((MaskT)1 << i); MO::st(ad, v); if (v == 0) present &= ~(1u << a); };
   uint32_t wi = 0, L = 0, pos = 0, tries = 0, span = 0, flags = 0;
   int64_t P = 0;
   int32_t d = 0, dlo = 0;
   MaskT mask = 0, vpos = 0, lmask = 0;
-  RngRing rng; rng.buf = s_rng + threadIdx.x; rng.start(A.seed, 0, 0);
+  RngRing rng; rng.start(A.seed, 0, 0);
+  asm volatile("mov.u32 %0, %1;" : "=r"(rng.addr) : "r"((uint32_t)__cvta_generic_to_shared(s_rng) + 4u * threadIdx.x));
 
   uint32_t rng_timer = 1;
   for (;;) {
@@ -281,16 +326,16 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
           // grow (decoy_generator.rs:142-159): uniform letters until the weight exceeds the upper limit
           int64_t w = MD_WATER_UDA;
           L = 0; mask = 0; vpos = 0; present = 0; bool dead = false;
-          for (int a = 0; a < MD_ALPHABET_SIZE; a++) pm[a * kThreads] = 0;
+          for (int a = 0; a < MD_ALPHABET_SIZE; a++) MO::st(pm_a + a * kPmStride, (MaskT)0);
           for (;;) {
             const uint32_t a = rng.below(MD_ALPHABET_SIZE);
             if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }  // > 60 residues: VARCHAR(60) would reject it
             if (!kNarrow || L < kBits) {
               if (VMODE == 1 && (int)a == va) vpos |= (MaskT)1 << L;
-              add_letter(a, L); seq.at(L) = (uint8_t)a;
+              add_letter(a, L); seq.set(L, a);
             }
             L++;
-            w += s_mprime[a];
+            w += (int32_t)tab_u32<tabs::mprime>(tb + 4u * a);
             if (w > pr.hi) break;
           }
           if (kNarrow && !dead && L > kBits) {
@@ -320,10 +365,10 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
       {
         const uint32_t ad = (uint32_t)(d < 0 ? -d : d), x = 2u * ad;
         const uint32_t gofs = d > 0 ? 0u : kAbove;
-        const uint32_t* g = s_gap + gofs;
-        uint32_t k = s_gtab[(d > 0 ? 0u : kGapTab) + min(x >> gap_shift, kGapTab - 1u)];
-        for (uint32_t gk = g[k]; gk < x; gk = g[k]) k++;                 // number of gaps below x (padding: 0xFFFFFFFF)
-        fm = s_gmask[gofs + k];                                          // d == 0: x == 0, k == 0, empty prefix
+        const uint32_t k0 = tab_u8<tabs::gtab>(tb + (d > 0 ? 0u : kGapTab) + min(x >> gap_shift, kGapTab - 1u));
+        uint32_t ga = tb + 4u * (gofs + k0);                             // walks gap[gofs + k] and, at the same index, gmask
+        for (uint32_t gk = tab_u32<tabs::gap>(ga); gk < x; gk = tab_u32<tabs::gap>(ga)) ga += 4u;   // number of gaps below x (padding: 0xFFFFFFFF)
+        fm = tab_u32<tabs::gmask>(ga);                                   // d == 0: x == 0, k == 0, empty prefix
       }
       // ---- ... and the per-letter position masks give the first position of the pass that can improve: OR of the masks of
       //      the qualifying letters -- or, when most letters qualify (right after a kick), the complement of the OR over
@@ -333,15 +378,12 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
         const uint32_t m0 = fm & present, n0 = present & ~fm;
         const bool inv = __popc(n0) < __popc(m0);
         MaskT acc = 0;
-#ifdef MD_PM_UNROLL2
-        for (uint32_t m = inv ? n0 : m0; m;) {
-          MaskT v = pm[(__ffs(m) - 1) * kThreads]; m &= m - 1;
-          if (m) { v |= pm[(__ffs(m) - 1) * kThreads]; m &= m - 1; }
-          acc |= v;
+        for (uint32_t m = inv ? n0 : m0; m;) {     // from the top bit: one FLO (bfind) per letter instead of BREV + FLO for __ffs
+          uint32_t h;
+          asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(m));
+          acc |= MO::ld(pm_a + h * kPmStride);
+          m &= ~(1u << h);
         }
-#else
-        for (uint32_t m = inv ? n0 : m0; m; m &= m - 1) acc |= pm[(__ffs(m) - 1) * kThreads];
-#endif
         cand = inv ? ~acc & lmask : acc;
         cand = pos < L ? cand & (~(MaskT)0 << pos) : (MaskT)0;           // pos == L: the pass ended with a substitution
       }
@@ -352,18 +394,19 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
       uint32_t kick_lo = 0;
       if (sub) p = MO::ffs(cand) - 1u;
       else { const uint64_t rl = (uint64_t)rng.next() * L; p = (uint32_t)(rl >> 32); kick_lo = (uint32_t)rl; }
-      const uint32_t old = seq.at(p);
+      const uint32_t old = seq.get(p);
+      const int32_t m_old = (int32_t)tab_u32<tabs::mprime>(tb + 4u * old);
       uint32_t c;
       if (sub) {
         // best single substitution = letter whose (mass+fixed) is closest to mprime[old] - d; strict improvement,
         // ties by alphabet order (the reference follows HashMap order there)
-        const int32_t target = min(max(s_mprime[old] - d, nn_lo), nn_hi);
+        const int32_t target = min(max(m_old - d, nn_lo), nn_hi);
         const int32_t t2 = 2 * target;
-        uint32_t k = s_nntab[(uint32_t)(target - nn_lo) >> nn_shift];
-        for (int32_t th = s_thr2[k]; t2 > th; th = s_thr2[k]) k++;       // nearest distinct mass (padding: INT32_MAX)
-        c = s_nnletter[k];
+        uint32_t k = tab_u8<tabs::nntab>(tb + ((uint32_t)(target - nn_lo) >> nn_shift));
+        for (int32_t th = (int32_t)tab_u32<tabs::thr2>(tb + 4u * k); t2 > th; th = (int32_t)tab_u32<tabs::thr2>(tb + 4u * k)) k++;   // nearest distinct mass (padding: INT32_MAX)
+        c = tab_u8<tabs::nnletter>(tb + k);
 #ifdef MD_DECOY_CHECK   // (debug builds) the letter filter and the nearest-mass search must agree
-        const int32_t nd = d + s_mprime[c] - s_mprime[old];
+        const int32_t nd = d + (int32_t)tab_u32<tabs::mprime>(tb + 4u * c) - m_old;
         if (!((uint32_t)(nd < 0 ? -nd : nd) < (uint32_t)(d < 0 ? -d : d) && c != old)) { flags |= 4u; c = old; }
 #endif
       } else {
@@ -372,9 +415,9 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
       // ---- put letter c at position p: remove_modification_at + swap + fixed modification of the new letter (:470-482)
       {
         const MaskT bit = (MaskT)1 << p;
-        if (VMODE != 0) { if (mask & bit) { d -= s_var[old]; mask &= ~bit; } }
-        d += s_mprime[c] - s_mprime[old];
-        seq.at(p) = (uint8_t)c; del_letter(old, p); add_letter(c, p);
+        if (VMODE != 0) { if (mask & bit) { d -= (int32_t)tab_u32<tabs::var>(tb + 4u * old); mask &= ~bit; } }
+        d += (int32_t)tab_u32<tabs::mprime>(tb + 4u * c) - m_old;
+        seq.set(p, c); del_letter(old, p); add_letter(c, p);
         if (VMODE == 1) vpos = (vpos & ~bit) | ((int)c == va ? bit : (MaskT)0);
       }
       bool hit = false;
@@ -384,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
           if (!hit && vpos) hit = try_variable_simple_d<MaskT>(M.nvar, vdelta, vpos, d, mask, dlo, span);
         } else if (VMODE == 2) {
           if (!hit) {
-            TSeqCode sc{seq, T.code_of_a};
+            SeqCode<SSeq> sc{seq, T.code_of_a};
             int64_t w = P + d; uint64_t m64 = (uint64_t)mask;
             const int64_t lo = P + dlo;
             if (md_try_variable(M, sc, L, w, m64, lo, lo + (int64_t)span, A.overflow)) hit = true;
