@@ -247,14 +247,16 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
     M.nvar = max_var; M.var_simple_code = -1;
     for (uint32_t i = 0; i < n; i++) {
       uint8_t pos = (uint8_t)toupper(mods[i].position);
-      MD_REQUIRE(pos != 'N' && pos != 'C', MD_ERR_UNSUPPORTED, "terminal modifications (position N/C) are outside the hot path");
-      MD_REQUIRE(pos == 'A', MD_ERR_INVALID, "modification position must be A, N or C");
+      MD_REQUIRE(pos == 'A' || pos == 'N' || pos == 'C', MD_ERR_INVALID, "modification position must be A, N or C");
+      const uint8_t pcode = pos == 'A' ? MD_POS_A : pos == 'N' ? MD_POS_N : MD_POS_C;
       uint8_t aa = (uint8_t)toupper(mods[i].amino_acid);
       uint32_t code = md_code_of(aa);
       MD_REQUIRE(md_alpha_of_code(code) >= 0, MD_ERR_INVALID, "modification on a letter without a <x>_count column (alphabet " MD_ALPHABET ")");
-      if (mods[i].is_fix) { M.has_fix[code] = 1; M.fix[code] = mods[i].mono_mass; }
-      else { M.has_var[code] = 1; M.var[code] = mods[i].mono_mass; }
+      if (mods[i].is_fix) { M.has_fix[code] = 1; M.fix[code] = mods[i].mono_mass; M.fix_pos[code] = pcode; }
+      else { M.has_var[code] = 1; M.var[code] = mods[i].mono_mass; M.var_pos[code] = pcode; }
     }
+    for (int c = 0; c < MD_NCODES; c++)
+      if ((M.has_fix[c] && M.fix_pos[c] != MD_POS_A) || (M.has_var[c] && M.var_pos[c] != MD_POS_A)) M.has_terminal = 1;
     // sorted modifiable letters (identification.rs:173-178): ascending by character
     int n_var_letters = 0, var_code = -1;
     for (int ch = 'A'; ch <= 'Z'; ch++) {
@@ -268,7 +270,7 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
       M.letter_alpha[k] = md_alpha_of_code(code); M.letter_delta[k] = merged; M.letter_mass[k] = M.mass[code] + merged;
       if (M.has_var[code]) { n_var_letters++; var_code = (int)code; }
     }
-    if (n_var_letters == 1 && !M.has_fix[var_code]) M.var_simple_code = var_code;
+    if (n_var_letters == 1 && !M.has_fix[var_code] && !M.has_terminal) M.var_simple_code = var_code;
     ctx->mods = M; ctx->mods_set = true; ctx->index.ready = false; ctx->dindex.ready = false;
   });
 }

@@ -142,7 +142,28 @@ struct ModTables {
   uint32_t nvar;                           // -n
   // fast path of try_variable_modifications: exactly one variable letter, without a fixed mod
   int32_t var_simple_code;                 // code of that letter, or -1
+  // position of the letter's fixed / variable modification (modification.rs:24-33): MD_POS_A anywhere, MD_POS_N / MD_POS_C
+  // terminus.  A terminal modification sits on the first / last residue only, and only when that residue is its letter
+  // (add_modification_at, modified_peptide.rs:421-447; set_variable_modification_at, :339-367).
+  uint8_t fix_pos[MD_NCODES];
+  uint8_t var_pos[MD_NCODES];
+  uint32_t has_terminal;                   // any modification with position N or C
 };
+#define MD_POS_A 0
+#define MD_POS_N 1
+#define MD_POS_C 2
+__host__ __device__ inline bool md_pos_at(uint32_t pos, uint32_t i, uint32_t L) {
+  return pos == MD_POS_A || (pos == MD_POS_N && i == 0) || (pos == MD_POS_C && i + 1 == L);
+}
+// does residue i of a sequence of L residues carry its letter's fixed modification?
+__host__ __device__ inline bool md_fix_applies(const ModTables& M, uint32_t code, uint32_t i, uint32_t L) {
+  return M.has_fix[code] && md_pos_at(M.fix_pos[code], i, L);
+}
+// can it take its letter's variable modification?  (the slot -- side chain, N-terminus, C-terminus -- must exist at this
+// position and must not hold the fixed modification: AlreadyFixModificationInPlace, modified_peptide.rs:311,327,350)
+__host__ __device__ inline bool md_can_var(const ModTables& M, uint32_t code, uint32_t i, uint32_t L) {
+  return M.has_var[code] && md_pos_at(M.var_pos[code], i, L) && !(M.has_fix[code] && M.fix_pos[code] == M.var_pos[code]);
+}
 
 // Philox4x32-10 (must equal the oracle's)
 struct Philox4 {

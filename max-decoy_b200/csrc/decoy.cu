@@ -448,13 +448,75 @@ __global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, c
   if (flags) atomicMax(A.overflow, (flags & 4u) ? 3 : 2);
 }
 
+// Terminal modifications (position N / C): the attempt restated literally, one lane per attempt -- the weight of a residue
+// depends on where it stands (md_fix_applies), so neither the letter filter nor the per-letter position masks of
+// k_decoy_random hold.  As in the reference the repair loop rates a substitution with the position-blind substitution map
+// (get_one_amino_acid_substitute_map, decoy_generator.rs:301-324: every letter with its fixed delta) and then applies it
+// with add_modification_at's position rules (modified_peptide.rs:421-447).  Same RNG stream, same output rows as
+// k_decoy_random; a correctness path, not a tuned one.
+__global__ void __launch_bounds__(kThreads) k_decoy_random_terminal(const RandomArgs A, const __grid_constant__ ModTables M, const __grid_constant__ DecoyTables T,
+                                                                    AttemptOut O, PeptideView PV) {
+  __shared__ uint8_t sseq[MD_MAX_PEPTIDE_LEN * kThreads];
+  TSeq seq{sseq + threadIdx.x};
+  auto fixd = [&](uint32_t a, uint32_t i, uint32_t L) -> int64_t { const uint32_t c = T.code_of_a[a]; return md_fix_applies(M, c, i, L) ? M.fix[c] : 0; };
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < A.total; wi += gridDim.x * blockDim.x) {
+    const uint32_t li = find_entry(A.att_off, A.n_list, wi);
+    const md_precursor pr = A.prec[A.list[li]];
+    Philox4 rng; rng.init(A.seed, pr.spectrum_id, A.att_base[li] + (wi - A.att_off[li]), MD_TAG_RANDOM);
+    // grow (decoy_generator.rs:142-159; push_modification, modified_peptide.rs:182-208: the residue that was last loses its
+    // C-terminus modification, the new one takes its letter's fixed modification where its position allows)
+    int64_t w = MD_WATER_UDA;
+    uint32_t L = 0; bool dead = false;
+    for (;;) {
+      const uint32_t a = rng.below(MD_ALPHABET_SIZE);
+      if (L >= MD_MAX_PEPTIDE_LEN) { dead = true; break; }
+      if (L > 0) { const uint32_t pc = T.code_of_a[seq.get(L - 1)]; if (M.has_fix[pc] && M.fix_pos[pc] == MD_POS_C) w -= M.fix[pc]; }
+      seq.at(L) = (uint8_t)a; L++;
+      w += M.mass[T.code_of_a[a]] + fixd(a, L - 1, L);
+      if (w > pr.hi) break;
+    }
+    uint64_t mask = 0;
+    bool hit = false;
+    // put letter c at position p: remove_modification_at + swap + add_modification_at (:470-482, :493-505)
+    auto replace_at = [&](uint32_t p, uint32_t c) {
+      const uint32_t old = seq.get(p);
+      w -= M.mass[T.code_of_a[old]] + fixd(old, p, L);
+      if ((mask >> p) & 1) { w -= M.var[T.code_of_a[old]]; mask &= ~(1ull << p); }
+      seq.at(p) = (uint8_t)c;
+      w += M.mass[T.code_of_a[c]] + fixd(c, p, L);
+    };
+    for (uint32_t t = 0; t < 100 && !dead && !hit; t++) {                    // 'tries (:453)
+      for (uint32_t i = 0; i < L && !hit; i++) {                             // 'sequence (:454)
+        const uint32_t cur = seq.get(i);
+        int64_t best = pr.mass - w; if (best < 0) best = -best;
+        uint32_t bestc = cur;
+        for (uint32_t c = 0; c < MD_ALPHABET_SIZE; c++) {                    // 'swaps (:459-468), alphabet order
+          if (c == cur) continue;
+          int64_t d = pr.mass - (w + T.mprime[c] - T.mprime[cur]); if (d < 0) d = -d;
+          if (d < best) { best = d; bestc = c; }
+        }
+        if (bestc != cur) {
+          replace_at(i, bestc);
+          if (md_in_window(w, pr.lo, pr.hi)) hit = true;                     // :483
+          else { SeqCode<TSeq> sc{seq, T.code_of_a}; if (md_try_variable(M, sc, L, w, mask, pr.lo, pr.hi, A.overflow)) hit = true; }   // :484
+        }
+      }
+      if (hit) break;
+      const uint64_t rl = (uint64_t)rng.next() * L;                           // the kick (:489-505), one word as in k_decoy_random
+      replace_at((uint32_t)(rl >> 32), (uint32_t)(((uint64_t)(uint32_t)rl * MD_ALPHABET_SIZE) >> 32));
+    }
+    store_attempt(O, wi, seq, hit ? L : 0, mask, w, T, PV);
+  }
+}
+
 // vary_targets (decoy_generator.rs:265-296), counter-based: attempt a shuffles target (a mod T) of the spectrum
 __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* __restrict__ prec, const uint32_t* __restrict__ list,
                                                             const uint32_t* __restrict__ att_off, const uint32_t* __restrict__ att_base, uint32_t n_list,
                                                             uint32_t total, uint64_t seed, const __grid_constant__ DecoyTables T,
                                                             const uint64_t* __restrict__ cand_off, const uint64_t* __restrict__ cand_desc,
                                                             const uint64_t* __restrict__ cand_mask, const int64_t* __restrict__ cand_w,
-                                                            const uint8_t* __restrict__ idx_rows, AttemptOut O, PeptideView PV) {
+                                                            const uint8_t* __restrict__ idx_rows, AttemptOut O, PeptideView PV,
+                                                            const __grid_constant__ ModTables M) {
   __shared__ uint8_t sseq[MD_MAX_PEPTIDE_LEN * kThreads];
   TSeq seq{sseq + threadIdx.x};
   const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -476,7 +538,7 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
     const int a = md_alpha_of_code(row[__ffsll((long long)m) - 1]);
     if (a >= 0) wfix -= T.var_a[a];
   }
-  if (!md_in_window(wfix, pr.lo, pr.hi)) { O.len[wi] = 0; return; }
+  if (!M.has_terminal && !md_in_window(wfix, pr.lo, pr.hi)) { O.len[wi] = 0; return; }   // (a permutation keeps this weight)
   bool ok = true;
   for (uint32_t i = 0; i < L; i++) {
     int a = md_alpha_of_code(row[i]);
@@ -488,6 +550,11 @@ __global__ void __launch_bounds__(kThreads) k_decoy_permute(const md_precursor* 
   for (uint32_t i = L; i > 1; i--) {
     uint32_t j = rng.below(i);
     uint8_t a = seq.at(i - 1); seq.at(i - 1) = seq.at(j); seq.at(j) = a;
+  }
+  if (M.has_terminal) {   // terminal modifications: the weight depends on which residues end up first and last (from_string, modified_peptide.rs:118-139)
+    wfix = MD_WATER_UDA;
+    for (uint32_t i = 0; i < L; i++) { const uint32_t cc = T.code_of_a[seq.get(i)]; wfix += M.mass[cc] + (md_fix_applies(M, cc, i, L) ? M.fix[cc] : 0); }
+    if (!md_in_window(wfix, pr.lo, pr.hi)) { O.len[wi] = 0; return; }
   }
   store_attempt(O, wi, seq, L, 0, wfix, T, PV);
 }
@@ -806,7 +873,10 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   W.dec_hash.need(slots + 1); W.dec_attempt.need(slots + 1); W.dec_count.need(n + 1);
   MD_CUDA(cudaMemsetAsync(W.dec_count.p, 0, (n + 1) * sizeof(uint32_t), ctx->stream));
   if (!n || !n_per) return;
-  if (mode == MD_DECOY_EXHAUSTIVE) { decoys_exhaustive_dev(ctx, n, n_per); return; }
+  if (mode == MD_DECOY_EXHAUSTIVE) {
+    MD_REQUIRE(!ctx->mods.has_terminal, MD_ERR_UNSUPPORTED, "exhaustive decoys enumerate compositions: not defined with terminal modifications (the weight depends on the order)");
+    decoys_exhaustive_dev(ctx, n, n_per); return;
+  }
   MD_REQUIRE(mode == MD_DECOY_REFERENCE_RANDOM || mode == MD_DECOY_PERMUTE_TARGET, MD_ERR_INVALID, "unknown decoy mode");
 
   const DecoyTables T = make_tables(ctx->mods);
@@ -940,7 +1010,10 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       }
       RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total; RA.att_blk = W.t_blk.p;
       RA.seed = seed; RA.overflow = d_ovf.p;
-      if (!wide_only) {
+      if (ctx->mods.has_terminal) {
+        RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = nullptr; RA.spill_n = nullptr;
+        MD_LAUNCH(ctx, k_decoy_random_terminal, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * 8u), kThreads, 0, RA, ctx->mods, T, O, PV);
+      } else if (!wide_only) {
         RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = W.t_spill.p; RA.spill_n = d_queue.p + 1;
         launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, O, PV);
         RA.queue = d_queue.p + 2; RA.remap = W.t_spill.p; RA.remap_n = d_queue.p + 1; RA.spill = nullptr; RA.spill_n = nullptr;
@@ -951,7 +1024,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       }
     } else {
       MD_LAUNCH(ctx, k_decoy_permute, blocks(total, kThreads), kThreads, 0, W.prec.p, d_list.p, d_off.p, d_base.p, n_list, total, seed, T, W.cand_off.p,
-                W.cand_desc.p, W.cand_mask.p, W.cand_w.p, ctx->index.rows.p, O, PV);
+                W.cand_desc.p, W.cand_mask.p, W.cand_w.p, ctx->index.rows.p, O, PV, ctx->mods);
     }
     MD_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->mark("  attempts");

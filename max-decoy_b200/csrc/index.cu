@@ -37,7 +37,7 @@ __global__ void k_index_entries(const uint32_t* __restrict__ pep, uint32_t n, co
   uint64_t vp = 0;
   for (uint32_t k = 0; k < L; k++) {
     uint32_t c = md_code_of(s[k]);
-    if (M.has_fix[c]) w += M.fix[c];
+    if (md_fix_applies(M, c, k, L)) w += M.fix[c];
     if (M.has_var[c]) vp |= 1ULL << k;
   }
   wfix[i] = w; varpos[i] = vp;
@@ -365,6 +365,7 @@ static void index_build_for(md_ctx* ctx, PeptideStore& P, MassIndex& X) {
 void index_build_run(md_ctx* ctx) {
   MD_REQUIRE(ctx->peps.ready, MD_ERR_STATE, "md_index_build: md_digest first");
   MD_REQUIRE(ctx->mods_set, MD_ERR_STATE, "md_index_build: md_set_modifications first");
+  MD_REQUIRE(!(ctx->var_mode == MD_VARMOD_EXPANDED && ctx->mods.has_terminal), MD_ERR_UNSUPPORTED, "expanded variable-modification mode is defined for position-A modifications only");
   index_build_for(ctx, ctx->peps, ctx->index);
   index_build_store(ctx);
 }

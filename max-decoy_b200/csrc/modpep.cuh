@@ -1,9 +1,10 @@
 // modpep.cuh -- device restatement of the ModifiedPeptide mass-window logic
 // (models/peptides/modified_peptide.rs:157-159 hits_mass_tolerance, :369-401 remove_all_variable_modifications,
 //  :512-543 try_variable_modifications; utility/combinations/n_choose_k.rs:12-49 subset order).
-// Only position-'A' (Anywhere) modifications are on the hot path, so a working peptide is
-// (sequence, weight, mask of residues carrying their variable modification); a residue whose
-// letter has a fixed modification always carries it and never a variable one (:355, :532).
+// A working peptide is (sequence, weight, mask of residues carrying their variable modification).  Which residues carry
+// their letter's fixed modification, and which can take the variable one, follows from letter and position alone
+// (md_fix_applies / md_can_var in common.cuh: anywhere, or the matching terminus; a slot that holds the fixed
+// modification never takes the variable one, :355, :532).
 #pragma once
 #include "common.cuh"
 
@@ -61,7 +62,7 @@ __device__ bool md_try_variable(const ModTables& M, Seq seq, uint32_t len, int64
   uint64_t allpos = 0, eff = 0;
   for (uint32_t i = 0; i < len; i++) {
     uint32_t c = seq(i);
-    if (M.has_var[c]) { allpos |= 1ULL << i; if (!M.has_fix[c]) eff |= 1ULL << i; }
+    if (M.has_var[c]) { allpos |= 1ULL << i; if (md_can_var(M, c, i, len)) eff |= 1ULL << i; }
   }
   const uint32_t d = (uint32_t)__popcll(allpos);
   if (d == 0) return false;

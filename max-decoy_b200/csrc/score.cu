@@ -180,6 +180,11 @@ struct ScoreConst {
   uint32_t q2p, r2p;          // 2*proton
   uint32_t tq[32], tr[32];    // per residue code: (mass + fixed delta) = q*w + r
   uint32_t vq[32], vr[32];    // per residue code: (mass + fixed + variable delta)
+  // per residue code: its letter's fixed N-terminus modification as floor-split (q, r) (q may be "negative", i.e. wrapped), added
+  // to the b-ion prefix when the code is the first residue -- k_score only; with such a modification nothing runs through
+  // k_score_pipe.  (C-terminus modifications need nothing here: no b ion holds the last residue, and the y ions come from
+  // the candidate's modified weight; a variable terminal modification is a mask bit on the end residue like any other.)
+  uint32_t nq[32], nr[32];
   uint32_t max_frag_charge;
   uint32_t top_k, n_per;
 };
@@ -258,7 +263,7 @@ struct CandRef { const uint4* row; const uint4* row_hi; uint32_t len; uint64_t m
 // unsigned min.  The last residue is never a prefix: at position len-1 kStop is added to QB, which throws every later
 // b and y bin of every charge out of the table -- no per-residue length predicate.  The loop runs in 4-residue words up
 // to the longest candidate of the warp.
-template <int NCH, bool HASVAR, bool MAPG>
+template <int NCH, bool HASVAR, bool MAPG, bool TERM = false>
 __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen, const TableView& V, const ScoreConst& C, const LaneTab& L) {
   const uint32_t w = C.w;
   const uint32_t K2 = C.qp - 1u, K3 = C.q2p - 1u;
@@ -284,6 +289,11 @@ __device__ __forceinline__ int64_t score_one(const CandRef& cr, uint32_t maxlen,
   const uint4 v0 = __ldg(cr.row);
   uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
   if (nword > 4) v1 = __ldg(cr.row + 1);
+  if (TERM) {   // a fixed N-terminus modification of the first residue's letter is part of every b ion
+    const uint32_t code0 = v0.x & 31u;
+    QB += C.nq[code0]; R1 += C.nr[code0];
+    if (R1 >= w) { R1 -= w; QB++; }
+  }
   for (uint32_t c = 0; c * 4 < nword; c++) {
     const uint4 v = c == 0 ? v0 : (c == 1 ? v1 : __ldg(cr.row_hi + (c - 2)));
     const uint32_t words[4] = {v.x, v.y, v.z, v.w};
@@ -389,7 +399,7 @@ __device__ __forceinline__ void score_units(const ScoreArgs& A, const ScoreConst
       cr = cand_ref<HASVAR>(A, s, c0 + v, nt, t0c, C.n_per);
     }
     const uint32_t maxlen = __reduce_max_sync(0xffffffffu, cr.len);
-    const int64_t part = score_one<NCH, HASVAR, MAPG>(cr, maxlen, V, C, L);
+    const int64_t part = score_one<NCH, HASVAR, MAPG, true>(cr, maxlen, V, C, L);
     if (slot < cn) s_score[v] += part;
   }
 }
@@ -1356,6 +1366,13 @@ void split_qr(int64_t m, uint32_t w, uint32_t* q, uint32_t* r) {
   *q = (uint32_t)(m / w); *r = (uint32_t)(m % w);
 }
 
+// k_score_pipe scores with position-independent residue masses; a fixed N-terminus modification needs k_score (ScoreConst::nq)
+bool classic_only(const md_ctx* ctx) {
+  if (getenv("MD_SCORE_CLASSIC") != nullptr) return true;
+  for (int c = 0; c < MD_NCODES; c++) if (ctx->mods.has_fix[c] && ctx->mods.fix_pos[c] == MD_POS_N) return true;
+  return false;
+}
+
 }  // namespace
 
 void precursors_dev(md_ctx* ctx, const SpectraDev& S, const md_search_params& p, uint32_t id_base) {
@@ -1375,7 +1392,7 @@ void score_prepare_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const
   W.pk_bin.need(n_peaks + 1); W.pk_yq.need(n_peaks + 1); W.pk_count.need(n + 1); W.pk_hbin.need(n + 1);
   DevBuf<int>& d_flag = W.t_unsorted; d_flag.need(4);
   W.stat64.need(32);
-  const bool tables = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  const bool tables = p.top_k <= kFastTopK && !classic_only(ctx);
   if (tables) { W.tab_pool.need((size_t)n * kTabMaxBytes + 256); W.tab_desc.need((size_t)n * sizeof(TabDesc) + 16); W.left_list.need(n + 2); }
   cudaStream_t main = ctx->stream, side = ctx->stream2;
   MD_CUDA(cudaEventRecord(ctx->ev_fork, main));
@@ -1416,7 +1433,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   int h_pre[4] = {0, 0, 0, 0};
   uint32_t n_left = 0;           // spectra k_build_tables found too dense for the pipelined kernel
   MD_CUDA(cudaMemcpyAsync(h_pre, d_flag.p, sizeof(h_pre), cudaMemcpyDeviceToHost, ctx->stream));
-  const bool tables_built = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr;
+  const bool tables_built = p.top_k <= kFastTopK && !classic_only(ctx);
   if (tables_built) MD_CUDA(cudaMemcpyAsync(&n_left, W.left_list.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   // ---- K4
   ScoreConst C;
@@ -1427,8 +1444,14 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   bool has_var = false;
   for (int c = 0; c < 32; c++) {
     int64_t m = c < MD_NCODES ? ctx->mods.mass[c] : 0;
-    int64_t f = (c < MD_NCODES && ctx->mods.has_fix[c]) ? ctx->mods.fix[c] : 0;
+    int64_t f = (c < MD_NCODES && ctx->mods.has_fix[c] && ctx->mods.fix_pos[c] == MD_POS_A) ? ctx->mods.fix[c] : 0;
     int64_t v = (c < MD_NCODES && ctx->mods.has_var[c]) ? ctx->mods.var[c] : 0;
+    if (c < MD_NCODES && ctx->mods.has_fix[c] && ctx->mods.fix_pos[c] == MD_POS_N) {   // floor split: the remainder stays in [0, w)
+      const int64_t d = ctx->mods.fix[c], wq = (int64_t)C.w;
+      int64_t q = d / wq, r = d % wq;
+      if (r < 0) { r += wq; q--; }
+      C.nq[c] = (uint32_t)q; C.nr[c] = (uint32_t)r;
+    }
     split_qr(m + f, C.w, &C.tq[c], &C.tr[c]);
     split_qr(m + f + v, C.w, &C.vq[c], &C.vr[c]);
     MD_REQUIRE(C.tq[c] < (1u << 22) && C.vq[c] < (1u << 22), MD_ERR_UNSUPPORTED, "fragment_tolerance too small for this residue mass");
@@ -1443,7 +1466,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
   // chunks: split every spectrum into `parts` work items (contiguous ranges of candidate chunks; each builds the table
   // itself, which is cheap beside the chunks), about two items per SM.  MD_SCORE_SPLIT_MIN = candidates per spectrum
   // (batch average) from which that is done (tests lower it).
-  const bool pipe_path = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr && getenv("MD_SCORE_SPLIT_CLASSIC") == nullptr;
+  const bool pipe_path = p.top_k <= kFastTopK && !classic_only(ctx) && getenv("MD_SCORE_SPLIT_CLASSIC") == nullptr;
   uint32_t parts = 1;
   {
     uint64_t n_cand = (uint64_t)n * n_per, split_min = 16ull * kCandChunk;
@@ -1504,7 +1527,7 @@ void score_run_dev(md_ctx* ctx, const SpectraDev& S, uint64_t n_peaks, const md_
     else { if (parts > 1) launch(k_score<false, 2>); else if (single) launch(k_score<false, 0>); else launch(k_score<false, 1>); }
   };
   // the pipelined kernel (builders + scorers) takes whole-spectrum work items with at most 8 PSM rows; MD_SCORE_CLASSIC=1 forces k_score
-  const bool pipe = p.top_k <= kFastTopK && getenv("MD_SCORE_CLASSIC") == nullptr && (parts == 1 || pipe_path);
+  const bool pipe = p.top_k <= kFastTopK && !classic_only(ctx) && (parts == 1 || pipe_path);
   if (pipe) {
     // the table records are there (score_prepare_dev); the length-sorted candidate order and the schedule, each by the whole GPU at once
     W.cand_order.need((size_t)n * kPOrder + 16);

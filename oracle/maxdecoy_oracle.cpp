@@ -135,6 +135,19 @@ struct ModSet {
   bool has_var[MD_ALPHABET_SIZE] = {};
   int64_t fix[MD_ALPHABET_SIZE] = {};      // fixed delta per letter
   int64_t var[MD_ALPHABET_SIZE] = {};      // variable delta per letter
+  // position of the letter's fixed / variable modification: 'A' anywhere, 'N' / 'C' terminus (modification.rs:24-33).
+  // A terminal modification sits on the first / last residue only, and only when that residue is its letter
+  // (add_modification_at, modified_peptide.rs:421-447; set_variable_modification_at, :339-367).  One fixed and one
+  // variable modification per letter (HashMap<char, Modification>, identification.rs:163-171).
+  uint8_t fix_pos[MD_ALPHABET_SIZE] = {};
+  uint8_t var_pos[MD_ALPHABET_SIZE] = {};
+  bool has_terminal = false;
+  static bool at(uint8_t pos, uint32_t i, uint32_t L) { return pos == 'A' || (pos == 'N' && i == 0) || (pos == 'C' && i + 1 == L); }
+  // does residue i of a sequence of L residues, letter a, carry the letter's fixed modification?
+  bool fix_applies(int a, uint32_t i, uint32_t L) const { return has_fix[a] && at(fix_pos[a], i, L); }
+  // can it take the letter's variable modification?  (its slot -- side chain, N-terminus, C-terminus -- must exist at this
+  // position and must not hold the fixed modification: AlreadyFixModificationInPlace, :311,327,350)
+  bool can_var(int a, uint32_t i, uint32_t L) const { return has_var[a] && at(var_pos[a], i, L) && !(has_fix[a] && fix_pos[a] == var_pos[a]); }
   std::vector<int> letters;                // sorted modifiable letters (identification.rs:173-178), alphabet idx
   std::vector<uint8_t> letter_chars;
   int64_t merged(int a) const { return has_var[a] ? var[a] : fix[a]; }  // identification.rs:190-196
@@ -214,12 +227,15 @@ struct Occ { std::string g; uint8_t mc; uint32_t prot; };
 // ---------------------------------------------------------------------------------------
 // ModifiedPeptide filter: models/peptides/modified_peptide.rs:118-159 (from_string, fixed mods),
 // :512-543 (try_variable_modifications), utility/combinations/n_choose_k.rs:12-49 (order).
-// Only position 'A' (Anywhere) modifications are on the hot path.
+// Terminal (N/C) modifications follow the slot model the reference's add_modification_at / set_variable_modification_at
+// spell out (ModSet::fix_applies / can_var); its `modifications` vector bookkeeping for them is not restated (push_modification
+// leaves the vector one entry short per terminal modification, :182-208, which makes later index-based calls hit the wrong
+// residue or panic -- there is no behaviour to pin there).
 // ---------------------------------------------------------------------------------------
 struct ModState {  // the mutable working peptide
   std::vector<int> aa;          // alphabet idx, or -1 for letters outside the alphabet
   std::vector<uint8_t> raw;     // letter
-  std::vector<uint8_t> mod;     // 0 none, 1 fixed, 2 variable   (ModifiedPeptide.modifications)
+  std::vector<uint8_t> mod;     // bit 0: the letter's fixed modification is applied, bit 1: its variable one   (ModifiedPeptide.modifications + n/c_terminus_modification)
   int64_t w;
 };
 
@@ -232,18 +248,18 @@ void from_string(const ModSet& M, const uint8_t* s, uint32_t len, ModState* st) 
     int a = alpha_index(s[i]);
     st->aa[i] = a;
     st->w += residue_mass(s[i]);
-    if (a >= 0 && M.has_fix[a]) { st->w += M.fix[a]; st->mod[i] = 1; }
+    if (a >= 0 && M.fix_applies(a, i, len)) { st->w += M.fix[a]; st->mod[i] = 1; }
   }
 }
 
 void remove_all_var(const ModSet& M, ModState* st) {  // :369-401
   for (size_t i = 0; i < st->mod.size(); i++)
-    if (st->mod[i] == 2) { st->w -= M.var[st->aa[i]]; st->mod[i] = 0; }
+    if (st->mod[i] & 2) { st->w -= M.var[st->aa[i]]; st->mod[i] &= (uint8_t)~2; }
 }
 
 uint64_t var_mask_of(const ModState& st) {
   uint64_t m = 0;
-  for (size_t i = 0; i < st.mod.size(); i++) if (st.mod[i] == 2) m |= 1ULL << i;
+  for (size_t i = 0; i < st.mod.size(); i++) if (st.mod[i] & 2) m |= 1ULL << i;
   return m;
 }
 
@@ -281,8 +297,10 @@ bool try_variable(const ModSet& M, ModState* st, int64_t lo, int64_t hi) {  // :
       for (uint32_t b = 0; b < d; b++) {
         if (!((mask >> (d - 1 - b)) & 1)) continue;
         uint32_t i = pos[b];
-        if (st->mod[i] != 0) continue;  // AlreadyFixModificationInPlace -> continue 'positions (:355,532)
-        st->mod[i] = 2; st->w += M.var[st->aa[i]];
+        // AlreadyFixModificationInPlace -> continue 'positions (:355,532); a terminal modification away from its terminus
+        // falls through set_variable_modification_at without effect (:345-366)
+        if (!M.can_var(st->aa[i], i, (uint32_t)st->aa.size())) continue;
+        st->mod[i] |= 2; st->w += M.var[st->aa[i]];
       }
       if (in_window(st->w, lo, hi)) return true;
       mask = prev_combination(mask);
@@ -390,10 +408,10 @@ void candidates_for(const md_ctx* ctx, const md_precursor& pr, std::vector<Candi
 // ---------------------------------------------------------------------------------------
 // decoys
 // ---------------------------------------------------------------------------------------
-// remove_modification_at (:403-419) for Anywhere mods
+// remove_modification_at (:403-419): whatever residue i carries (side chain and, at the ends, terminus)
 inline void remove_mod_at(const ModSet& M, ModState* st, uint32_t i) {
-  if (st->mod[i] == 1) st->w -= M.fix[st->aa[i]];
-  else if (st->mod[i] == 2) st->w -= M.var[st->aa[i]];
+  if (st->mod[i] & 1) st->w -= M.fix[st->aa[i]];
+  if (st->mod[i] & 2) st->w -= M.var[st->aa[i]];
   st->mod[i] = 0;
 }
 inline void replace_at(const ModSet& M, ModState* st, uint32_t i, int c) {  // :470-482 / :493-505
@@ -401,7 +419,7 @@ inline void replace_at(const ModSet& M, ModState* st, uint32_t i, int c) {  // :
   st->w -= residue_mass(st->raw[i]);
   st->w += residue_mass((uint8_t)kAlphabet[c]);
   st->aa[i] = c; st->raw[i] = (uint8_t)kAlphabet[c];
-  if (M.has_fix[c]) { st->w += M.fix[c]; st->mod[i] = 1; }
+  if (M.fix_applies(c, i, (uint32_t)st->aa.size())) { st->w += M.fix[c]; st->mod[i] = 1; }   // add_modification_at (:421-447)
 }
 
 // One attempt of DecoyGenerator::generate_decoys' worker loop (utility/decoy_generator.rs:139-187)
@@ -416,9 +434,12 @@ bool random_attempt(const ModSet& M, const md_precursor& pr, uint64_t seed, uint
   st->w = convert_mass_to_int(18.010565);
   for (;;) {                                            // 'amino_acid_loop (:142-159)
     int c = (int)rng.below(MD_ALPHABET_SIZE);
+    // push_modification (:182-208): the residue that was last loses its C-terminus modification ...
+    if (!st->aa.empty() && (st->mod.back() & 1) && M.fix_pos[st->aa.back()] == 'C') { st->w -= M.fix[st->aa.back()]; st->mod.back() &= (uint8_t)~1; }
     st->aa.push_back(c); st->raw.push_back((uint8_t)kAlphabet[c]); st->mod.push_back(0);
     st->w += residue_mass((uint8_t)kAlphabet[c]);
-    if (M.has_fix[c]) { st->w += M.fix[c]; st->mod.back() = 1; }
+    // ... and the new one takes its letter's fixed modification: anywhere, C-terminus (it is the last one now), N-terminus if it is the first
+    if (M.fix_applies(c, (uint32_t)st->aa.size() - 1, (uint32_t)st->aa.size())) { st->w += M.fix[c]; st->mod.back() = 1; }
     if (st->w > pr.hi) break;                           // GreaterThenMassTolerance (:294-300)
     if (st->aa.size() > MD_MAX_PEPTIDE_LEN) return false;
   }
@@ -652,7 +673,7 @@ int64_t score_candidate(const ModSet& M, const BinnedSpectrum& B, const uint8_t*
     int a = alpha_index(seq[i]);
     int64_t v = residue_mass(seq[i]);
     if (a >= 0) {
-      if (M.has_fix[a]) v += M.fix[a];
+      if (M.fix_applies(a, i, len)) v += M.fix[a];   // (a terminal modification adds to the end residue's mass: every b ion holds the first residue, every y ion the last)
       if ((mask >> i) & 1) v += M.var[a];
     }
     m[i] = v; total += v;
@@ -786,14 +807,15 @@ int md_set_modifications(md_ctx* ctx, const md_modification* mods, uint32_t n, u
   ModSet M; M.nvar = max_var;
   for (uint32_t i = 0; i < n; i++) {
     uint8_t pos = (uint8_t)std::toupper(mods[i].position);
-    if (pos == 'N' || pos == 'C') return fail(ctx, MD_ERR_UNSUPPORTED, "terminal modifications (position N/C) are outside the hot path");
-    if (pos != 'A') return fail(ctx, MD_ERR_INVALID, "modification position must be A, N or C");  // modification.rs:24-33
+    if (pos != 'A' && pos != 'N' && pos != 'C') return fail(ctx, MD_ERR_INVALID, "modification position must be A, N or C");  // modification.rs:24-33
     uint8_t aa = (uint8_t)std::toupper(mods[i].amino_acid);
     int a = alpha_index(aa);
     if (a < 0) return fail(ctx, MD_ERR_INVALID, "modification on a letter without a <x>_count column (alphabet " MD_ALPHABET ")");
-    if (mods[i].is_fix) { M.has_fix[a] = true; M.fix[a] = mods[i].mono_mass; }
-    else { M.has_var[a] = true; M.var[a] = mods[i].mono_mass; }
+    if (mods[i].is_fix) { M.has_fix[a] = true; M.fix[a] = mods[i].mono_mass; M.fix_pos[a] = pos; }
+    else { M.has_var[a] = true; M.var[a] = mods[i].mono_mass; M.var_pos[a] = pos; }
   }
+  M.has_terminal = false;   // (of the modifications that survived: a later entry of a letter replaces an earlier one)
+  for (int a = 0; a < MD_ALPHABET_SIZE; a++) if ((M.has_fix[a] && M.fix_pos[a] != 'A') || (M.has_var[a] && M.var_pos[a] != 'A')) M.has_terminal = true;
   for (int a = 0; a < MD_ALPHABET_SIZE; a++)
     if (M.has_fix[a] || M.has_var[a]) {
       if (residue_mass((uint8_t)kAlphabet[a]) + M.merged(a) <= 0) return fail(ctx, MD_ERR_INVALID, "modified residue mass must be positive");
@@ -919,6 +941,7 @@ int md_index_build(md_ctx* ctx) {
   if (!ctx->peps.ready) return fail(ctx, MD_ERR_STATE, "md_index_build: md_digest first");
   if (!ctx->mods.set) return fail(ctx, MD_ERR_STATE, "md_index_build: md_set_modifications first");
   const Peptides& P = ctx->peps; const ModSet& M = ctx->mods;
+  if (ctx->var_mode == MD_VARMOD_EXPANDED && M.has_terminal) return fail(ctx, MD_ERR_UNSUPPORTED, "expanded variable-modification mode is defined for position-A modifications only");
   size_t n = P.seq.size();
   std::vector<std::pair<int64_t, uint32_t>> kv(n);
   for (size_t i = 0; i < n; i++) {
@@ -1026,6 +1049,7 @@ int md_generate_decoys(md_ctx* ctx, const md_precursor* pr, uint32_t n_spec, uin
   if (!ctx || !out || (n_spec && !pr)) return fail(ctx, MD_ERR_INVALID, "md_generate_decoys: null argument");
   if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_generate_decoys: md_index_build first");
   if (mode < 0 || mode > 2) return fail(ctx, MD_ERR_INVALID, "md_generate_decoys: unknown mode");
+  if (mode == MD_DECOY_EXHAUSTIVE && ctx->mods.has_terminal && n_spec && n_per) return fail(ctx, MD_ERR_UNSUPPORTED, "exhaustive decoys enumerate compositions: not defined with terminal modifications (the weight depends on the order)");
   std::vector<std::vector<Decoy>> per(n_spec);
   parallel_for(n_spec, ctx->n_threads, [&](uint32_t s) { gen_decoys(ctx, pr[s], n_per, mode, seed, &per[s]); });
   return fill_decoy_table(per, out);
@@ -1041,6 +1065,7 @@ int md_identify(md_ctx* ctx, const md_spectra* S, const md_search_params* p, md_
   if (!ctx->index.ready) return fail(ctx, MD_ERR_STATE, "md_identify: md_index_build first");
   int rc = validate_spectra(ctx, S); if (rc) return rc;
   if (p->decoy_mode < 0 || p->decoy_mode > 2) return fail(ctx, MD_ERR_INVALID, "md_identify: unknown decoy mode");
+  if (p->decoy_mode == MD_DECOY_EXHAUSTIVE && ctx->mods.has_terminal && S->n && p->n_decoys) return fail(ctx, MD_ERR_UNSUPPORTED, "exhaustive decoys enumerate compositions: not defined with terminal modifications (the weight depends on the order)");
   const int64_t w = (int64_t)std::llround(p->fragment_tolerance * 1000000.0);
   if (w < 100 || w > 2000000) return fail(ctx, MD_ERR_INVALID, "md_identify: fragment_tolerance must be in [0.0001, 2] Da");
   const uint32_t mfc = p->max_fragment_charge ? p->max_fragment_charge : 3;

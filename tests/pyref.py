@@ -70,15 +70,81 @@ def precursor_window(mz, z, lppm, uppm):                # identification.rs:203-
 
 
 class Mods:
-    """fixed / variable maps of identification_task (identification.rs:163-196); Anywhere position only."""
+    """fixed / variable maps of identification_task (identification.rs:163-196): one fixed and one variable
+    modification per letter, each with its position A / N / C (modification.rs:24-33)."""
 
     def __init__(self, mods, nvar):
         self.fix = {m.amino_acid: m.mono_mass_int for m in mods if m.is_fix}
         self.var = {m.amino_acid: m.mono_mass_int for m in mods if not m.is_fix}
+        self.fix_pos = {m.amino_acid: getattr(m, "position", "A") for m in mods if m.is_fix}
+        self.var_pos = {m.amino_acid: getattr(m, "position", "A") for m in mods if not m.is_fix}
         self.nvar = nvar
         self.letters = sorted(set(self.fix) | set(self.var))        # :173-178
         self.merged = dict(self.fix)
         self.merged.update(self.var)                                # variable overrides fixed (:190-196)
+
+
+class SlotPeptide:
+    """ModifiedPeptide with the three modification slots the reference's add_modification_at (modified_peptide.rs:421-447)
+    and set_variable_modification_at (:339-367) distinguish: `side[i]` (= modifications[i]), `nterm`
+    (= n_terminus_modification, residue 0) and `cterm` (= c_terminus_modification, last residue).  Each holds None,
+    ('fix', delta) or ('var', delta).  from_string = add_modification_at of the letter's fixed modification at every index."""
+
+    def __init__(self, mods, seq):
+        self.mods, self.seq = mods, seq
+        self.w = to_int(H2O)
+        self.side = [None] * len(seq)
+        self.nterm = self.cterm = None
+        for i, c in enumerate(seq):
+            self.w += residue_mass(c)
+            if c in mods.fix:
+                self._add(i, "fix", mods.fix_pos[c], mods.fix[c])
+
+    def _add(self, i, kind, pos, delta):
+        last = len(self.seq) - 1
+        if i == 0 and pos == "N":
+            if self.nterm is not None:
+                return False                                        # AlreadyFixModificationInPlace (:327)
+            self.nterm = (kind, delta)
+        elif i == last and pos == "C":
+            if self.cterm is not None:
+                return False                                        # :311
+            self.cterm = (kind, delta)
+        elif pos == "A":
+            if self.side[i] is not None:
+                return False                                        # :350
+            self.side[i] = (kind, delta)
+        else:
+            return False                                            # a terminal modification away from its terminus: no effect (:345-366)
+        self.w += delta
+        return True
+
+    def remove_all_variable(self):                                  # :369-401
+        if self.nterm and self.nterm[0] == "var":
+            self.w -= self.nterm[1]
+            self.nterm = None
+        if self.cterm and self.cterm[0] == "var":
+            self.w -= self.cterm[1]
+            self.cterm = None
+        for i, s in enumerate(self.side):
+            if s and s[0] == "var":
+                self.w -= s[1]
+                self.side[i] = None
+
+    def set_variable(self, i):
+        c = self.seq[i]
+        return self._add(i, "var", self.mods.var_pos[c], self.mods.var[c])
+
+    def var_mask(self):
+        m = 0
+        for i, s in enumerate(self.side):
+            if s and s[0] == "var":
+                m |= 1 << i
+        if self.nterm and self.nterm[0] == "var":
+            m |= 1
+        if self.cterm and self.cterm[0] == "var":
+            m |= 1 << (len(self.seq) - 1)
+        return m
 
 
 def fanout_queries(mods, P, lo, hi):                    # identification.rs:214-222, 374-403
@@ -117,35 +183,20 @@ def n_choose_k_masks(d, k):                             # n_choose_k.rs:12-49: d
 
 def modified_peptide_filter(mods, seq, lo, hi):         # identification.rs:242-257; modified_peptide.rs:118-159,512-543
     """-> (accepted, weight, var position mask)"""
-    w = to_int(H2O)
-    state = []                                          # per residue: None / 'fix' / 'var'
-    for c in seq:
-        w += residue_mass(c)
-        if c in mods.fix:
-            w += mods.fix[c]
-            state.append("fix")
-        else:
-            state.append(None)
-    if lo <= w <= hi:
-        return True, w, 0
+    mp = SlotPeptide(mods, seq)
+    if lo <= mp.w <= hi:
+        return True, mp.w, 0
     positions = [i for i, c in enumerate(seq) if c in mods.var]
     for n in range(1, mods.nvar + 1):
         if n > len(positions):
             continue
         for chosen in n_choose_k_masks(len(positions), n):
-            for i, s in enumerate(state):                           # remove_all_variable_modifications
-                if s == "var":
-                    w -= mods.var[seq[i]]
-                    state[i] = None
+            mp.remove_all_variable()
             for b in chosen:
-                i = positions[b]
-                if state[i] is not None:                            # AlreadyFixModificationInPlace
-                    continue
-                state[i] = "var"
-                w += mods.var[seq[i]]
-            if lo <= w <= hi:
-                return True, w, sum(1 << i for i, s in enumerate(state) if s == "var")
-    return False, w, 0
+                mp.set_variable(positions[b])                       # errors -> continue 'positions
+            if lo <= mp.w <= hi:
+                return True, mp.w, mp.var_mask()
+    return False, mp.w, 0
 
 
 def candidates_sql(mods, peptides, P, lo, hi):
@@ -208,10 +259,13 @@ def score(mods, T, seq, mask, z, w, max_frag_charge=3):
         return 0
     nch = min(max(z - 1, 1), max_frag_charge)
     m = []
+    last = len(seq) - 1
     for i, c in enumerate(seq):
         v = residue_mass(c)
         if c in ALPHABET:
-            v += mods.fix.get(c, 0)
+            fp = getattr(mods, "fix_pos", {}).get(c, "A")
+            if c in mods.fix and (fp == "A" or (fp == "N" and i == 0) or (fp == "C" and i == last)):
+                v += mods.fix[c]
             if (mask >> i) & 1:
                 v += mods.var.get(c, 0)
         m.append(v)

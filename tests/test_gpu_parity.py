@@ -368,8 +368,8 @@ def test_error_reporting(gpu):
     assert ei.value.status == -2
     e.digest(list(wl.proteins(50)), 2, 5, 50)
     with pytest.raises(maxdecoy.MaxDecoyError) as ei:
-        e.set_modifications([maxdecoy.Modification("x:1", "nterm", "N", True, "A", 42.0)], 0)
-    assert ei.value.status == -5                              # terminal modifications: outside the hot path
+        e.set_modifications([maxdecoy.Modification("x:1", "bad position", "Q", True, "A", 42.0)], 0)
+    assert ei.value.status == -1                              # position must be A, N or C (modification.rs:24-33)
     with pytest.raises(maxdecoy.MaxDecoyError):
         e.digest(["MKR"], 2, 5, 61)
     e.set_modifications([synth.CAM], 0)
