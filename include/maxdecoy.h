@@ -83,7 +83,10 @@ MD_API int md_precursor_window(double mz, uint32_t charge, int64_t lower_ppm, in
 typedef struct md_modification {
   char accession[24];  /* lower-cased by the library (modification.rs:48) */
   char name[40];
-  uint8_t position;    /* 'A' anywhere, 'N', 'C' (modification.rs:24-33); only 'A' is on the hot path */
+  uint8_t position;    /* 'A' anywhere, 'N' / 'C' terminus (modification.rs:24-33): a terminal modification sits on the first / last residue
+                        * only, and only when that residue is `amino_acid` (add_modification_at, modified_peptide.rs:421-447;
+                        * set_variable_modification_at, :339-367).  MD_DECOY_EXHAUSTIVE and MD_VARMOD_EXPANDED return
+                        * MD_ERR_UNSUPPORTED with terminal modifications. */
   uint8_t is_fix;      /* != 0 -> fixed */
   uint8_t amino_acid;  /* one letter code, upper-cased */
   uint8_t _pad[5];

@@ -262,14 +262,18 @@ const std::map<char, std::string> kNames = {   // models/amino_acids/amino_acid.
     {'F', "Phenylalanine"}, {'P', "Proline"}, {'O', "Pyrrolysine"}, {'S', "Serine"}, {'T', "Threonine"}, {'U', "Selenocysteine"},
     {'V', "Valine"}, {'W', "Tryptophan"}, {'Y', "Tyrosine"}};
 
-// ModifiedPeptide::get_modification_summary_for_header (models/peptides/modified_peptide.rs:606-659), position 'A' only
+// ModifiedPeptide::get_modification_summary_for_header (models/peptides/modified_peptide.rs:606-659): the fixed modification
+// where its position allows (anywhere; N / C: first / last residue only), the variable one where the mask says
 std::string mod_summary(const std::string& seq, const std::vector<Mod>& mods, uint64_t var_mask) {
   std::map<std::string, int> counts;
   for (size_t i = 0; i < seq.size(); i++) {
-    const Mod* hit = nullptr;
-    for (auto& m : mods) if (m.is_fix && m.aa == seq[i]) hit = &m;
-    if (!hit && ((var_mask >> i) & 1)) for (auto& m : mods) if (!m.is_fix && m.aa == seq[i]) hit = &m;
-    if (hit) counts[hit->accession + "|" + hit->name]++;
+    const Mod* fix = nullptr; const Mod* var = nullptr;
+    for (auto& m : mods) if (m.is_fix && m.aa == seq[i]) fix = &m;
+    if (fix && !(fix->position == 'A' || (fix->position == 'N' && i == 0) || (fix->position == 'C' && i + 1 == seq.size()))) fix = nullptr;
+    if ((var_mask >> i) & 1) for (auto& m : mods) if (!m.is_fix && m.aa == seq[i]) var = &m;
+    if (var && fix && var->position == fix->position) var = nullptr;
+    if (fix) counts[fix->accession + "|" + fix->name]++;
+    if (var) counts[var->accession + "|" + var->name]++;
   }
   std::string out;
   for (auto& kv : counts) out += "(" + std::to_string(kv.second) + "|" + kv.first + ")";

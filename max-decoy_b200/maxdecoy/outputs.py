@@ -33,16 +33,22 @@ def rust_f64(x):
 
 
 def modification_summary(sequence, mods, var_mask=0):
-    """ModifiedPeptide::get_modification_summary_for_header for position-'A' modifications: every residue whose
-    letter has a fixed modification carries it; residue i carries its variable modification iff bit i of var_mask."""
+    """ModifiedPeptide::get_modification_summary_for_header (modified_peptide.rs:606-659): a residue carries its letter's
+    fixed modification where the modification's position allows (anywhere; N / C: first / last residue only), and its
+    variable modification iff bit i of var_mask (the library sets that bit only where the variable modification's own
+    slot -- side chain or terminus -- is free)."""
     fix = {m.amino_acid: m for m in mods if m.is_fix}
     var = {m.amino_acid: m for m in mods if not m.is_fix}
+    last = len(sequence) - 1
     counts = {}
     for i, c in enumerate(sequence):
+        hits = []
         m = fix.get(c)
-        if m is None and (var_mask >> i) & 1:
-            m = var.get(c)
-        if m is not None:
+        if m is not None and (m.position == "A" or (m.position == "N" and i == 0) or (m.position == "C" and i == last)):
+            hits.append(m)
+        if (var_mask >> i) & 1 and c in var and not (hits and hits[0].position == var[c].position):
+            hits.append(var[c])
+        for m in hits:
             key = "%s|%s" % (m.accession, m.name)
             counts[key] = counts.get(key, 0) + 1
     return "".join("(%d|%s)" % (counts[k], k) for k in sorted(counts))

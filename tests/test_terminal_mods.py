@@ -154,6 +154,16 @@ def test_terminal_weight_examples(cpu):
     assert not sp.set_variable(0) and not sp.set_variable(2) and sp.w == base("SAS") + S_NTERM_FIX.mono_mass_int
 
 
+def test_terminal_header_summary():
+    """ModRes summary (modified_peptide.rs:606-659): side-chain, N-terminus and C-terminus slots, sorted by accession|name."""
+    from maxdecoy import outputs
+    mods = [K_CTERM_FIX, M_NTERM_FIX, synth.OXM]
+    assert outputs.modification_summary("MKAKMK", mods, 1 << 4) == "(1|unimod:1|Acetyl)(1|unimod:35|Oxidation)(1|x:259|Label:13C(6)15N(2))"
+    assert outputs.modification_summary("MKAKMK", mods, 1) == "(1|unimod:1|Acetyl)(1|unimod:35|Oxidation)(1|x:259|Label:13C(6)15N(2))"
+    assert outputs.modification_summary("AKAKMA", mods, 0) == ""
+    assert outputs.modification_summary("SAS", [S_NTERM_FIX, S_NTERM_VAR], 0) == "(1|x:3|Acetyl)"
+
+
 @pytest.mark.parametrize("mods,nvar", MOD_SETS, ids=IDS)
 def test_terminal_scores_and_decoys(cpu, mods, nvar):
     """Scores of targets and decoys against the dense Python table with the terminal masses on the end residues; every
