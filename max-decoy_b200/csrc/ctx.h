@@ -73,7 +73,6 @@ struct IdentifyWorkspace {
   // per-call temporaries kept between calls (cudaMalloc/cudaFree inside a call would serialise the device)
   DevBuf<uint64_t> t_size; DevBuf<int16_t> t_K; DevBuf<uint32_t> t_flag, t_pos; DevBuf<int> t_ovf, t_unsorted;
   DevBuf<uint32_t> t_list, t_off, t_base, t_queue, t_spill, t_blk;
-  DevBuf<uint32_t> t_chunks, t_cstate, t_succ, t_need, t_attn, t_next, t_run, t_seen, t_mult;   // early stop of the decoy rounds (decoy.cu: RandomArgs)
   DevBuf<md_precursor> t_win;        // MD_VARMOD_EXPANDED: shifted windows, one per (spectrum, count vector)
   // exhaustive mode
   DevBuf<int32_t> ex_comp; DevBuf<uint64_t> ex_cum; DevBuf<uint32_t> ex_ncomp;

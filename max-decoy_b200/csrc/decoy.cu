@@ -79,9 +79,9 @@ struct AttemptOut {
 
 // write one finished attempt (len == 0 -> failure)
 template <class SeqT>
-__device__ uint64_t store_attempt(const AttemptOut& O, uint64_t slot, const SeqT& seq, uint32_t L, uint64_t mask, int64_t w, const DecoyTables& T,
-                                  const PeptideView& PV) {   // -> the sequence hash of a kept row (0 is returned as 1), 0 otherwise
-  if (L == 0) { O.len[slot] = 0; return 0; }
+__device__ void store_attempt(const AttemptOut& O, uint64_t slot, const SeqT& seq, uint32_t L, uint64_t mask, int64_t w, const DecoyTables& T,
+                              const PeptideView& PV) {
+  if (L == 0) { O.len[slot] = 0; return; }
   uint8_t ascii[MD_MAX_PEPTIDE_LEN];
   uint64_t h = md_hash_init();
   uint8_t* row = O.rows + slot * MD_DECOY_ROW;
@@ -95,9 +95,8 @@ __device__ uint64_t store_attempt(const AttemptOut& O, uint64_t slot, const SeqT
   { const uint32_t pad = MD_CODE_OTHER * 0x01010101u;
     for (uint32_t c = (L + 15u) >> 4; c < MD_DECOY_ROW / 16; c++) reinterpret_cast<uint4*>(row)[c] = make_uint4(pad, pad, pad, pad); }
   h = md_hash_fin(h, L);
-  if (is_peptide(ascii, L, h, PV.ht_key, PV.ht_val, PV.ht_mask, PV.seq, PV.off, PV.len)) { O.len[slot] = 0; return 0; }
+  if (is_peptide(ascii, L, h, PV.ht_key, PV.ht_val, PV.ht_mask, PV.seq, PV.off, PV.len)) { O.len[slot] = 0; return; }
   O.len[slot] = (uint8_t)L; O.mask[slot] = mask; O.w[slot] = w; O.hash[slot] = h;
-  return h ? h : 1ull;
 }
 
 // work item -> (list entry, attempt ordinal) by binary search on the round's prefix of attempt counts
@@ -234,18 +233,7 @@ template <uint32_t OFF> __device__ __forceinline__ uint32_t tab_u8(uint32_t addr
   uint32_t v; asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF)); return v;
 }
 
-// Early stop (narrow pass of a round, `chunks` set): the work items of a list entry are padded to whole chunks of kChunk
-// attempts and handed out chunk by chunk in LAYER order -- the first chunk of every entry, then the second of every entry
-// still planned, ... -- so that a spectrum's attempts are spread over the launch instead of all being in flight at once.
-// A spectrum that has reported `need` successes gets no further chunk: the first lane to draw an item of a chunk decides
-// for the whole chunk (chunk_state: 0 undecided, 1 run, 2 skipped).  Successes are counted through a per-spectrum bit set
-// over their sequence hashes (`seen`, seen_bits per spectrum, kept for the whole call), i.e. repeats of a sequence are not
-// counted -- small precursors have few decoys and find the same ones again and again; two sequences on one bit only make the
-// spectrum stop a little later.  Exactness does not depend on the timing: only the
-// leading run of executed chunks of an entry counts as attempted (k_round_prefix -> att_run), a later round resumes there.
-constexpr uint32_t kChunkLog = 6, kChunk = 1u << kChunkLog;
 struct RandomArgs {
-  const uint32_t* chunks; uint32_t* chunk_state; uint32_t* succ; const uint32_t* need; const uint32_t* att_n; uint32_t* seen; uint32_t seen_bits;
   const md_precursor* prec; const uint32_t* list; const uint32_t* att_off; const uint32_t* att_base;
   const uint32_t* att_blk;              // coarse index into att_off (find_entry_coarse)
   uint32_t n_list, total;
@@ -266,7 +254,7 @@ struct RandomArgs {
 // VMODE: 0 = no variable modification can apply, 1 = one variable letter without a fixed modification (its positions are
 // tracked, try_variable_modifications needs no walk over the sequence), 2 = anything else (generic enumeration).
 template <int VMODE, class MaskT>
-__global__ void __launch_bounds__(kThreads, sizeof(MaskT) == 4 ? 10 : 6) k_decoy_random(const RandomArgs A, const __grid_constant__ ModTables M, const __grid_constant__ DecoyTables T,
+__global__ void __launch_bounds__(kThreads) k_decoy_random(const RandomArgs A, const __grid_constant__ ModTables M, const __grid_constant__ DecoyTables T,
                                                            AttemptOut O, PeptideView PV) {
   using MO = MaskOps<MaskT>;
   constexpr uint32_t kBits = MO::bits;
@@ -325,45 +313,13 @@ __global__ void __launch_bounds__(kThreads, sizeof(MaskT) == 4 ? 10 : 6) k_decoy
     uint32_t free_m = 0;
     if (__popc(busy_m) <= 32 - kRefillMin) free_m = __ballot_sync(0xffffffffu, !busy && (!drained || pending));
     if (free_m && (__popc(free_m) >= kRefillMin || busy_m == 0)) {
-      if (!busy && pending) {
-        // (early stop: the attempt's spectrum was left in its hash slot when it was drawn)
-        const uint32_t sp = (A.chunks && pending == 1) ? (uint32_t)O.hash[wi] : 0u;
-        const uint64_t kept = store_attempt(O, wi, seq, pending == 1 ? L : 0, (uint64_t)mask, P + d, T, PV);
-        if (A.chunks && kept) {
-          const uint32_t b = (uint32_t)(kept >> 20) & (A.seen_bits - 1u);
-          const uint32_t old = atomicOr(A.seen + (size_t)sp * (A.seen_bits >> 5) + (b >> 5), 1u << (b & 31u));
-          if (!((old >> (b & 31u)) & 1u)) atomicAdd(A.succ + sp, 1u);
-        }
-        pending = 0;
-      }
+      if (!busy && pending) { store_attempt(O, wi, seq, pending == 1 ? L : 0, (uint64_t)mask, P + d, T, PV); pending = 0; }
       if (!busy && !drained) {
         const uint32_t q = atomicAdd(A.queue, 1u);
-        bool take = q < total;
-        uint32_t li = 0;
-        if (!take) drained = true;
+        if (q >= total) drained = true;
         else {
-          if (A.chunks) {
-            const uint32_t cj = A.chunks[q >> kChunkLog];
-            wi = (cj << kChunkLog) + (q & (kChunk - 1u));
-            li = find_entry_coarse(A.att_off, A.att_blk, wi);
-            take = wi - A.att_off[li] < A.att_n[li];           // (padding of the entry's last chunk)
-            if (take) {
-              const uint32_t sp = A.list[li];
-              uint32_t st = *(volatile uint32_t*)(A.chunk_state + cj);
-              if (st == 0u) {
-                const uint32_t mine = *(volatile uint32_t*)(A.succ + sp) >= A.need[sp] ? 2u : 1u;
-                st = atomicCAS(A.chunk_state + cj, 0u, mine);
-                if (st == 0u) st = mine;
-              }
-              take = st == 1u;
-              if (take) O.hash[wi] = sp;
-            }
-          } else {
-            wi = A.remap ? A.remap[q] : q;
-            li = find_entry_coarse(A.att_off, A.att_blk, wi);
-          }
-        }
-        if (take) {
+          wi = A.remap ? A.remap[q] : q;
+          const uint32_t li = find_entry_coarse(A.att_off, A.att_blk, wi);
           const md_precursor pr = A.prec[A.list[li]];
           P = pr.mass;
           rng.start(A.seed, pr.spectrum_id, A.att_base[li] + (wi - A.att_off[li]));
@@ -615,7 +571,7 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ att_base, uint32_t n_per, uint32_t slots, uint32_t max_na, AttemptOut A,
                                                       uint64_t n_slots, uint8_t* __restrict__ dec_rows, uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask,
                                                       int64_t* __restrict__ dec_w, uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt,
-                                                      uint32_t* __restrict__ dec_count, const uint32_t* __restrict__ att_run) {
+                                                      uint32_t* __restrict__ dec_count) {
   extern __shared__ __align__(16) unsigned long long s_key[];     // slots (0 = empty)
   unsigned long long* s_hash = s_key + slots;                     // max_na: hash of a success (0 -> 1), 0 = failed attempt
   uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_hash + max_na); // slots
@@ -623,7 +579,7 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
   __shared__ uint32_t s_wsum[8];
   __shared__ uint32_t s_collision;
   const uint32_t li = blockIdx.x, s = list[li];
-  const uint32_t a0 = att_off[li], na = att_run ? att_run[li] : att_off[li + 1] - a0;   // (early stop: the executed prefix)
+  const uint32_t a0 = att_off[li], na = att_off[li + 1] - a0;
   const uint32_t have = dec_count[s];
   const uint64_t dbase = (uint64_t)s * n_per;
   const uint32_t smask = slots - 1;
@@ -747,14 +703,13 @@ __global__ void __launch_bounds__(256) k_decoy_select(const uint32_t* __restrict
 __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restrict__ list, const uint32_t* __restrict__ att_off,
                                                       const uint32_t* __restrict__ att_base, uint32_t n_per, AttemptOut A, uint64_t n_slots, uint8_t* __restrict__ dec_rows,
                                                       uint8_t* __restrict__ dec_len, uint64_t* __restrict__ dec_mask, int64_t* __restrict__ dec_w,
-                                                      uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt, uint32_t* __restrict__ dec_count,
-                                                      const uint32_t* __restrict__ att_run) {
+                                                      uint64_t* __restrict__ dec_hash, uint32_t* __restrict__ dec_attempt, uint32_t* __restrict__ dec_count) {
   __shared__ uint64_t s_hash[kMaxRoundAttempts];
   __shared__ uint8_t s_keep[kMaxRoundAttempts];
   __shared__ uint32_t s_scan[256];
   __shared__ uint32_t s_base;
   const uint32_t li = blockIdx.x, s = list[li];
-  const uint32_t a0 = att_off[li], na = att_run ? att_run[li] : att_off[li + 1] - a0;
+  const uint32_t a0 = att_off[li], na = att_off[li + 1] - a0;
   const uint32_t have = dec_count[s];
   const uint64_t dbase = (uint64_t)s * n_per;
   for (uint32_t a = threadIdx.x; a < na; a += blockDim.x) s_hash[a] = A.len[a0 + a] ? A.hash[a0 + a] : 0ULL;
@@ -810,38 +765,6 @@ __global__ void __launch_bounds__(256) k_decoy_select_n2(const uint32_t* __restr
   }
   __syncthreads();
   if (threadIdx.x == 0) dec_count[s] = min(n_per, have + s_base);
-}
-
-// Early stop: how many attempts of each list entry count as attempted -- the leading run of executed chunks; the entries a
-// spectrum has in the later levels of the round count only behind a fully executed predecessor (next: entry of the same
-// spectrum one level up, or 0xFFFFFFFF).  One thread per first-level entry.
-__global__ void k_round_prefix(const uint32_t* __restrict__ chunk_state, const uint32_t* __restrict__ att_off, const uint32_t* __restrict__ att_n,
-                               const uint32_t* __restrict__ next, uint32_t n_first, uint32_t* __restrict__ att_run) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_first) return;
-  bool ok = true;
-  for (uint32_t li = e; li != 0xFFFFFFFFu; li = next[li]) {
-    uint32_t run = 0;
-    if (ok) {
-      const uint32_t c0 = att_off[li] >> kChunkLog, nc = (att_n[li] + kChunk - 1u) >> kChunkLog;
-      uint32_t k = 0;
-      while (k < nc && chunk_state[c0 + k] == 1u) k++;
-      run = min(k << kChunkLog, att_n[li]);
-      ok = run == att_n[li];
-    }
-    att_run[li] = run;
-  }
-}
-
-// Early stop: what each listed spectrum has to report before it stops = what it has reported so far + what it still misses
-// + a small margin (sequences equal to a stored or an earlier accepted decoy that the bit set does not know), times `mult`.
-__global__ void k_round_need(const uint32_t* __restrict__ list, uint32_t n_first, const uint32_t* __restrict__ mult, const uint32_t* __restrict__ succ,
-                             const uint32_t* __restrict__ dec_count, uint32_t n_per, uint32_t* __restrict__ need) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_first) return;
-  const uint32_t s = list[e], rem = n_per - min(n_per, dec_count[s]);
-  const unsigned long long v = (unsigned long long)succ[s] + (unsigned long long)(rem + 2u) * mult[e];
-  need[s] = (uint32_t)min(v, 0xFFFFFFF0ull);
 }
 
 template <class MaskT>
@@ -1012,9 +935,7 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
   DevBuf<int>& d_ovf = W.t_ovf;
   d_list.need((size_t)n * kRoundLevels + 1); d_off.need((size_t)n * kRoundLevels + 2); d_base.need((size_t)n * kRoundLevels + 1); d_queue.need(4); d_ovf.need(1);
   MD_CUDA(cudaMemsetAsync(d_ovf.p, 0, sizeof(int), ctx->stream));
-  std::vector<uint32_t> list, off, base, blk, att_n, chunk_tab, next, need, run, dupf(n, 1u);
-  uint32_t seen_bits = 0;
-  const bool chunked = mode == MD_DECOY_REFERENCE_RANDOM && !ctx->mods.has_terminal && !wide_only && getenv("MD_DECOY_NO_EARLY_STOP") == nullptr;
+  std::vector<uint32_t> list, off, base, blk;
   const double later_factor = getenv("MD_DECOY_LATER_PCT") ? std::max(100, atoi(getenv("MD_DECOY_LATER_PCT"))) / 100.0 : 1.05;   // head room of the later rounds (swept on C2: 100..180 %)
   const uint32_t want0_pct = getenv("MD_DECOY_WANT0_PCT") ? (uint32_t)std::max(100, atoi(getenv("MD_DECOY_WANT0_PCT"))) : 110u;   // round 0 asks for n * 1.10 + 32 attempts (swept on C2: 100..160 %)
   for (int round = 0;; round++) {   // until every spectrum has its decoys or has used up its attempts (every round makes progress)
@@ -1028,28 +949,16 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
     for (uint32_t si = 0; si < n; si++) {
       const uint32_t s = by_mass[si];
       if (count[s] >= n_per || used[s] >= cap[s]) continue;
-      todo.push_back(s);
-    }
-    // Early stop (see RandomArgs): with at least one chunk per lane in flight spread over different spectra, a spectrum has
-    // about one chunk running when it reports its last success, so planning more than it needs costs next to nothing --
-    // the round asks for up to a full list entry per spectrum (within a memory budget for the attempt rows) and the
-    // spectra stop themselves.  Smaller rounds keep the tight budgets (their chunks all start at once), with the stop as a bonus.
-    const uint32_t gen_pct = getenv("MD_DECOY_GENEROUS_PCT") ? (uint32_t)std::max(100, atoi(getenv("MD_DECOY_GENEROUS_PCT"))) : 230u;
-    const uint64_t gen_min = getenv("MD_DECOY_GENEROUS_MIN") ? (uint64_t)atoll(getenv("MD_DECOY_GENEROUS_MIN")) : (uint64_t)ctx->n_sm * (uint64_t)occ_narrow * kThreads / kChunk;   // (tests lower it)
-    const bool generous = chunked && (uint64_t)todo.size() >= gen_min;
-    const uint64_t gen_cap = generous ? std::max<uint64_t>(kChunk, std::min<uint64_t>(kMaxRoundAttempts, (12ull << 30) / (96ull * todo.size()))) : 0;
-    for (uint32_t s : todo) {
       uint32_t want;
       if (used[s] == 0) { const uint32_t rem = n_per - count[s]; want = (uint32_t)((uint64_t)rem * want0_pct / 100u) + 32; }
       else {
         double yield = std::max(0.02, (double)count[s] / (double)used[s]);
         want = (uint32_t)((double)(n_per - count[s]) / yield * later_factor) + 48;
       }
-      if (generous) want = (uint32_t)std::max<uint64_t>(want, std::min<uint64_t>(gen_cap, (uint64_t)want * gen_pct / 100u));
       want = std::min<uint32_t>({want, (uint32_t)(kMaxRoundAttempts * kRoundLevels), cap[s] - used[s]});
-      wants.push_back(want); sum += want;
+      todo.push_back(s); wants.push_back(want); sum += want;
     }
-    const double boost = round == 0 || sum == 0 || generous ? 1.0 : std::min(4.0, std::max(1.0, 300000.0 / (double)sum));
+    const double boost = round == 0 || sum == 0 ? 1.0 : std::min(4.0, std::max(1.0, 300000.0 / (double)sum));
     // A list entry is at most kMaxRoundAttempts attempts of one spectrum (the selection kernel's table); a spectrum that gets
     // more this round -- the hard ones, which would otherwise need a round per 4096 attempts, each round as long as its slowest
     // attempt however few attempts it has -- has several entries with consecutive attempt ordinals.  The list holds every
@@ -1069,65 +978,18 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       }
     }
     uint32_t level_begin[kRoundLevels + 1];
-    att_n.clear();
     for (int c = 0; c < kRoundLevels; c++) {
       level_begin[c] = (uint32_t)list.size();
-      // (early stop: the work items of an entry are padded to whole chunks; att_n is what the entry really has)
-      for (const Entry& e : level[c]) { list.push_back(e.s); base.push_back(e.base); att_n.push_back(e.n); off.push_back(off.back() + (chunked ? (e.n + kChunk - 1u) & ~(kChunk - 1u) : e.n)); }
+      for (const Entry& e : level[c]) { list.push_back(e.s); base.push_back(e.base); off.push_back(off.back() + e.n); }
     }
     level_begin[kRoundLevels] = (uint32_t)list.size();
     if (list.empty()) break;
     const uint32_t n_list = (uint32_t)list.size(), total = off.back();
-    uint32_t n_chunks = 0;
-    if (chunked) {
-      // chunk ids (work item >> kChunkLog) in layer order, level by level; the level-0 entries come in the order of `todo`, and
-      // a spectrum's entry one level up is found through `next`
-      chunk_tab.clear(); next.assign(n_list, 0xFFFFFFFFu);
-      std::vector<uint32_t> alive, last_of(n, 0xFFFFFFFFu);
-      for (int c = 0; c < kRoundLevels; c++) {
-        alive.clear();
-        for (uint32_t i = level_begin[c]; i < level_begin[c + 1]; i++) {
-          alive.push_back(i);
-          if (last_of[list[i]] != 0xFFFFFFFFu) next[last_of[list[i]]] = i;
-          last_of[list[i]] = i;
-        }
-        for (uint32_t k = 0; !alive.empty(); k++) {
-          size_t keep = 0;
-          for (uint32_t i : alive) {
-            const uint32_t nc = (att_n[i] + kChunk - 1u) >> kChunkLog;
-            chunk_tab.push_back((off[i] >> kChunkLog) + k);
-            if (k + 1 < nc) alive[keep++] = i;
-          }
-          alive.resize(keep);
-        }
-      }
-      n_chunks = (uint32_t)chunk_tab.size();
-      // the margin of a spectrum doubles every time a stop came too early (k_round_need)
-      need.resize(level_begin[1]);
-      for (uint32_t i = 0; i < level_begin[1]; i++) need[i] = dupf[list[i]];
-    }
     W.att_rows.need((size_t)total * MD_DECOY_ROW + 64); W.att_len.need(total + 1); W.att_mask.need(total + 1); W.att_w.need(total + 1); W.att_hash.need(total + 1);
     AttemptOut O{W.att_rows.p, W.att_len.p, W.att_mask.p, W.att_w.p, W.att_hash.p};
     MD_CUDA(cudaMemcpyAsync(d_list.p, list.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n_list + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     MD_CUDA(cudaMemcpyAsync(d_base.p, base.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (chunked) {
-      W.t_chunks.need(n_chunks + 1); W.t_cstate.need((total >> kChunkLog) + 1); W.t_succ.need(n + 1); W.t_need.need(n + 1); W.t_attn.need(n_list + 1);
-      W.t_next.need(n_list + 1); W.t_run.need(n_list + 1);
-      MD_CUDA(cudaMemcpyAsync(W.t_chunks.p, chunk_tab.data(), n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-      W.t_mult.need(n_list + 1);
-      MD_CUDA(cudaMemcpyAsync(W.t_mult.p, need.data(), level_begin[1] * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-      MD_CUDA(cudaMemcpyAsync(W.t_attn.p, att_n.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-      MD_CUDA(cudaMemcpyAsync(W.t_next.p, next.data(), n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-      MD_CUDA(cudaMemsetAsync(W.t_cstate.p, 0, ((size_t)(total >> kChunkLog) + 1) * sizeof(uint32_t), ctx->stream));
-      if (round == 0) {
-        seen_bits = 1024; while (seen_bits < 32u * n_per && seen_bits < (1u << 20)) seen_bits <<= 1;
-        W.t_seen.need((size_t)n * (seen_bits >> 5) + 1);
-        MD_CUDA(cudaMemsetAsync(W.t_seen.p, 0, (size_t)n * (seen_bits >> 5) * sizeof(uint32_t), ctx->stream));
-        MD_CUDA(cudaMemsetAsync(W.t_succ.p, 0, ((size_t)n + 1) * sizeof(uint32_t), ctx->stream));
-      }
-      MD_LAUNCH(ctx, k_round_need, blocks(level_begin[1], 128), 128, 0, d_list.p, level_begin[1], W.t_mult.p, W.t_succ.p, W.dec_count.p, n_per, W.t_need.p);
-    }
     MD_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (mode == MD_DECOY_REFERENCE_RANDOM) {
       // narrow pass (32-bit position masks) over every attempt, then the wide pass over those that grew past 32 residues
@@ -1148,20 +1010,12 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       }
       RA.prec = W.prec.p; RA.list = d_list.p; RA.att_off = d_off.p; RA.att_base = d_base.p; RA.n_list = n_list; RA.total = total; RA.att_blk = W.t_blk.p;
       RA.seed = seed; RA.overflow = d_ovf.p;
-      RA.chunks = nullptr; RA.chunk_state = nullptr; RA.succ = nullptr; RA.need = nullptr; RA.att_n = nullptr; RA.seen = nullptr; RA.seen_bits = 0;
       if (ctx->mods.has_terminal) {
         RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = nullptr; RA.spill_n = nullptr;
         MD_LAUNCH(ctx, k_decoy_random_terminal, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * 8u), kThreads, 0, RA, ctx->mods, T, O, PV);
       } else if (!wide_only) {
         RA.queue = d_queue.p; RA.remap = nullptr; RA.remap_n = nullptr; RA.spill = W.t_spill.p; RA.spill_n = d_queue.p + 1;
-        if (chunked) {
-          RA.chunks = W.t_chunks.p; RA.chunk_state = W.t_cstate.p; RA.succ = W.t_succ.p; RA.need = W.t_need.p; RA.att_n = W.t_attn.p;
-          RA.seen = W.t_seen.p; RA.seen_bits = seen_bits;
-          RA.total = n_chunks << kChunkLog;
-        }
-        launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>((RA.total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, O, PV);
-        if (chunked) MD_LAUNCH(ctx, k_round_prefix, blocks(level_begin[1], 128), 128, 0, W.t_cstate.p, d_off.p, W.t_attn.p, W.t_next.p, level_begin[1], W.t_run.p);
-        RA.chunks = nullptr; RA.chunk_state = nullptr; RA.succ = nullptr; RA.need = nullptr; RA.att_n = nullptr; RA.total = total;
+        launch_random<uint32_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_narrow), RA, T, O, PV);
         RA.queue = d_queue.p + 2; RA.remap = W.t_spill.p; RA.remap_n = d_queue.p + 1; RA.spill = nullptr; RA.spill_n = nullptr;
         launch_random<uint64_t>(ctx, vmode, std::min<uint32_t>((total + kThreads - 1) / kThreads, (uint32_t)ctx->n_sm * (uint32_t)occ_wide), RA, T, O, PV);
       } else {
@@ -1185,32 +1039,18 @@ void decoys_generate_dev(md_ctx* ctx, uint32_t n, uint32_t n_per, int mode, uint
       if (smem <= 220 * 1024) {
         MD_CUDA(cudaFuncSetAttribute(k_decoy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MD_LAUNCH(ctx, k_decoy_select, le - lb, 256, smem, d_list.p + lb, d_off.p + lb, d_base.p + lb, n_per, slots, max_na, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p,
-                  W.dec_w.p, W.dec_hash.p, W.dec_attempt.p, W.dec_count.p, chunked ? W.t_run.p + lb : nullptr);
+                  W.dec_w.p, W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       } else {
         MD_LAUNCH(ctx, k_decoy_select_n2, le - lb, 256, 0, d_list.p + lb, d_off.p + lb, d_base.p + lb, n_per, O, (uint64_t)n * n_per, W.dec_rows.p, W.dec_len.p, W.dec_mask.p, W.dec_w.p,
-                  W.dec_hash.p, W.dec_attempt.p, W.dec_count.p, chunked ? W.t_run.p + lb : nullptr);
+                  W.dec_hash.p, W.dec_attempt.p, W.dec_count.p);
       }
     }
     MD_CUDA(cudaMemcpyAsync(count.data(), W.dec_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (chunked) { run.resize(n_list); MD_CUDA(cudaMemcpyAsync(run.data(), W.t_run.p, n_list * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
     MD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->mark("  select");
-    if (chunked) {
-      uint64_t ran = 0;
-      std::vector<uint8_t> stopped(n, 0);
-      for (uint32_t i = 0; i < n_list; i++) { used[list[i]] += run[i]; ran += run[i]; if (run[i] < att_n[i]) stopped[list[i]] = 1; }
-      // stopped, yet still short: its successes held more duplicates than the margin allowed for
-      for (uint32_t s : todo) if (stopped[s] && count[s] < n_per && dupf[s] < 64) dupf[s] *= 2;
-      ctx->acc_attempts += ran;
-    } else {
-      for (uint32_t i = 0; i < n_list; i++) used[list[i]] += off[i + 1] - off[i];
-      ctx->acc_attempts += total;
-    }
-    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms;
-      if (ctx->trace) {
-        uint64_t ran = 0; if (chunked) for (uint32_t v : run) ran += v; else ran = total;
-        fprintf(stderr, "[md_trace]   decoy round %d: entries=%u planned=%u attempted=%llu kernel=%.3f ms\n", round, n_list, total, (unsigned long long)ran, ms);
-      } }
+    for (uint32_t i = 0; i < n_list; i++) used[list[i]] += off[i + 1] - off[i];
+    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->acc_ms_kdecoy += ms; ctx->acc_attempts += total;
+      if (ctx->trace) fprintf(stderr, "[md_trace]   decoy round %d: spectra=%u attempts=%u kernel=%.3f ms\n", round, n_list, total, ms); }
   }
   const int ovf = d2h_scalar(ctx, d_ovf.p);
   MD_REQUIRE(ovf != 3, MD_ERR_DEVICE, "decoy generation: internal error (substitution filter disagrees with the mass search)");
