@@ -13,6 +13,11 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 gpu, cpu = maxdecoy.Engine(), oracle_engine(8)
 extra = [Modification("x:21", "Phospho", "A", False, "S", 79.966331), Modification("x:7", "Deamid", "A", False, "N", 0.984016),
          Modification("x:9", "FixK", "A", True, "K", 8.014199)]
+# terminal (N / C) modifications, drawn from their own stream so that the other configurations stay what they were
+terminal = [Modification("t:1", "Acetyl", "N", True, "M", 42.010565), Modification("t:2", "PyroGlu", "N", False, "Q", -17.026549),
+            Modification("t:3", "LabelK", "C", True, "K", 8.014199), Modification("t:4", "MethylR", "C", False, "R", 14.01565),
+            Modification("t:5", "CarbS", "N", False, "S", 43.005814)]
+trng = np.random.default_rng((int(sys.argv[2]) if len(sys.argv) > 2 else 2026) + 1)
 bad = 0
 for r in range(rounds):
     n_prot = int(rng.integers(50, 500)); n_spec = int(rng.integers(1, 70)); mc = int(rng.integers(0, 3))
@@ -20,6 +25,9 @@ for r in range(rounds):
     nvar = int(rng.integers(0, 4)); nd = int(rng.choice([0, 1, 7, 64, 300])); mode = int(rng.choice([0, 0, 0, 2]))
     topk = int(rng.choice([1, 5, 8, 20])); ppm = int(rng.choice([5, 10, 50])); absw = int(rng.choice([0, 0, 0, 3_000_000, 40_000_000]))
     expanded = rng.random() < 0.3
+    term = [m for m in terminal if trng.random() < 0.35] if trng.random() < 0.35 else []
+    if term:    # (the expanded mode is defined for position-A modifications only; decoy modes here: 0 reference-random, 2 permuted targets)
+        mods = mods + term; expanded = False
     prots = synth.synthetic_proteins(n_prot, seed=int(rng.integers(1 << 30)))
     sp, _ = synth.synthetic_spectra(prots, n_spec, mc, mods=tuple(m for m in mods if m.amino_acid in "CM"), seed=int(rng.integers(1 << 30)))
     for e in (gpu, cpu):
@@ -48,8 +56,8 @@ for r in range(rounds):
             w = np.nonzero(scg != scc)[0]
             spec = np.searchsorted(og, w, side="right") - 1
             print("   first differing candidates:", w[:8], "spectra:", spec[:8], "of n_targets", pg["n_targets"][spec[:8], 0], "gpu", scg[w[:4]], "cpu", scc[w[:4]])
-    print("round %2d prot=%d spec=%d mc=%d mods=%d nvar=%d nd=%d mode=%d k=%d ppm=%d abs=%d exp=%d store=%d pairs=%d -> %s"
-          % (r, n_prot, n_spec, mc, len(mods), nvar, nd, mode, topk, ppm, absw, expanded, len(store), len(scg), "ok" if ok else "MISMATCH"), flush=True)
+    print("round %2d prot=%d spec=%d mc=%d mods=%d (terminal %d) nvar=%d nd=%d mode=%d k=%d ppm=%d abs=%d exp=%d store=%d pairs=%d -> %s"
+          % (r, n_prot, n_spec, mc, len(mods), len(term), nvar, nd, mode, topk, ppm, absw, expanded, len(store), len(scg), "ok" if ok else "MISMATCH"), flush=True)
     bad += not ok
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
