@@ -91,3 +91,32 @@ def test_digest_and_identification_end_to_end(tmp_path):
     subprocess.check_call(_native_host() + ["digest", "-i", str(tmp_path / "db.fasta"), "-c", "2", "-l", "5", "-h", "50", "-o", str(tmp_path / "dig_native")])
     assert (tmp_path / "dig_native" / "peptides.csv").read_text() == (tmp_path / "dig" / "peptides.csv").read_text()
     assert (tmp_path / "dig_native" / "peptides_proteins.csv").read_text() == (tmp_path / "dig" / "peptides_proteins.csv").read_text()
+
+
+@pytest.mark.gpu
+def test_identification_with_terminal_modifications_both_hosts(tmp_path):
+    """Terminal (N / C) modifications through both command lines: same PSM rows, same per-spectrum FASTA (incl. the ModRes
+    summary with the terminus slots, modified_peptide.rs:606-659) and Comet parameters."""
+    from maxdecoy import Modification
+    prots = list(wl.proteins(150))
+    mods = [synth.CAM, synth.OXM, Modification("unimod:1", "Acetyl", "N", True, "M", 42.010565),
+            Modification("unimod:28", "Gln->pyro-Glu", "N", False, "Q", -17.026549), Modification("x:259", "Label", "C", True, "K", 8.014199)]
+    (tmp_path / "db.fasta").write_text(synth.fasta_text(prots))
+    (tmp_path / "mods.csv").write_text(synth.mods_csv_text(mods))
+    sp, _ = wl.spectra(150, 12, 2)
+    (tmp_path / "run.mgf").write_text(synth.mgf_text(sp))
+    common = ["identification", "-m", str(tmp_path / "mods.csv"), "-s", str(tmp_path / "run.mgf"), "--fasta", str(tmp_path / "db.fasta"),
+              "-n", "2", "-d", "30", "-l", "2000", "-u", "2000", "--seed", "3"]
+    subprocess.check_call(CLI + common + ["-o", str(tmp_path / "out")])
+    subprocess.check_call(_native_host() + common + ["-o", str(tmp_path / "out_native")])
+    rows = (tmp_path / "out" / "psms.csv").read_text().splitlines()
+    rows_native = (tmp_path / "out_native" / "psms.csv").read_text().splitlines()
+    assert len(rows) > 12 and [r.split(",")[:10] for r in rows_native] == [r.split(",")[:10] for r in rows]
+    summaries = set()
+    for name in ("1.fasta", "5.fasta", "12.fasta"):
+        text = (tmp_path / "out" / name).read_text()
+        assert (tmp_path / "out_native" / name).read_text() == text, name
+        summaries |= {ln.split("ModRes=")[1] for ln in text.splitlines() if "ModRes=" in ln}
+    assert any("x:259|Label" in s for s in summaries)          # a C-terminal K somewhere among targets / decoys
+    a = (tmp_path / "out_native" / "1.comet.params").read_text().replace("out_native", "out")
+    assert a == (tmp_path / "out" / "1.comet.params").read_text()
