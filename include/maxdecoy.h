@@ -85,8 +85,8 @@ typedef struct md_modification {
   char name[40];
   uint8_t position;    /* 'A' anywhere, 'N' / 'C' terminus (modification.rs:24-33): a terminal modification sits on the first / last residue
                         * only, and only when that residue is `amino_acid` (add_modification_at, modified_peptide.rs:421-447;
-                        * set_variable_modification_at, :339-367).  MD_DECOY_EXHAUSTIVE and MD_VARMOD_EXPANDED return
-                        * MD_ERR_UNSUPPORTED with terminal modifications. */
+                        * set_variable_modification_at, :339-367).  MD_DECOY_EXHAUSTIVE returns MD_ERR_UNSUPPORTED
+                        * with terminal modifications (compositions: the weight would depend on the order). */
   uint8_t is_fix;      /* != 0 -> fixed */
   uint8_t amino_acid;  /* one letter code, upper-cased */
   uint8_t _pad[5];

@@ -217,6 +217,7 @@ constexpr int kMaxVarLetters = 6, kMaxVarCombos = 96;
 struct VarCombos {
   int n_letters, n_combos;
   uint8_t code[kMaxVarLetters];              // residue codes of the variable-modifiable letters, ascending
+  uint8_t pos[kMaxVarLetters];               // where the letter's variable modification can sit (MD_POS_A / _N / _C)
   int64_t delta[kMaxVarLetters];
   uint8_t k[kMaxVarCombos][kMaxVarLetters];  // count vectors, sum <= nvar
   int64_t shift[kMaxVarCombos];              // sum k_a * delta_a
@@ -257,7 +258,7 @@ __global__ void k_expand_count(const uint64_t* __restrict__ flat_off, const uint
   uint64_t total = 1;
   for (int a = 0; a < V.n_letters; a++) {
     uint32_t c = 0;
-    for (uint32_t i = 0; i < L; i++) c += r[i] == V.code[a];
+    for (uint32_t i = 0; i < L; i++) c += r[i] == V.code[a] && md_pos_at(V.pos[a], i, L);
     total *= binom_capped(c, V.k[q][a]);
     if (total > 0xFFFFFull) { *overflow = 1; total = 0; break; }   // more than 2^20 placements of one peptide
   }
@@ -286,7 +287,7 @@ __global__ void k_expand_scatter(const uint64_t* __restrict__ flat_off, const ui
   uint32_t dcount[kMaxVarLetters];
   for (int a = 0; a < V.n_letters; a++) {
     uint64_t m = 0;
-    for (uint32_t i = 0; i < L; i++) if (r[i] == V.code[a]) m |= 1ULL << i;
+    for (uint32_t i = 0; i < L; i++) if (r[i] == V.code[a] && md_pos_at(V.pos[a], i, L)) m |= 1ULL << i;
     allpos[a] = m; dcount[a] = (uint32_t)__popcll(m);
     const uint32_t k = V.k[q][a];
     first[a] = k == 0 ? 0ULL : (((1ULL << dcount[a]) - 1) ^ ((1ULL << (dcount[a] - k)) - 1));   // 2^d - 2^(d-k)
@@ -365,7 +366,6 @@ static void index_build_for(md_ctx* ctx, PeptideStore& P, MassIndex& X) {
 void index_build_run(md_ctx* ctx) {
   MD_REQUIRE(ctx->peps.ready, MD_ERR_STATE, "md_index_build: md_digest first");
   MD_REQUIRE(ctx->mods_set, MD_ERR_STATE, "md_index_build: md_set_modifications first");
-  MD_REQUIRE(!(ctx->var_mode == MD_VARMOD_EXPANDED && ctx->mods.has_terminal), MD_ERR_UNSUPPORTED, "expanded variable-modification mode is defined for position-A modifications only");
   index_build_for(ctx, ctx->peps, ctx->index);
   index_build_store(ctx);
 }
@@ -428,9 +428,9 @@ static uint64_t candidates_expanded_dev(md_ctx* ctx, uint32_t n) {
   memset(&V, 0, sizeof(V));
   for (int ch = 'A'; ch <= 'Z'; ch++) {
     const uint32_t code = md_code_of((uint8_t)ch);
-    if (!M.has_var[code] || M.has_fix[code]) continue;
+    if (!M.has_var[code] || (M.has_fix[code] && M.fix_pos[code] == M.var_pos[code])) continue;   // (its slot holds the fixed modification)
     MD_REQUIRE(V.n_letters < kMaxVarLetters, MD_ERR_UNSUPPORTED, "expanded variable-modification mode: more than 6 variable letters");
-    V.code[V.n_letters] = (uint8_t)code; V.delta[V.n_letters] = M.var[code]; V.n_letters++;
+    V.code[V.n_letters] = (uint8_t)code; V.pos[V.n_letters] = M.var_pos[code]; V.delta[V.n_letters] = M.var[code]; V.n_letters++;
   }
   {  // count vectors in ascending mixed-radix order, last letter fastest
     std::vector<uint8_t> k(kMaxVarLetters, 0);

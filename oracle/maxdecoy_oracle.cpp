@@ -334,7 +334,7 @@ void candidates_expanded(const md_ctx* ctx, const md_precursor& pr, std::vector<
   std::vector<int> letters;                                // variable-modifiable letters by character
   {
     std::vector<uint8_t> chars;
-    for (int a = 0; a < MD_ALPHABET_SIZE; a++) if (M.has_var[a] && !M.has_fix[a]) chars.push_back((uint8_t)kAlphabet[a]);
+    for (int a = 0; a < MD_ALPHABET_SIZE; a++) if (M.has_var[a] && !(M.has_fix[a] && M.fix_pos[a] == M.var_pos[a])) chars.push_back((uint8_t)kAlphabet[a]);   // (unless its slot holds the fixed modification)
     std::sort(chars.begin(), chars.end());
     for (uint8_t c : chars) letters.push_back(alpha_index(c));
   }
@@ -352,7 +352,7 @@ void candidates_expanded(const md_ctx* ctx, const md_precursor& pr, std::vector<
         std::vector<std::vector<uint32_t>> pos(nl);
         bool ok = true;
         for (size_t a = 0; a < nl; a++) {
-          for (uint32_t i = 0; i < q.size(); i++) if (q[i] == kAlphabet[letters[a]]) pos[a].push_back(i);
+          for (uint32_t i = 0; i < q.size(); i++) if (q[i] == kAlphabet[letters[a]] && ModSet::at(M.var_pos[letters[a]], i, (uint32_t)q.size())) pos[a].push_back(i);   // where the modification's slot exists
           if (pos[a].size() < k[a]) ok = false;
         }
         if (!ok) continue;
@@ -941,7 +941,6 @@ int md_index_build(md_ctx* ctx) {
   if (!ctx->peps.ready) return fail(ctx, MD_ERR_STATE, "md_index_build: md_digest first");
   if (!ctx->mods.set) return fail(ctx, MD_ERR_STATE, "md_index_build: md_set_modifications first");
   const Peptides& P = ctx->peps; const ModSet& M = ctx->mods;
-  if (ctx->var_mode == MD_VARMOD_EXPANDED && M.has_terminal) return fail(ctx, MD_ERR_UNSUPPORTED, "expanded variable-modification mode is defined for position-A modifications only");
   size_t n = P.seq.size();
   std::vector<std::pair<int64_t, uint32_t>> kv(n);
   for (size_t i = 0; i < n; i++) {
@@ -957,9 +956,9 @@ int md_index_build(md_ctx* ctx) {
     ctx->fixed.resize(n);
     for (size_t i = 0; i < n; i++) {
       const uint32_t p = ctx->index.pep[i];
-      int64_t w = P.weight[p];
-      for (int a = 0; a < MD_ALPHABET_SIZE; a++) if (M.has_fix[a]) w += (int64_t)P.counts[(size_t)p * MD_ALPHABET_SIZE + a] * M.fix[a];
-      ctx->fixed[i] = {w, (uint32_t)i};
+      ModState st;
+      from_string(M, (const uint8_t*)P.seq[p].data(), (uint32_t)P.seq[p].size(), &st);   // weight with the fixed modifications where their positions allow
+      ctx->fixed[i] = {st.w, (uint32_t)i};
     }
     std::sort(ctx->fixed.begin(), ctx->fixed.end());
   }

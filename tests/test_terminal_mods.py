@@ -206,17 +206,63 @@ def test_terminal_scores_and_decoys(cpu, mods, nvar):
     assert total_dec > 0
 
 
+def _expanded_bruteforce(pm, seqs, lo, hi):
+    """Every peptide x every subset (<= nvar) of the positions that can take their letter's variable modification, slot by slot."""
+    import itertools
+    want = set()
+    span = pm.nvar * max([abs(v) for v in pm.var.values()] + [0])
+    for p, q in enumerate(seqs):
+        base = pyref.SlotPeptide(pm, q)
+        if base.w - span > hi or base.w + span < lo:
+            continue
+        elig = []
+        for j, c in enumerate(q):
+            if c in pm.var:
+                t = pyref.SlotPeptide(pm, q)
+                if t.set_variable(j):
+                    elig.append(j)
+        for n in range(0, pm.nvar + 1):
+            for sub in itertools.combinations(elig, n):
+                w = base.w + sum(pm.var[q[j]] for j in sub)
+                if lo <= w <= hi:
+                    want.add((p, sum(1 << j for j in sub), w))
+    return want
+
+
+@pytest.mark.parametrize("mods,nvar", MOD_SETS[1:], ids=IDS[1:])
+def test_terminal_expanded_mode_equals_bruteforce(cpu, mods, nvar):
+    """MD_VARMOD_EXPANDED with terminal modifications: every placement of <= nvar variable modifications on the positions
+    where their slot exists and is free, against the brute force over all peptides and subsets."""
+    _setup(cpu, 100, mods, nvar)
+    peptides = _table(cpu)
+    seqs = [p[0] for p in peptides]
+    pm = pyref.Mods(mods, nvar)
+    pre = _precursors(pm, peptides, seed=21, n=16, narrow=10)
+    pre = [(P, lo, hi, z, sid) if hi - lo < 1_000_000 else (P, P - 1_500_000, P + 1_500_000, z, sid) for (P, lo, hi, z, sid) in pre]
+    cpu.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
+    try:
+        cpu.index_build()
+        exp = cpu.candidates(pre)
+        n_var = 0
+        for s, (P, lo, hi, z, sid) in enumerate(pre):
+            a, b = int(exp["off"][s]), int(exp["off"][s + 1])
+            got = [(int(exp["peptide_id"][i]) - 1, int(exp["var_mask"][i]), int(exp["mod_weight"][i])) for i in range(a, b)]
+            assert len(set(got)) == len(got)
+            assert set(got) == _expanded_bruteforce(pm, seqs, lo, hi), s
+            n_var += sum(1 for g in got if g[1])
+        assert int(exp["off"][-1]) > 0
+        if mods != MOD_SETS[4][0]:
+            assert n_var > 0
+    finally:
+        cpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+        cpu.index_build()
+
+
 def test_terminal_unsupported_modes(cpu):
     _setup(cpu, 40, (K_CTERM_FIX,), 0)
     pre = [(900_400_000, 900_300_000, 900_500_000, 2, 0)]
     with pytest.raises(maxdecoy.MaxDecoyError):
         cpu.generate_decoys(pre, 5, maxdecoy.DECOY_EXHAUSTIVE, seed=0)
-    cpu.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
-    try:
-        with pytest.raises(maxdecoy.MaxDecoyError):
-            cpu.index_build()
-    finally:
-        cpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
 
 
 # ------------------------------------------------------------------------------------------------ GPU: CUDA vs oracle
@@ -271,14 +317,34 @@ def test_terminal_gpu_bit_exact(gpu, cpu, mods, nvar):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mods,nvar", MOD_SETS[1:], ids=IDS[1:])
+def test_terminal_expanded_gpu_bit_exact(gpu, cpu, mods, nvar):
+    for e in (gpu, cpu):
+        e.digest(list(wl.proteins(300)), 2, 5, 50)
+        e.set_modifications(list(mods), nvar)
+        e.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
+        e.index_build()
+    try:
+        peptides = _table(cpu)
+        pm = pyref.Mods(mods, nvar)
+        pre = _precursors(pm, peptides, seed=4, n=48, narrow=24)
+        _equal(gpu.candidates(pre), cpu.candidates(pre))
+        sp = _spectra_for(cpu, peptides, mods, nvar, 32, seed=9)
+        prm = SearchParams(10, 10, n_decoys=20, seed=5, top_k=5, abs_lower_uda=1_500_000, abs_upper_uda=1_500_000)
+        rg = gpu.identify(sp, prm, want_all_scores=True)
+        rc = cpu.identify(sp, prm, want_all_scores=True)
+        assert np.array_equal(rg[3], rc[3]) and np.array_equal(rg[2], rc[2])
+        for f in ("rank", "is_decoy", "candidate", "var_mask", "mod_weight", "raw_score", "n_targets", "n_decoys"):
+            assert np.array_equal(rg[0][f], rc[0][f]), f
+        assert int(rc[0]["n_targets"].sum()) > 0
+    finally:
+        for e in (gpu, cpu):
+            e.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+
+
+@pytest.mark.gpu
 def test_terminal_gpu_unsupported_modes(gpu):
     _setup(gpu, 40, (K_CTERM_FIX,), 0)
     pre = [(900_400_000, 900_300_000, 900_500_000, 2, 0)]
     with pytest.raises(maxdecoy.MaxDecoyError):
         gpu.generate_decoys(pre, 5, maxdecoy.DECOY_EXHAUSTIVE, seed=0)
-    gpu.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
-    try:
-        with pytest.raises(maxdecoy.MaxDecoyError):
-            gpu.index_build()
-    finally:
-        gpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)

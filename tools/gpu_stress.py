@@ -26,8 +26,7 @@ for r in range(rounds):
     topk = int(rng.choice([1, 5, 8, 20])); ppm = int(rng.choice([5, 10, 50])); absw = int(rng.choice([0, 0, 0, 3_000_000, 40_000_000]))
     expanded = rng.random() < 0.3
     term = [m for m in terminal if trng.random() < 0.35] if trng.random() < 0.35 else []
-    if term:    # (the expanded mode is defined for position-A modifications only; decoy modes here: 0 reference-random, 2 permuted targets)
-        mods = mods + term; expanded = False
+    mods = mods + term    # (decoy modes here: 0 reference-random, 2 permuted targets; exhaustive decoys are not defined with terminal modifications)
     prots = synth.synthetic_proteins(n_prot, seed=int(rng.integers(1 << 30)))
     sp, _ = synth.synthetic_spectra(prots, n_spec, mc, mods=tuple(m for m in mods if m.amino_acid in "CM"), seed=int(rng.integers(1 << 30)))
     for e in (gpu, cpu):
