@@ -185,28 +185,26 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
   const uint32_t cnt = MO::popc(allpos);
   const uint32_t nmax = nvar < cnt ? nvar : cnt;
   const int32_t base = d - (int32_t)MO::popc(mask) * delta;
-  // quick reject (nearly always: the window is a few hundredths of a Da wide, delta is many Da): base + n * delta, n = 1..nmax,
-  // lies between its first and its last value, and unless the window meets that range only the failure's side effect is left
-  {
-    const int32_t e1 = base + delta, e2 = base + (int32_t)nmax * delta;
-    const int32_t lo_end = min(e1, e2), hi_end = max(e1, e2);
-    const bool maybe = hi_end >= dlo && (lo_end < dlo || (uint32_t)(lo_end - dlo) <= span);
-    if (!maybe) {
-      MaskT last = allpos;
-      for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;
-      d = e2; mask = last;
-      return false;
-    }
-  }
-  MaskT first = 0, rest = allpos;
+  // The subset sizes are walked with nothing but the residual: base + n * delta, n = 1..nmax, first one inside the window.
+  // Every lane that holds the letter runs these few instructions together.  (A "cannot hit" test in front of a loop that
+  // also built the subsets was slower: after a failure the reference leaves the nmax modifications applied, the repair
+  // loop then steers THAT weight towards the precursor, so base sits nmax * delta away from the window and the test
+  // passes for most of the lanes that get here -- they then ran the loop two or three at a time.)
+  uint32_t nhit = 0;
+  int32_t dn = base;
   for (uint32_t n = 1; n <= nmax; n++) {
-    first |= rest & ((MaskT)0 - rest); rest &= rest - 1;
-    const int32_t dn = base + (int32_t)n * delta;
-    if ((uint32_t)dn - (uint32_t)dlo <= span) { d = dn; mask = first; return true; }
+    dn += delta;
+    if (nhit == 0u && (uint32_t)dn - (uint32_t)dlo <= span) nhit = n;
   }
-  MaskT last = allpos;
-  for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;   // the nmax last positions
-  d = base + (int32_t)nmax * delta; mask = last;
+  if (nhit) {                                 // the first nhit positions (NChooseK order: the first subset of that size)
+    MaskT first = 0, rest = allpos;
+    for (uint32_t n = 0; n < nhit; n++) { first |= rest & ((MaskT)0 - rest); rest &= rest - 1; }
+    d = base + (int32_t)nhit * delta; mask = first;
+    return true;
+  }
+  MaskT last = allpos;                        // on failure the last subset tried stays applied: the nmax last positions
+  for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;
+  d = dn; mask = last;
   return false;
 }
 
