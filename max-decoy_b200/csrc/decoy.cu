@@ -192,9 +192,19 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
   // passes for most of the lanes that get here -- they then ran the loop two or three at a time.)
   uint32_t nhit = 0;
   int32_t dn = base;
-  for (uint32_t n = 1; n <= nmax; n++) {
-    dn += delta;
-    if (nhit == 0u && (uint32_t)dn - (uint32_t)dlo <= span) nhit = n;
+  if (nvar <= 4u) {      // (the usual -n: four predicated steps, no loop whose trip count differs from lane to lane)
+#pragma unroll
+    for (uint32_t n = 1; n <= 4u; n++) {
+      dn += delta;
+      if (n <= nmax && nhit == 0u && (uint32_t)dn - (uint32_t)dlo <= span) nhit = n;
+    }
+    dn = base + (int32_t)nmax * delta;
+  } else {
+#pragma unroll 1
+    for (uint32_t n = 1; n <= nmax; n++) {
+      dn += delta;
+      if (nhit == 0u && (uint32_t)dn - (uint32_t)dlo <= span) nhit = n;
+    }
   }
   if (nhit) {                                 // the first nhit positions (NChooseK order: the first subset of that size)
     MaskT first = 0, rest = allpos;
@@ -203,6 +213,7 @@ __device__ __forceinline__ bool try_variable_simple_d(uint32_t nvar, int32_t del
     return true;
   }
   MaskT last = allpos;                        // on failure the last subset tried stays applied: the nmax last positions
+#pragma unroll 1
   for (uint32_t k = cnt; k > nmax; k--) last &= last - 1;
   d = dn; mask = last;
   return false;
