@@ -141,6 +141,51 @@ def test_terminal_candidates_equal_literal_slots(cpu, mods, nvar):
         assert n_var > 0
 
 
+def test_terminal_random_modification_sets(cpu):
+    """Random modification sets (letters, positions A / N / C, fixed / variable, signs) on two letters: the oracle's
+    candidates against the literal fan-out + slot-by-slot filter, in reference mode; and the expanded mode against the
+    brute force over all placements."""
+    rng = np.random.default_rng(99)
+    letters = "KRMQSCNDE"
+    n_found = n_exp = 0
+    for trial in range(24):
+        two = rng.choice(len(letters), size=2, replace=False)
+        mods = []
+        for li in two:
+            for is_fix in (True, False):
+                if rng.random() < 0.65:
+                    delta = float(rng.choice([42.010565, 15.994915, 8.014199, -17.026549, 14.01565, 79.966331]))
+                    mods.append(Modification("r:%d%d" % (li, is_fix), "m%d%d" % (li, is_fix), str(rng.choice(["A", "N", "C"])), is_fix, letters[li], delta))
+        if not mods:
+            continue
+        nvar = int(rng.integers(0, 4))
+        _setup(cpu, 25, mods, nvar)
+        peptides = _table(cpu)
+        pm = pyref.Mods(mods, nvar)
+        pre = _precursors(pm, peptides, seed=100 + trial, n=6, narrow=3)
+        got = cpu.candidates(pre)
+        for s, (P, lo, hi, z, sid) in enumerate(pre):
+            want = pyref.candidates_sql(pm, peptides, P, lo, hi)
+            a, b = int(got["off"][s]), int(got["off"][s + 1])
+            have = {int(got["peptide_id"][i]) - 1: (int(got["mod_weight"][i]), int(got["var_mask"][i])) for i in range(a, b)}
+            assert have == want, (trial, s, [(m.amino_acid, m.position, m.is_fix) for m in mods])
+            n_found += len(want)
+        if nvar and pm.var:
+            cpu.set_variable_mode(maxdecoy.VARMOD_EXPANDED)
+            try:
+                cpu.index_build()
+                exp = cpu.candidates(pre[:3])
+                seqs = [p[0] for p in peptides]
+                for s, (P, lo, hi, z, sid) in enumerate(pre[:3]):
+                    a, b = int(exp["off"][s]), int(exp["off"][s + 1])
+                    got_e = {(int(exp["peptide_id"][i]) - 1, int(exp["var_mask"][i]), int(exp["mod_weight"][i])) for i in range(a, b)}
+                    assert got_e == _expanded_bruteforce(pm, seqs, lo, hi), (trial, s)
+                    n_exp += len(got_e)
+            finally:
+                cpu.set_variable_mode(maxdecoy.VARMOD_REFERENCE)
+    assert n_found > 20 and n_exp > 20
+
+
 def test_terminal_weight_examples(cpu):
     """Hand-checked weights: the terminal delta counts once, at its end, whatever the letter count."""
     pm = pyref.Mods((K_CTERM_FIX, M_NTERM_FIX), 0)
